@@ -1,0 +1,19 @@
+"""CPU oracle for the PQN hot path — TEST INFRASTRUCTURE ONLY.
+
+Nothing under ``oracle/`` is product code.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it, and only as the checker (or as the timed CPU
+baseline), never as the thing shipped.  ``purejaxql_b200`` must not import it.
+
+PARITY UNPINNED: the reference (mttga/purejaxql @47af6d7) has no tests, golden
+vectors or fixtures, and its environment / PRNG arithmetic lives in third-party
+packages that are absent from ``/root/reference`` and not installable here
+(``gymnax==0.0.6``, ``jax>=0.4.16,<=0.4.38``, ``flax``, ``optax``; see
+``pyproject.toml:27-31,51`` of the reference).  The modules here restate the
+*published* algorithms of those pinned versions and are anchored on
+
+* the Random123 Threefry-2x32-20 known-answer vectors (public KATs),
+* publicly documented jax.random outputs for ``PRNGKey(0)`` (see
+  ``tests/golden/README.md``),
+* the reference's own call sites (file:line cited per function).
+"""
