@@ -1,0 +1,181 @@
+/* libpqn_b200.so — C ABI of the B200-native PQN rollout-and-update hot path.
+ *
+ * The reference (mttga/purejaxql) has no FFI boundary of its own: its hot path
+ * is traced Python/JAX.  The entry points below are what a binding for that
+ * path would call; each cites the reference interface it replaces
+ * (paths relative to the reference repo).  INTEGRATION.md shows the
+ * reference-side ctypes stub.
+ *
+ * Conventions
+ *  - plain C, no torch types; every pointer is a DEVICE pointer unless the
+ *    name ends in _host; the caller owns every buffer; the library allocates
+ *    nothing.
+ *  - every call enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *    returns immediately: 0 = PQN_OK, negative = PQN_E_*; pqn_last_error()
+ *    returns a thread-local message for the last failure.
+ *  - `rng_mode`: 0 = jax "original" threefry counter layout (default of the
+ *    reference's pinned jax<=0.4.38), 1 = jax_threefry_partitionable=True.
+ *  - env state is an opaque word-major SoA block: uint32 state[words][N]
+ *    (pqn_env_info gives `state_words`; layout documented in DESIGN.md and
+ *    mirrored by purejaxql_b200/envs.py for import/export to gymnax fields).
+ *  - batched over N = num_seeds * num_envs flat environments; seed s owns
+ *    envs [s*num_envs, (s+1)*num_envs).
+ */
+#ifndef PQN_B200_H
+#define PQN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PQN_OK 0
+#define PQN_E_INVALID (-1)   /* bad argument (unknown env id, null pointer, bad size) */
+#define PQN_E_CUDA (-2)      /* a CUDA runtime / launch error; see pqn_last_error() */
+#define PQN_E_UNSUPPORTED (-3)
+
+/* env ids (gymnax registry names in comments) */
+#define PQN_ENV_BREAKOUT 0        /* "Breakout-MinAtar" */
+#define PQN_ENV_ASTERIX 1         /* "Asterix-MinAtar" */
+#define PQN_ENV_SPACE_INVADERS 2  /* "SpaceInvaders-MinAtar" */
+#define PQN_ENV_FREEWAY 3         /* "Freeway-MinAtar" */
+#define PQN_ENV_SEAQUEST 4        /* "Seaquest-MinAtar" */
+#define PQN_ENV_CARTPOLE 16       /* "CartPole-v1" */
+#define PQN_ENV_ACROBOT 17        /* "Acrobot-v1" */
+
+typedef struct pqn_env_info_t {
+  int32_t state_words;      /* uint32 words per env in the SoA state block (incl. 5 LogWrapper words) */
+  int32_t obs_dim;          /* flattened observation length (400 for Breakout, 4 CartPole, 6 Acrobot) */
+  int32_t obs_shape[3];     /* (H, W, C) for MinAtar, (D, 1, 1) for classic control */
+  int32_t num_actions;      /* env.action_space(params).n  — pqn_minatar.py:151 */
+  int32_t max_steps;        /* env_params.max_steps_in_episode default — pqn_minatar.py:105 */
+  int32_t binary_obs;       /* 1: obs are {0,1}; the rollout buffer stores them bit-packed */
+  int32_t packed_obs_words; /* uint32 words per packed obs row (64-byte multiple), 0 if !binary_obs */
+} pqn_env_info_t;
+
+const char* pqn_last_error(void);
+int pqn_version(void);
+
+/* gymnax.make(name) metadata — pqn_minatar.py:103-105,151,157. */
+int pqn_env_info(int env_id, pqn_env_info_t* out_host);
+
+/* ---- jax.random plumbing on device ------------------------------------- */
+/* out[n][num][2] = jax.random.split(keys[n], num)   (pqn_minatar.py:108,112,183,459) */
+int pqn_rng_split(const uint32_t* keys, int64_t n, int32_t num, uint32_t* out, int rng_mode, void* stream);
+/* Threefry-2x32-20 block function on n (key, counter) pairs: KAT hook for tests. */
+int pqn_threefry2x32(const uint32_t* key_pairs, const uint32_t* ctr_pairs, uint32_t* out_pairs, int64_t n,
+                     void* stream);
+/* out[n][len] = jax.random.random_bits(keys[n], 32, (len,)) — sort keys of jax.random.permutation (:303) */
+int pqn_rng_bits(const uint32_t* keys, int64_t n, int64_t len, uint32_t* out, int rng_mode, void* stream);
+
+/* ---- the environment operator: vmapped LogWrapper(env).reset / .step ------
+ * replaces vmap_reset / vmap_step, pqn_minatar.py:107-112 (gymnax protocol:
+ * env.reset(key, params) -> (obs, state); env.step(key, state, action, params)
+ * -> (obs, state, reward, done, info)).  keys: uint32[N][2] (one per env, i.e.
+ * the caller already did jax.random.split(rng, n_envs)).  obs: float32[N][obs_dim].
+ * info outputs may be NULL.  max_steps <= 0 selects the env default. */
+int pqn_env_reset(int env_id, const uint32_t* keys, uint32_t* state, float* obs, int64_t N, int max_steps,
+                  int rng_mode, void* stream);
+int pqn_env_step(int env_id, const uint32_t* keys, uint32_t* state, const int32_t* action, float* obs,
+                 float* reward, uint8_t* done, float* info_discount, float* info_returned_episode_returns,
+                 int32_t* info_returned_episode_lengths, int32_t* info_timestep, int64_t N, int max_steps,
+                 int rng_mode, void* stream);
+/* current observation of `state` as packed bits (binary_obs envs): uint32[N][packed_obs_words] */
+int pqn_env_obs_packed(int env_id, const uint32_t* state, uint32_t* obs_packed, int64_t N, void* stream);
+/* current observation of `state` as float32[N][obs_dim] */
+int pqn_env_obs(int env_id, const uint32_t* state, float* obs, int64_t N, void* stream);
+
+/* ---- epsilon-greedy (eps_greedy_exploration, pqn_minatar.py:115-128,194-196) */
+int pqn_eps_greedy(const uint32_t* keys /*[N][2]*/, const float* q /*[N][A]*/, const float* eps /*[1] device*/,
+                   int32_t* action, int64_t N, int32_t A, int rng_mode, void* stream);
+
+/* ---- fused rollout step (_step_env body, pqn_minatar.py:181-210) -----------
+ * One launch = for every (seed s, env e): per-env keys from the step's
+ * (rng_a, rng_s) pair, argmax + eps-greedy on q, LogWrapper(env).step with
+ * auto-reset, and the stores of this step's transition row.
+ *   step_keys: uint32[S][2][2]   (rng_a, rng_s) of this step for each seed
+ *   q:         float32[S*E][A]   Q(last_obs) from the Q-network forward
+ *   eps:       float32[1]        device scalar (eps_scheduler(n_updates), :195)
+ *   obs_next:  packed uint32[S*E][packed_obs_words] (binary envs) or
+ *              float32[S*E][obs_dim] (classic control) — new_obs
+ *   action/reward/done/maxq: this step's rows ([S*E] each); reward is scaled
+ *              by rew_scale (:205); maxq = max_a q (next_q of the Q(lambda) scan)
+ *   info_sums: float64[S][5] running sums over the update of
+ *              (returned_episode_returns, returned_episode_lengths, timestep,
+ *               returned_episode, discount) — :338 takes their means.        */
+int pqn_rollout_act_step(int env_id, const uint32_t* step_keys, const float* q, const float* eps,
+                         uint32_t* state, void* obs_next, int32_t* action, float* reward, uint8_t* done,
+                         float* maxq, double* info_sums, int32_t S, int32_t E, int max_steps,
+                         float rew_scale, int rng_mode, void* stream);
+/* keys_out[T][S][2][2], rng_inout[S][2]: the scan carry chain
+ * rng, rng_a, rng_s = split(rng, 3) for T steps (pqn_minatar.py:183). */
+int pqn_rollout_keys(uint32_t* rng_inout, uint32_t* keys_out, int32_t S, int32_t T, int rng_mode, void* stream);
+
+/* ---- Q(lambda) targets (last_q bootstrap + reverse scan, pqn_minatar.py:227-260)
+ *   q_last: float32[N][A] = Q(next_obs[T-1]);  reward/maxq float32[T][N], done uint8[T][N]
+ *   targets: float32[T][N]                                                     */
+int pqn_qlambda(const float* reward, const uint8_t* done, const float* maxq, const float* q_last,
+                float* targets, int32_t T, int64_t N, int32_t A, float gamma, float lambda, void* stream);
+
+/* ---- Q-network (QNetwork/CNN pqn_minatar.py:24-69; MLP QNetwork pqn_gymnax.py:29-58)
+ * All network entry points are batched over S independent seeds: parameter
+ * blocks are float32[S][P] with the per-seed layout given by pqn_net_layout. */
+#define PQN_NET_MINATAR_CNN 0
+#define PQN_NET_MLP 1
+
+typedef struct pqn_net_desc_t {
+  int32_t kind;        /* PQN_NET_* */
+  int32_t in_c;        /* CNN: input channels C (obs 10x10xC)   | MLP: input dim D */
+  int32_t hidden;      /* CNN: 128 (fixed)                      | MLP: HIDDEN_SIZE */
+  int32_t layers;      /* CNN: ignored                          | MLP: NUM_LAYERS (1 or 2) */
+  int32_t num_actions; /* A */
+} pqn_net_desc_t;
+
+/* offsets (in floats) of each tensor inside one seed's parameter block; flax
+ * names: see SURVEY Appendix C.  Unused entries are -1. */
+typedef struct pqn_net_layout_t {
+  int64_t total;                 /* floats per seed */
+  int64_t bn_scale, bn_bias;     /* BatchNorm_0 (dummy input norm)      [in] */
+  int64_t conv_w, conv_b;        /* CNN_0/Conv_0 kernel [3,3,C,16] HWIO, bias [16] */
+  int64_t ln0_scale, ln0_bias;   /* CNN: CNN_0/LayerNorm_0 [16] | MLP: LayerNorm_0 [H] */
+  int64_t d0_w, d0_b;            /* CNN: CNN_0/Dense_0 [1024,128]/[128] | MLP: Dense_0 [D,H]/[H] */
+  int64_t ln1_scale, ln1_bias;   /* CNN: CNN_0/LayerNorm_1 [128] | MLP: LayerNorm_1 [H] (layers==2) */
+  int64_t d1_w, d1_b;            /* MLP only: Dense_1 [H,H]/[H] (layers==2) */
+  int64_t head_w, head_b;        /* final Dense [H,A]/[A] */
+} pqn_net_layout_t;
+
+int pqn_net_layout(const pqn_net_desc_t* desc_host, pqn_net_layout_t* out_host);
+/* bytes of scratch the forward/backward need for `rows` samples per seed */
+int64_t pqn_net_workspace_bytes(const pqn_net_desc_t* desc_host, int32_t S, int64_t rows);
+
+/* q[S][rows][A] = network.apply(params, obs, train=False) — pqn_minatar.py:184-191,227-234.
+ *  obs: packed uint32[S][rows_total][packed_words] (CNN) or float32[S][rows_total][D] (MLP);
+ *  gather (may be NULL): int32[S][rows] row indices into the seed's obs rows
+ *  (minibatch gather of preprocess_transition, :299-307); obs_rows_per_seed is
+ *  the stride of the obs buffer in rows. */
+int pqn_qnet_forward(const pqn_net_desc_t* desc_host, const float* params, const void* obs,
+                     const int32_t* gather, int64_t obs_rows_per_seed, float* q, int32_t S, int64_t rows,
+                     void* workspace, void* stream);
+
+/* One _learn_phase gradient (pqn_minatar.py:266-291): loss = 0.5*mean((Q(obs)[a]-target)^2),
+ * grads[S][P] (overwritten), loss_sum[S] += loss, qsa_sum[S] += mean(q_sa),
+ * bn_sums: float32[S][2*in] += per-feature (sum x, sum x^2) of the raw obs minibatch
+ * (dummy BatchNorm statistics, :65,293-296); may be NULL. */
+int pqn_qnet_loss_grad(const pqn_net_desc_t* desc_host, const float* params, const void* obs,
+                       const int32_t* gather, int64_t obs_rows_per_seed, const int32_t* action,
+                       const float* target, float* grads, float* loss_sum, float* qsa_sum, float* bn_sums,
+                       int32_t S, int64_t rows, void* workspace, void* stream);
+
+/* optax.chain(clip_by_global_norm(max_norm), radam(lr_t)) + apply_updates
+ * (pqn_minatar.py:159-162,292).  sched: float32[num_steps][4] per optimizer step
+ * (lr, 1-b1^t, 1-b2^t, rect (0 => un-rectified step)); step_counter: int32[1]
+ * device counter (grad_steps), incremented by the call. */
+int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu, const float* sched,
+                        int32_t* step_counter, float* gnorm_scratch /*[2][S]*/, int32_t S, int64_t P,
+                        float max_norm, float b1, float b2, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQN_B200_H */

@@ -1,0 +1,107 @@
+"""ctypes binding of libpqn_b200.so (the C ABI in include/pqn_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` /
+``python -m purejaxql_b200.build``.  Loading fails loudly when it is missing:
+there is no fallback implementation.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpqn_b200.so")
+
+
+class EnvInfo(Structure):
+    _fields_ = [("state_words", c_int32), ("obs_dim", c_int32), ("obs_shape", c_int32 * 3),
+                ("num_actions", c_int32), ("max_steps", c_int32), ("binary_obs", c_int32),
+                ("packed_obs_words", c_int32)]
+
+
+class NetDesc(Structure):
+    _fields_ = [("kind", c_int32), ("in_c", c_int32), ("hidden", c_int32), ("layers", c_int32),
+                ("num_actions", c_int32)]
+
+
+class NetLayout(Structure):
+    _fields_ = [(n, c_int64) for n in (
+        "total", "bn_scale", "bn_bias", "conv_w", "conv_b", "ln0_scale", "ln0_bias", "d0_w", "d0_b",
+        "ln1_scale", "ln1_bias", "d1_w", "d1_b", "head_w", "head_b")]
+
+
+class PqnError(RuntimeError):
+    pass
+
+
+_SIGS = {
+    "pqn_last_error": (c_char_p, []),
+    "pqn_version": (c_int, []),
+    "pqn_env_info": (c_int, [c_int, POINTER(EnvInfo)]),
+    "pqn_rng_split": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int, c_void_p]),
+    "pqn_threefry2x32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pqn_rng_bits": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "pqn_env_reset": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "pqn_env_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "pqn_env_obs_packed": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pqn_env_obs": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pqn_eps_greedy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int, c_void_p]),
+    "pqn_rollout_act_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int, c_float, c_int,
+                                     c_void_p]),
+    "pqn_rollout_keys": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int, c_void_p]),
+    "pqn_qlambda": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_float,
+                            c_float, c_void_p]),
+    "pqn_net_layout": (c_int, [POINTER(NetDesc), POINTER(NetLayout)]),
+    "pqn_net_workspace_bytes": (c_int64, [POINTER(NetDesc), c_int32, c_int64]),
+    "pqn_qnet_forward": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32,
+                                 c_int64, c_void_p, c_void_p]),
+    "pqn_qnet_loss_grad": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
+    "pqn_radam_clip_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                    c_int64, c_float, c_float, c_float, c_float, c_void_p]),
+}
+
+EXPORTS = tuple(_SIGS)
+_lib = None
+
+
+def lib():
+    """The loaded library (raises PqnError with build instructions if absent)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PqnError(
+                f"{LIB_PATH} is not built. Run `python -m purejaxql_b200.build` (needs nvcc). "
+                "purejaxql_b200 has no CPU fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)  # AttributeError here == header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().pqn_last_error().decode("utf-8", "replace")
+        raise PqnError(f"{what or 'libpqn_b200'} failed (rc={rc}): {msg}")
+
+
+def p(t):
+    """Device pointer of a torch tensor (or None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise PqnError("libpqn_b200 takes CUDA tensors only (no CPU fallback); got a CPU tensor")
+    if not t.is_contiguous():
+        raise PqnError("libpqn_b200 takes contiguous tensors")
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

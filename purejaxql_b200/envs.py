@@ -1,0 +1,197 @@
+"""Host-side mirror of the gymnax environment protocol over libpqn_b200's
+batched environment operator.
+
+Mirrors what the reference uses of gymnax (purejaxql/pqn_minatar.py:103-112):
+
+    env, env_params = make("Breakout-MinAtar")       # gymnax.make + LogWrapper
+    obs, state = env.reset(keys, env_params)          # keys: uint32[N,2] (already split)
+    obs, state, reward, done, info = env.step(keys, state, action, env_params)
+    env.action_space(env_params).n, env.observation_space(env_params).shape,
+    env_params.max_steps_in_episode
+
+The functional protocol is kept (state in, state out) but batched natively —
+there is no ``jax.vmap`` to wrap it with — and ``state`` is the library's
+word-major SoA block (``uint32[state_words, N]`` CUDA tensor).
+``state_to_fields`` / ``fields_to_state`` convert to and from gymnax's field
+names for interop and parity tests (pure tensor ops, usable on CPU tensors).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from types import SimpleNamespace
+
+import torch
+
+from . import _lib
+
+ENV_IDS = {
+    "Breakout-MinAtar": 0,
+    "Asterix-MinAtar": 1,
+    "SpaceInvaders-MinAtar": 2,
+    "Freeway-MinAtar": 3,
+    "Seaquest-MinAtar": 4,
+    "CartPole-v1": 16,
+    "Acrobot-v1": 17,
+}
+
+LOG_FIELDS = ("episode_returns", "episode_lengths", "returned_episode_returns",
+              "returned_episode_lengths", "timestep")
+
+
+@dataclass
+class EnvParams:
+    max_steps_in_episode: int
+
+
+def _u2f(t):
+    return t.contiguous().view(torch.float32)
+
+
+def _f2u(t):
+    return t.to(torch.float32).contiguous().view(torch.int32)
+
+
+# --------------------------------------------------------------------------- #
+# state <-> gymnax field conversion (int32 views of the uint32 words)
+# --------------------------------------------------------------------------- #
+def state_to_fields(env_name: str, state: torch.Tensor) -> dict:
+    """uint32/int32[state_words, N] -> dict of gymnax EnvState + LogEnvState fields."""
+    st = state.view(torch.int32) if state.dtype != torch.int32 else state
+    f = {}
+    if env_name == "Breakout-MinAtar":
+        w = st[0]
+        f["ball_y"] = w & 15
+        f["ball_x"] = (w >> 4) & 15
+        f["ball_dir"] = (w >> 8) & 3
+        f["pos"] = (w >> 10) & 15
+        f["last_y"] = (w >> 14) & 15
+        f["last_x"] = (w >> 18) & 15
+        f["strike"] = ((w >> 22) & 1).bool()
+        f["terminal"] = ((w >> 23) & 1).bool()
+        f["time"] = st[1]
+        n = st.shape[1]
+        p = torch.arange(100, device=st.device)
+        words = st[2:6].to(torch.int64) & 0xFFFFFFFF                       # [4, N]
+        bits = (words[p >> 5] >> (p & 31).unsqueeze(1)) & 1                # [100, N]
+        f["brick_map"] = bits.t().reshape(n, 10, 10).to(torch.float32)
+        core = 6
+    elif env_name == "CartPole-v1":
+        for j, k in enumerate(("x", "x_dot", "theta", "theta_dot")):
+            f[k] = _u2f(st[j])
+        f["time"] = st[4]
+        core = 5
+    elif env_name == "Acrobot-v1":
+        for j, k in enumerate(("joint_angle1", "joint_angle2", "velocity_1", "velocity_2")):
+            f[k] = _u2f(st[j])
+        f["time"] = st[4]
+        core = 5
+    else:
+        raise KeyError(env_name)
+    f["log_episode_returns"] = _u2f(st[core + 0])
+    f["log_episode_lengths"] = st[core + 1]
+    f["log_returned_episode_returns"] = _u2f(st[core + 2])
+    f["log_returned_episode_lengths"] = st[core + 3]
+    f["log_timestep"] = st[core + 4]
+    return f
+
+
+def fields_to_state(env_name: str, f: dict) -> torch.Tensor:
+    """Inverse of :func:`state_to_fields` -> int32[state_words, N]."""
+    i32 = lambda t: torch.as_tensor(t).to(torch.int32)
+    if env_name == "Breakout-MinAtar":
+        w = (i32(f["ball_y"]) | (i32(f["ball_x"]) << 4) | (i32(f["ball_dir"]) << 8) | (i32(f["pos"]) << 10)
+             | (i32(f["last_y"]) << 14) | (i32(f["last_x"]) << 18) | (i32(f["strike"]) << 22)
+             | (i32(f["terminal"]) << 23))
+        n = w.shape[0]
+        bm = (torch.as_tensor(f["brick_map"]).reshape(n, 100) != 0).to(torch.int64)
+        words = []
+        for k in range(4):
+            lo, hi = 32 * k, min(100, 32 * k + 32)
+            sh = torch.arange(hi - lo, device=bm.device)
+            v = (bm[:, lo:hi] << sh).sum(1)
+            v = torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32)
+            words.append(v)
+        core = [w, i32(f["time"])] + words
+    elif env_name == "CartPole-v1":
+        core = [_f2u(torch.as_tensor(f[k])) for k in ("x", "x_dot", "theta", "theta_dot")] + [i32(f["time"])]
+    elif env_name == "Acrobot-v1":
+        core = [_f2u(torch.as_tensor(f[k])) for k in
+                ("joint_angle1", "joint_angle2", "velocity_1", "velocity_2")] + [i32(f["time"])]
+    else:
+        raise KeyError(env_name)
+    log = [_f2u(torch.as_tensor(f["log_episode_returns"])), i32(f["log_episode_lengths"]),
+           _f2u(torch.as_tensor(f["log_returned_episode_returns"])), i32(f["log_returned_episode_lengths"]),
+           i32(f["log_timestep"])]
+    return torch.stack(core + log).contiguous()
+
+
+# --------------------------------------------------------------------------- #
+# the batched environment
+# --------------------------------------------------------------------------- #
+class BatchedEnv:
+    """``LogWrapper(gymnax.make(name)[0])`` (optionally with
+    ``FlattenObservationWrapper``), batched over the leading axis."""
+
+    def __init__(self, name: str, flatten_obs: bool = False, rng_mode: int = 0):
+        if name not in ENV_IDS:
+            raise KeyError(f"unknown env {name!r}; known: {sorted(ENV_IDS)}")
+        self.name = name
+        self.env_id = ENV_IDS[name]
+        info = _lib.EnvInfo()
+        _lib.check(_lib.lib().pqn_env_info(self.env_id, info), "pqn_env_info")
+        self.info = info
+        self.state_words = info.state_words
+        self.obs_dim = info.obs_dim
+        self.binary_obs = bool(info.binary_obs)
+        self.packed_obs_words = info.packed_obs_words
+        self.num_actions = info.num_actions
+        shape = tuple(info.obs_shape) if self.binary_obs else (info.obs_dim,)
+        self._obs_shape = (info.obs_dim,) if flatten_obs else shape
+        self.default_params = EnvParams(max_steps_in_episode=info.max_steps)
+        self.rng_mode = rng_mode
+
+    # gymnax spaces -------------------------------------------------------
+    def action_space(self, params=None):
+        return SimpleNamespace(n=self.num_actions)
+
+    def observation_space(self, params=None):
+        return SimpleNamespace(shape=self._obs_shape)
+
+    # protocol ------------------------------------------------------------
+    def reset(self, keys: torch.Tensor, params: EnvParams | None = None):
+        params = params or self.default_params
+        n = keys.shape[0]
+        state = torch.empty((self.state_words, n), dtype=torch.int32, device=keys.device)
+        obs = torch.empty((n,) + self._obs_shape, dtype=torch.float32, device=keys.device)
+        _lib.check(_lib.lib().pqn_env_reset(self.env_id, _lib.p(keys), _lib.p(state), _lib.p(obs), n,
+                                            params.max_steps_in_episode, self.rng_mode, _lib.stream_ptr()),
+                   "pqn_env_reset")
+        return obs, state
+
+    def step(self, keys: torch.Tensor, state: torch.Tensor, action: torch.Tensor,
+             params: EnvParams | None = None, inplace: bool = False):
+        params = params or self.default_params
+        n = keys.shape[0]
+        dev = keys.device
+        state = state if inplace else state.clone()
+        obs = torch.empty((n,) + self._obs_shape, dtype=torch.float32, device=dev)
+        reward = torch.empty(n, dtype=torch.float32, device=dev)
+        done = torch.empty(n, dtype=torch.uint8, device=dev)
+        disc = torch.empty(n, dtype=torch.float32, device=dev)
+        ret = torch.empty(n, dtype=torch.float32, device=dev)
+        ln = torch.empty(n, dtype=torch.int32, device=dev)
+        ts = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().pqn_env_step(
+            self.env_id, _lib.p(keys), _lib.p(state), _lib.p(action.to(torch.int32).contiguous()), _lib.p(obs),
+            _lib.p(reward), _lib.p(done), _lib.p(disc), _lib.p(ret), _lib.p(ln), _lib.p(ts), n,
+            params.max_steps_in_episode, self.rng_mode, _lib.stream_ptr()), "pqn_env_step")
+        done_b = done.bool()
+        info = {"discount": disc, "returned_episode_returns": ret, "returned_episode_lengths": ln,
+                "timestep": ts, "returned_episode": done_b}
+        return obs, state, reward, done_b, info
+
+
+def make(env_name: str, flatten_obs: bool = False, rng_mode: int = 0):
+    """``gymnax.make(env_name)`` -> (env, env_params); the LogWrapper is built in."""
+    env = BatchedEnv(env_name, flatten_obs=flatten_obs, rng_mode=rng_mode)
+    return env, env.default_params
