@@ -97,26 +97,34 @@ int pqn_eps_greedy(const uint32_t* keys /*[N][2]*/, const float* q /*[N][A]*/, c
  *   step_keys: uint32[S][2][2]   (rng_a, rng_s) of this step for each seed
  *   q:         float32[S*E][A]   Q(last_obs) from the Q-network forward
  *   eps:       float32[1]        device scalar (eps_scheduler(n_updates), :195)
- *   obs_next:  packed uint32[S*E][packed_obs_words] (binary envs) or
- *              float32[S*E][obs_dim] (classic control) — new_obs
- *   action/reward/done/maxq: this step's rows ([S*E] each); reward is scaled
+ *   obs_next:  row (s,e) of new_obs goes to row  s*obs_seed_stride + e  of
+ *              obs_next: packed uint32[packed_obs_words] rows (binary envs) or
+ *              float32[obs_dim] rows (classic control).  The rollout buffer is
+ *              [S][T+1][E] rows, so the caller passes the step's base pointer
+ *              and obs_seed_stride = (T+1)*E.
+ *   action/reward/done/maxq: element (s,e) goes to  s*tr_seed_stride + e
+ *              (buffers are [S][T][E]; tr_seed_stride = T*E); reward is scaled
  *              by rew_scale (:205); maxq = max_a q (next_q of the Q(lambda) scan)
  *   info_sums: float64[S][5] running sums over the update of
  *              (returned_episode_returns, returned_episode_lengths, timestep,
- *               returned_episode, discount) — :338 takes their means.        */
+ *               returned_episode, discount) — :338 takes their means.  With
+ *              info_done_only != 0 only steps with done contribute (the
+ *              nanmean-where-returned_episode of get_test_metrics, :403-412). */
 int pqn_rollout_act_step(int env_id, const uint32_t* step_keys, const float* q, const float* eps,
-                         uint32_t* state, void* obs_next, int32_t* action, float* reward, uint8_t* done,
-                         float* maxq, double* info_sums, int32_t S, int32_t E, int max_steps,
-                         float rew_scale, int rng_mode, void* stream);
+                         uint32_t* state, void* obs_next, int64_t obs_seed_stride, int32_t* action,
+                         float* reward, uint8_t* done, float* maxq, int64_t tr_seed_stride, double* info_sums,
+                         int info_done_only, int32_t S, int32_t E, int max_steps, float rew_scale, int rng_mode,
+                         void* stream);
 /* keys_out[T][S][2][2], rng_inout[S][2]: the scan carry chain
  * rng, rng_a, rng_s = split(rng, 3) for T steps (pqn_minatar.py:183). */
 int pqn_rollout_keys(uint32_t* rng_inout, uint32_t* keys_out, int32_t S, int32_t T, int rng_mode, void* stream);
 
 /* ---- Q(lambda) targets (last_q bootstrap + reverse scan, pqn_minatar.py:227-260)
- *   q_last: float32[N][A] = Q(next_obs[T-1]);  reward/maxq float32[T][N], done uint8[T][N]
- *   targets: float32[T][N]                                                     */
+ *   q_last: float32[S*E][A] = Q(next_obs[T-1]);  reward/maxq/targets float32[S][T][E],
+ *   done uint8[S][T][E]                                                        */
 int pqn_qlambda(const float* reward, const uint8_t* done, const float* maxq, const float* q_last,
-                float* targets, int32_t T, int64_t N, int32_t A, float gamma, float lambda, void* stream);
+                float* targets, int32_t T, int32_t S, int32_t E, int32_t A, float gamma, float lambda,
+                void* stream);
 
 /* ---- Q-network (QNetwork/CNN pqn_minatar.py:24-69; MLP QNetwork pqn_gymnax.py:29-58)
  * All network entry points are batched over S independent seeds: parameter
@@ -159,21 +167,29 @@ int pqn_qnet_forward(const pqn_net_desc_t* desc_host, const float* params, const
                      void* workspace, void* stream);
 
 /* One _learn_phase gradient (pqn_minatar.py:266-291): loss = 0.5*mean((Q(obs)[a]-target)^2),
+ * action/target: [S][tr_rows_per_seed] indexed through `gather` like obs;
  * grads[S][P] (overwritten), loss_sum[S] += loss, qsa_sum[S] += mean(q_sa),
  * bn_sums: float32[S][2*in] += per-feature (sum x, sum x^2) of the raw obs minibatch
  * (dummy BatchNorm statistics, :65,293-296); may be NULL. */
 int pqn_qnet_loss_grad(const pqn_net_desc_t* desc_host, const float* params, const void* obs,
                        const int32_t* gather, int64_t obs_rows_per_seed, const int32_t* action,
-                       const float* target, float* grads, float* loss_sum, float* qsa_sum, float* bn_sums,
-                       int32_t S, int64_t rows, void* workspace, void* stream);
+                       const float* target, int64_t tr_rows_per_seed, float* grads, float* loss_sum,
+                       float* qsa_sum, float* bn_sums, int32_t S, int64_t rows, void* workspace, void* stream);
 
 /* optax.chain(clip_by_global_norm(max_norm), radam(lr_t)) + apply_updates
  * (pqn_minatar.py:159-162,292).  sched: float32[num_steps][4] per optimizer step
  * (lr, 1-b1^t, 1-b2^t, rect (0 => un-rectified step)); step_counter: int32[1]
  * device counter (grad_steps), incremented by the call. */
 int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu, const float* sched,
-                        int32_t* step_counter, float* gnorm_scratch /*[2][S]*/, int32_t S, int64_t P,
+                        int32_t* step_counter, float* gnorm_scratch /*[S]*/, int32_t S, int64_t P,
                         float max_norm, float b1, float b2, float eps, void* stream);
+
+/* dummy input BatchNorm running statistics (flax nn.BatchNorm momentum 0.99;
+ * pqn_minatar.py:65,293-296): batch_stats float32[S][2][F] (mean, var),
+ * bn_sums float32[S][2][F] (sum x, sum x^2 over `count` elements per feature);
+ * bn_sums is zeroed for the next minibatch. */
+int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F, float count, float momentum,
+                        void* stream);
 
 #ifdef __cplusplus
 }

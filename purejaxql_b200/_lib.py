@@ -48,20 +48,22 @@ _SIGS = {
     "pqn_env_obs_packed": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "pqn_env_obs": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "pqn_eps_greedy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int, c_void_p]),
-    "pqn_rollout_act_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int, c_float, c_int,
-                                     c_void_p]),
+    "pqn_rollout_act_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int32, c_int32,
+                                     c_int, c_float, c_int, c_void_p]),
     "pqn_rollout_keys": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int, c_void_p]),
-    "pqn_qlambda": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_float,
-                            c_float, c_void_p]),
+    "pqn_qlambda": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                            c_float, c_float, c_void_p]),
     "pqn_net_layout": (c_int, [POINTER(NetDesc), POINTER(NetLayout)]),
     "pqn_net_workspace_bytes": (c_int64, [POINTER(NetDesc), c_int32, c_int64]),
     "pqn_qnet_forward": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32,
                                  c_int64, c_void_p, c_void_p]),
     "pqn_qnet_loss_grad": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
-                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
+                                   c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p,
+                                   c_void_p]),
     "pqn_radam_clip_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                     c_int64, c_float, c_float, c_float, c_float, c_void_p]),
+    "pqn_bn_stats_update": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)
@@ -99,6 +101,15 @@ def p(t):
         raise PqnError("libpqn_b200 takes CUDA tensors only (no CPU fallback); got a CPU tensor")
     if not t.is_contiguous():
         raise PqnError("libpqn_b200 takes contiguous tensors")
+    return c_void_p(t.data_ptr())
+
+
+def raw(t):
+    """Device pointer of a (possibly strided) CUDA tensor view; the caller passes the strides."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise PqnError("libpqn_b200 takes CUDA tensors only (no CPU fallback); got a CPU tensor")
     return c_void_p(t.data_ptr())
 
 

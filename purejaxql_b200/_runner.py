@@ -1,0 +1,104 @@
+"""single_run / tune / main shared by pqn_minatar.py and pqn_gymnax.py
+(purejaxql/pqn_minatar.py:435-541; pqn_gymnax.py is the same modulo names)."""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+import time
+
+import torch
+
+from . import config_loader, jaxrandom as jr
+
+
+def _shard_seeds(rngs):
+    """Seeds are independent runs (jax.vmap over rngs, pqn_minatar.py:459-461):
+    under torchrun each rank trains a contiguous slice of the same split(key, NUM_SEEDS)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return rngs, 0, 1
+    r, w = dist.get_rank(), dist.get_world_size()
+    S = rngs.shape[0]
+    per = (S + w - 1) // w
+    return rngs[r * per:min(S, (r + 1) * per)], r, w
+
+
+def single_run(config, make_train, alg_file_name="pqn"):
+    config = {**config, **config["alg"]}                              # :437
+    print(config)
+    alg_name = config.get("ALG_NAME", "pqn")
+    env_name = config["ENV_NAME"]
+    use_wandb = config.get("WANDB_MODE", "disabled") != "disabled"
+    if use_wandb:
+        import wandb
+        wandb.init(entity=config["ENTITY"], project=config["PROJECT"],
+                   tags=[alg_name.upper(), env_name.upper(), "b200_native"],
+                   name=f'{config["ALG_NAME"]}_{config["ENV_NAME"]}', config=config, mode=config["WANDB_MODE"])
+    rng = jr.PRNGKey(config["SEED"])                                  # :456
+    t0 = time.time()
+    rngs = jr.split(rng, config["NUM_SEEDS"], int(config.get("JAX_THREEFRY_PARTITIONABLE", 0)))   # :459
+    local_rngs, rank, world = _shard_seeds(rngs)
+    train = make_train(config)
+    outs = train(local_rngs)                                          # :460-461 (seed axis is native)
+    torch.cuda.synchronize()
+    print(f"Took {time.time() - t0} seconds to complete.")
+    if config.get("SAVE_PATH", None) is not None:                     # :464-483
+        from .utils.save_load import save_params
+        model_state = outs["runner_state"][0]
+        save_dir = os.path.join(config["SAVE_PATH"], env_name)
+        os.makedirs(save_dir, exist_ok=True)
+        if rank == 0:
+            config_loader.save_yaml(
+                {k: v for k, v in config.items() if k != "alg"},
+                os.path.join(save_dir, f'{alg_name}_{env_name}_seed{config["SEED"]}_config.yaml'))
+        per = local_rngs.shape[0]
+        for i in range(per):
+            def pick(d):
+                return {k: (pick(v) if isinstance(v, dict) else v[i]) for k, v in d.items()}
+            gi = rank * ((config["NUM_SEEDS"] + world - 1) // world) + i
+            save_params(pick(model_state.params),
+                        os.path.join(save_dir, f'{alg_name}_{env_name}_seed{config["SEED"]}_vmap{gi}.safetensors'))
+    return outs
+
+
+def tune(default_config, make_train):
+    """wandb Bayesian sweep over LR (pqn_minatar.py:486-531)."""
+    import wandb
+    default_config = {**default_config, **default_config["alg"]}
+    print(default_config)
+    alg_name = default_config.get("ALG_NAME", "pqn")
+    env_name = default_config["ENV_NAME"]
+
+    def wrapped_make_train():
+        wandb.init(project=default_config["PROJECT"])
+        config = copy.deepcopy(default_config)
+        for k, v in dict(wandb.config).items():
+            config[k] = v
+        print("running experiment with params:", config)
+        rng = jr.PRNGKey(config["SEED"])
+        rngs = jr.split(rng, config["NUM_SEEDS"])
+        make_train(config)(rngs)
+        torch.cuda.synchronize()
+
+    sweep_config = {
+        "name": f"{alg_name}_{env_name}",
+        "method": "bayes",
+        "metric": {"name": "returned_episode_returns", "goal": "maximize"},
+        "parameters": {"LR": {"values": [0.001, 0.0005, 0.0001, 0.00005]}},
+    }
+    wandb.login()
+    sweep_id = wandb.sweep(sweep_config, entity=default_config["ENTITY"], project=default_config["PROJECT"])
+    wandb.agent(sweep_id, wrapped_make_train, count=1000)
+
+
+def main(make_train, argv=None):
+    """`python -m purejaxql_b200.pqn_minatar +alg=pqn_minatar alg.NUM_ENVS=4096 NUM_SEEDS=8`"""
+    argv = sys.argv[1:] if argv is None else argv
+    config = config_loader.compose(argv)
+    import yaml
+    print("Config:\n", yaml.safe_dump(config, sort_keys=False))
+    if config.get("HYP_TUNE", False):
+        tune(config, make_train)
+    else:
+        return single_run(config, make_train)

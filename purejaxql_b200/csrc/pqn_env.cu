@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(ENV_BLOCK)
                             void* __restrict__ obs_next, int32_t* __restrict__ action_out,
                             float* __restrict__ reward_out, uint8_t* __restrict__ done_out,
                             float* __restrict__ maxq_out, double* __restrict__ info_sums, int E, int max_steps,
-                            float rew_scale, int part) {
+                            float rew_scale, int part, int64_t obs_seed_stride, int64_t tr_seed_stride,
+                            int info_done_only) {
   const int seed = blockIdx.y;
   const int e = blockIdx.x * ENV_BLOCK + threadIdx.x;
   const int64_t N = (int64_t)gridDim.y * E;
@@ -222,22 +223,25 @@ __global__ void __launch_bounds__(ENV_BLOCK)
     env_step_full<Env>(split_at(ks, (uint32_t)E, (uint32_t)e, part), part, max_steps, s, lg, a, r, d);
     Env::store(s, state, N, i);
     log_store(lg, state, N, i, Env::CORE_WORDS);
-    action_out[i] = a;
-    reward_out[i] = rew_scale * r;
-    done_out[i] = d ? 1 : 0;
-    maxq_out[i] = mq;
+    const int64_t io = (int64_t)seed * obs_seed_stride + e;
+    const int64_t it = (int64_t)seed * tr_seed_stride + e;
+    action_out[it] = a;
+    reward_out[it] = rew_scale * r;
+    done_out[it] = d ? 1 : 0;
+    maxq_out[it] = mq;
     if constexpr (Env::BINARY_OBS) {
       uint32_t bits[Env::OBS_WORDS_PAD];
       Env::obs_bits(s, bits);
-      write_obs_packed<Env>(bits, reinterpret_cast<uint32_t*>(obs_next), i);
+      write_obs_packed<Env>(bits, reinterpret_cast<uint32_t*>(obs_next), io);
     } else {
-      write_obs_float_dense<Env>(s, reinterpret_cast<float*>(obs_next), i);
+      write_obs_float_dense<Env>(s, reinterpret_cast<float*>(obs_next), io);
     }
     sums[0] = lg.returned_episode_returns;
     sums[1] = (float)lg.returned_episode_lengths;
     sums[2] = (float)lg.timestep;
     sums[3] = d ? 1.f : 0.f;
     sums[4] = d ? 0.f : 1.f;
+    if (info_done_only && !d) { sums[0] = 0.f; sums[1] = 0.f; sums[2] = 0.f; sums[4] = 0.f; }
   }
   if (info_sums != nullptr) {
     // block reduction in double, one atomic per metric per block
@@ -275,12 +279,16 @@ __global__ void rollout_keys_kernel(uint32_t* __restrict__ rng_inout, uint32_t* 
   rng_inout[2 * s + 1] = c.k1;
 }
 
+// buffers are [S][T][E]; one thread per (seed, env)
 __global__ void qlambda_kernel(const float* __restrict__ reward, const uint8_t* __restrict__ done,
                                const float* __restrict__ maxq, const float* __restrict__ q_last,
-                               float* __restrict__ targets, int T, int64_t N, int A, float gamma, float lambda) {
+                               float* __restrict__ targets, int T, int S, int E, int A, float gamma, float lambda) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  qlambda_one(reward, done, maxq, q_last, targets, T, N, A, gamma, lambda, i);
+  if (i >= (int64_t)S * E) return;
+  const int64_t s = i / E, e = i - s * E;
+  const int64_t base = s * (int64_t)T * E;
+  qlambda_one(reward + base, done + base, maxq + base, q_last + i * A, targets + base, T, (int64_t)E, A, gamma, lambda,
+              e);
 }
 
 __global__ void rng_split_kernel(const uint32_t* __restrict__ keys, int64_t n, int num, uint32_t* __restrict__ out,
@@ -432,9 +440,9 @@ int pqn_eps_greedy(const uint32_t* keys, const float* q, const float* eps, int32
 }
 
 int pqn_rollout_act_step(int env_id, const uint32_t* step_keys, const float* q, const float* eps, uint32_t* state,
-                         void* obs_next, int32_t* action, float* reward, uint8_t* done, float* maxq,
-                         double* info_sums, int32_t S, int32_t E, int max_steps, float rew_scale, int rng_mode,
-                         void* stream) {
+                         void* obs_next, int64_t obs_seed_stride, int32_t* action, float* reward, uint8_t* done,
+                         float* maxq, int64_t tr_seed_stride, double* info_sums, int info_done_only, int32_t S,
+                         int32_t E, int max_steps, float rew_scale, int rng_mode, void* stream) {
   if (!step_keys || !q || !eps || !state || !obs_next || !action || !reward || !done || !maxq || S <= 0 || E <= 0)
     return set_error(PQN_E_INVALID, "pqn_rollout_act_step: bad argument");
   if (S > 65535) return set_error(PQN_E_INVALID, "pqn_rollout_act_step: S=%d exceeds gridDim.y", S);
@@ -442,7 +450,8 @@ int pqn_rollout_act_step(int env_id, const uint32_t* step_keys, const float* q, 
     const int ms = max_steps > 0 ? max_steps : EnvT::DEFAULT_MAX_STEPS;
     dim3 grid(blocks_for(E, ENV_BLOCK), (unsigned)S);
     rollout_act_step_kernel<EnvT><<<grid, ENV_BLOCK, 0, (cudaStream_t)stream>>>(
-        step_keys, q, eps, state, obs_next, action, reward, done, maxq, info_sums, E, ms, rew_scale, rng_mode);
+        step_keys, q, eps, state, obs_next, action, reward, done, maxq, info_sums, E, ms, rew_scale, rng_mode,
+        obs_seed_stride, tr_seed_stride, info_done_only);
   });
   return check_launch("pqn_rollout_act_step");
 }
@@ -454,12 +463,11 @@ int pqn_rollout_keys(uint32_t* rng_inout, uint32_t* keys_out, int32_t S, int32_t
 }
 
 int pqn_qlambda(const float* reward, const uint8_t* done, const float* maxq, const float* q_last, float* targets,
-                int32_t T, int64_t N, int32_t A, float gamma, float lambda, void* stream) {
-  if (!reward || !done || !maxq || !q_last || !targets || T <= 0 || N < 0 || A <= 0)
+                int32_t T, int32_t S, int32_t E, int32_t A, float gamma, float lambda, void* stream) {
+  if (!reward || !done || !maxq || !q_last || !targets || T <= 0 || S <= 0 || E <= 0 || A <= 0)
     return set_error(PQN_E_INVALID, "pqn_qlambda: bad argument");
-  if (N == 0) return PQN_OK;
-  qlambda_kernel<<<blocks_for(N, 256), 256, 0, (cudaStream_t)stream>>>(reward, done, maxq, q_last, targets, T, N, A,
-                                                                       gamma, lambda);
+  qlambda_kernel<<<blocks_for((int64_t)S * E, 256), 256, 0, (cudaStream_t)stream>>>(reward, done, maxq, q_last,
+                                                                                    targets, T, S, E, A, gamma, lambda);
   return check_launch("pqn_qlambda");
 }
 

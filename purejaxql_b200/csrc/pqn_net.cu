@@ -1,0 +1,1099 @@
+// Q-network forward / loss-gradient kernels for sm_100a, batched over S
+// independent seeds (blockIdx.y or .z = seed; every seed has its own weights).
+//
+// Reference: QNetwork/CNN  purejaxql/pqn_minatar.py:24-69,
+//            MLP QNetwork  purejaxql/pqn_gymnax.py:29-58,
+//            _loss_fn      purejaxql/pqn_minatar.py:271-291.
+// fp32 throughout (the north star asks for 1e-5 agreement with an fp32 oracle):
+// the dense contractions are register-tiled FFMA GEMMs (128x128x16 CTA tiles,
+// 8x8 per thread, double-buffered shared memory, 128-bit LDS) with the
+// bias + LayerNorm + ReLU (+ Q-head) epilogue fused in registers; the 3x3 conv
+// consumes the bit-packed observations directly (its input is {0,1}/255, so a
+// tap contributes either w/255 or nothing) and skips taps no lane of the warp
+// has set.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pqn_b200.h"
+#include "api_common.h"
+
+namespace pqn {
+
+constexpr int GT = 256;   // threads per GEMM CTA (16 x 16)
+constexpr int BK = 16;    // reduce-dim tile
+constexpr float LN_EPS = 1e-6f;
+constexpr int CONV_O = 16;   // conv output channels
+constexpr int CONV_PIX = 64; // 8x8 output pixels
+constexpr int HID_CNN = 128;
+constexpr int FLAT_CNN = CONV_PIX * CONV_O;  // 1024
+
+static inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
+
+static int make_layout(const pqn_net_desc_t* d, pqn_net_layout_t* L) {
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t o = off; off += align4(n); return o; };
+  L->d1_w = L->d1_b = L->ln1_scale = L->ln1_bias = L->conv_w = L->conv_b = -1;
+  const int A = d->num_actions;
+  if (d->kind == PQN_NET_MINATAR_CNN) {
+    const int C = d->in_c;
+    L->bn_scale = take(C); L->bn_bias = take(C);
+    L->conv_w = take(9 * C * CONV_O); L->conv_b = take(CONV_O);
+    L->ln0_scale = take(CONV_O); L->ln0_bias = take(CONV_O);
+    L->d0_w = take((int64_t)FLAT_CNN * HID_CNN); L->d0_b = take(HID_CNN);
+    L->ln1_scale = take(HID_CNN); L->ln1_bias = take(HID_CNN);
+    L->head_w = take((int64_t)HID_CNN * A); L->head_b = take(A);
+  } else if (d->kind == PQN_NET_MLP) {
+    const int D = d->in_c, H = d->hidden;
+    L->bn_scale = take(D); L->bn_bias = take(D);
+    L->d0_w = take((int64_t)D * H); L->d0_b = take(H);
+    L->ln0_scale = take(H); L->ln0_bias = take(H);
+    if (d->layers == 2) {
+      L->d1_w = take((int64_t)H * H); L->d1_b = take(H);
+      L->ln1_scale = take(H); L->ln1_bias = take(H);
+    }
+    L->head_w = take((int64_t)H * A); L->head_b = take(A);
+  } else {
+    return -1;
+  }
+  L->total = off;
+  return 0;
+}
+
+static int check_desc(const pqn_net_desc_t* d, const char* who) {
+  if (!d) return set_error(PQN_E_INVALID, "%s: desc is NULL", who);
+  if (d->num_actions < 1 || d->num_actions > 32) return set_error(PQN_E_INVALID, "%s: num_actions=%d out of [1,32]", who, d->num_actions);
+  if (d->kind == PQN_NET_MINATAR_CNN) {
+    if (d->in_c != 4 && d->in_c != 6 && d->in_c != 7 && d->in_c != 10)
+      return set_error(PQN_E_UNSUPPORTED, "%s: CNN in_c=%d (MinAtar uses 4/6/7/10)", who, d->in_c);
+    return PQN_OK;
+  }
+  if (d->kind == PQN_NET_MLP) {
+    if (d->hidden != 128 && d->hidden != 256) return set_error(PQN_E_UNSUPPORTED, "%s: MLP hidden=%d (128 or 256 built)", who, d->hidden);
+    if (d->layers != 1 && d->layers != 2) return set_error(PQN_E_UNSUPPORTED, "%s: MLP layers=%d (1 or 2 built)", who, d->layers);
+    if (d->in_c < 1 || d->in_c > 4096) return set_error(PQN_E_INVALID, "%s: MLP in dim %d", who, d->in_c);
+    return PQN_OK;
+  }
+  return set_error(PQN_E_INVALID, "%s: unknown net kind %d", who, d->kind);
+}
+
+// ---------------------------------------------------------------------------
+// GEMM tile core: acc[TM][TN] += As[k][rows of thread] * Bs[k][cols of thread]
+// thread (tx, ty) owns rows  {c*64 + ty*4 + i}  and cols {c*64 + tx*4 + j}.
+// ---------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN>
+__device__ __forceinline__ void tile_mma(const float* __restrict__ As, const float* __restrict__ Bs, int tx, int ty,
+                                         float (&acc)[TM][TN]) {
+#pragma unroll
+  for (int kk = 0; kk < BK; ++kk) {
+    float a[TM], b[TN];
+#pragma unroll
+    for (int c = 0; c < TM / 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(As + kk * BM + c * 64 + ty * 4);
+      a[4 * c] = v.x; a[4 * c + 1] = v.y; a[4 * c + 2] = v.z; a[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int c = 0; c < TN / 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(Bs + kk * BN + c * 64 + tx * 4);
+      b[4 * c] = v.x; b[4 * c + 1] = v.y; b[4 * c + 2] = v.z; b[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
+// Load 4 consecutive reduce-dim elements src[0..3] (bounds: r0+j < R), vector if allowed.
+__device__ __forceinline__ float4 load4_guard(const float* __restrict__ src, int r0, int R, bool vec_ok, bool row_ok) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!row_ok) return v;
+  if (vec_ok && r0 + 3 < R) return __ldg(reinterpret_cast<const float4*>(src));
+  if (r0 < R) v.x = __ldg(src);
+  if (r0 + 1 < R) v.y = __ldg(src + 1);
+  if (r0 + 2 < R) v.z = __ldg(src + 2);
+  if (r0 + 3 < R) v.w = __ldg(src + 3);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// dense_fwd: Y = LayerNorm(X @ W + b) -> ReLU  [-> head]
+//   MODE 0: write H          (inference hidden layer)
+//   MODE 1: write H, XHAT, RSTD  (training forward: what the backward needs)
+//   MODE 2: write Q = H @ Wh + bh only (inference last layer, Q-head fused)
+// grid = (ceil(rows/BM), S)
+// ---------------------------------------------------------------------------
+template <int BN, int MODE>
+__global__ void __launch_bounds__(GT) dense_fwd_kernel(
+    const float* __restrict__ X, int64_t x_seed_stride, int ldx, const float* __restrict__ params, int64_t P,
+    int64_t off_w, int64_t off_b, int64_t off_scale, int64_t off_bias, int64_t off_hw, int64_t off_hb, int A,
+    float* __restrict__ H, float* __restrict__ XHAT, float* __restrict__ RSTD, float* __restrict__ Q, int rows,
+    int K) {
+  constexpr int BM = (BN == 128) ? 128 : 64;
+  constexpr int TM = BM / 16, TN = BN / 16;
+  constexpr int A_LD = BM / 64, B_LD = BN / 64;
+  __shared__ __align__(16) float As[2][BK * BM];
+  __shared__ __align__(16) float Bs[2][BK * BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int seed = blockIdx.y;
+  const int m0 = blockIdx.x * BM;
+  const float* __restrict__ Xs = X + (int64_t)seed * x_seed_stride;
+  const float* __restrict__ prm = params + (int64_t)seed * P;
+  const float* __restrict__ W = prm + off_w;
+  const bool vecA = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(Xs) & 15) == 0);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (K + BK - 1) / BK;
+  float4 ra[A_LD], rb[B_LD];
+  auto gload = [&](int kt) {
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      const int f = tid + i * GT;
+      const int m = f >> 2, r4 = f & 3;
+      const int row = m0 + m;
+      const int k = kt * BK + r4 * 4;
+      ra[i] = load4_guard(Xs + (int64_t)row * ldx + k, k, K, vecA, row < rows);
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+      const int f = tid + i * GT;
+      const int r = f / (BN / 4), n4 = f % (BN / 4);
+      const int k = kt * BK + r;
+      rb[i] = (k < K) ? __ldg(reinterpret_cast<const float4*>(W + (int64_t)k * BN + n4 * 4))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      const int f = tid + i * GT;
+      const int m = f >> 2, r4 = f & 3;
+      float* dst = &As[buf][(r4 * 4) * BM + m];
+      dst[0] = ra[i].x; dst[BM] = ra[i].y; dst[2 * BM] = ra[i].z; dst[3 * BM] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+      const int f = tid + i * GT;
+      const int r = f / (BN / 4), n4 = f % (BN / 4);
+      *reinterpret_cast<float4*>(&Bs[buf][r * BN + n4 * 4]) = rb[i];
+    }
+  };
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    if (kt + 1 < nk) gload(kt + 1);
+    tile_mma<BM, BN, TM, TN>(As[kt & 1], Bs[kt & 1], tx, ty, acc);
+    if (kt + 1 < nk) sstore((kt + 1) & 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue: bias, LayerNorm over the BN columns of each row, ReLU
+  const float* __restrict__ bvec = prm + off_b;
+  const float* __restrict__ sc = prm + off_scale;
+  const float* __restrict__ bi = prm + off_bias;
+  float colb[TN], cols_[TN], colbi[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int col = (j >> 2) * 64 + tx * 4 + (j & 3);
+    colb[j] = __ldg(bvec + col); cols_[j] = __ldg(sc + col); colbi[j] = __ldg(bi + col);
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int row = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      acc[i][j] += colb[j];
+      s1 += acc[i][j];
+      s2 += acc[i][j] * acc[i][j];
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float mean = s1 * (1.0f / BN);
+    const float var = fmaxf(s2 * (1.0f / BN) - mean * mean, 0.f);
+    const float rstd = 1.0f / sqrtf(var + LN_EPS);
+    float xh[TN], h[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      xh[j] = (acc[i][j] - mean) * rstd;
+      h[j] = fmaxf(xh[j] * cols_[j] + colbi[j], 0.f);
+    }
+    const bool row_ok = row < rows;
+    const int64_t grow = (int64_t)seed * rows + row;
+    if (MODE == 0 || MODE == 1) {
+      if (row_ok) {
+#pragma unroll
+        for (int c = 0; c < TN / 4; ++c) {
+          const int col = c * 64 + tx * 4;
+          *reinterpret_cast<float4*>(H + grow * BN + col) = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+          if (MODE == 1)
+            *reinterpret_cast<float4*>(XHAT + grow * BN + col) =
+                make_float4(xh[4 * c], xh[4 * c + 1], xh[4 * c + 2], xh[4 * c + 3]);
+        }
+        if (MODE == 1 && tx == 0) RSTD[grow] = rstd;
+      }
+    } else {
+      const float* __restrict__ HW = prm + off_hw;
+      const float* __restrict__ HB = prm + off_hb;
+      for (int a = 0; a < A; ++a) {
+        float pq = 0.f;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          const int col = (j >> 2) * 64 + tx * 4 + (j & 3);
+          pq = fmaf(h[j], __ldg(HW + (int64_t)col * A + a), pq);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) pq += __shfl_xor_sync(0xffffffffu, pq, o);
+        if (tx == 0 && row_ok) Q[grow * A + a] = pq + __ldg(HB + a);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// wgrad: dW[kin][n] (+)= sum_rows X[row][kin] * dZ[row][n]
+// grid = (ceil(Kin/128), N/128, S*splits); atomicAdd when splits > 1
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(GT) wgrad_kernel(const float* __restrict__ X, int64_t x_seed_stride, int ldx,
+                                                   const float* __restrict__ DZ, int64_t dz_seed_stride, int N,
+                                                   float* __restrict__ grads, int64_t P, int64_t off_w, int rows,
+                                                   int Kin, int splits) {
+  constexpr int BM = 128, BN = 128, TM = 8, TN = 8;
+  __shared__ __align__(16) float As[2][BK * BM];
+  __shared__ __align__(16) float Bs[2][BK * BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int seed = blockIdx.z / splits, split = blockIdx.z % splits;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const float* __restrict__ Xs = X + (int64_t)seed * x_seed_stride;
+  const float* __restrict__ Zs = DZ + (int64_t)seed * dz_seed_stride;
+  int chunk = (rows + splits - 1) / splits;
+  chunk = (chunk + BK - 1) / BK * BK;
+  const int r_begin = split * chunk;
+  const int r_end = min(rows, r_begin + chunk);
+  const bool vecA = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(Xs) & 15) == 0);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (r_end > r_begin) ? (r_end - r_begin + BK - 1) / BK : 0;
+  float4 ra[2], rb[2];
+  auto gload = [&](int kt) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + i * GT;
+      const int r = f >> 5, m4 = f & 31;
+      const int row = r_begin + kt * BK + r;
+      const int kin = m0 + m4 * 4;
+      ra[i] = load4_guard(Xs + (int64_t)row * ldx + kin, kin, Kin, vecA, row < r_end);
+      rb[i] = (row < r_end) ? __ldg(reinterpret_cast<const float4*>(Zs + (int64_t)row * N + n0 + m4 * 4))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + i * GT;
+      const int r = f >> 5, m4 = f & 31;
+      *reinterpret_cast<float4*>(&As[buf][r * BM + m4 * 4]) = ra[i];
+      *reinterpret_cast<float4*>(&Bs[buf][r * BN + m4 * 4]) = rb[i];
+    }
+  };
+  if (nk > 0) {
+    gload(0);
+    sstore(0);
+  }
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    if (kt + 1 < nk) gload(kt + 1);
+    tile_mma<BM, BN, TM, TN>(As[kt & 1], Bs[kt & 1], tx, ty, acc);
+    if (kt + 1 < nk) sstore((kt + 1) & 1);
+    __syncthreads();
+  }
+  float* __restrict__ dW = grads + (int64_t)seed * P + off_w;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int kin = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+    if (kin >= Kin) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+      if (splits == 1) dW[(int64_t)kin * N + n] = acc[i][j];
+      else atomicAdd(dW + (int64_t)kin * N + n, acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dgrad: OUT[row][c] = (HPREV[row][c] > 0) * sum_n dZ[row][n] * W[c][n]
+// (ReLU mask of the previous layer fused; OUT may alias HPREV)
+// grid = (ceil(rows/128), Kprev/128, S)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(GT) dgrad_kernel(const float* __restrict__ DZ, int64_t dz_seed_stride, int N,
+                                                   const float* __restrict__ params, int64_t P, int64_t off_w,
+                                                   const float* HPREV, float* OUT, int64_t h_seed_stride, int rows,
+                                                   int Kprev) {
+  constexpr int BM = 128, BN = 128, TM = 8, TN = 8;
+  __shared__ __align__(16) float As[2][BK * BM];
+  __shared__ __align__(16) float Bs[2][BK * BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int seed = blockIdx.z;
+  const int m0 = blockIdx.x * BM, c0 = blockIdx.y * BN;
+  const float* __restrict__ Zs = DZ + (int64_t)seed * dz_seed_stride;
+  const float* __restrict__ W = params + (int64_t)seed * P + off_w;  // [Kprev][N]
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  const int nk = N / BK;
+  float4 ra[2], rb[2];
+  auto gload = [&](int kt) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + i * GT;
+      const int m = f >> 2, r4 = f & 3;
+      const int n = kt * BK + r4 * 4;
+      const int row = m0 + m;
+      ra[i] = (row < rows) ? __ldg(reinterpret_cast<const float4*>(Zs + (int64_t)row * N + n))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[i] = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(c0 + m) * N + n));
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + i * GT;
+      const int m = f >> 2, r4 = f & 3;
+      float* da = &As[buf][(r4 * 4) * BM + m];
+      da[0] = ra[i].x; da[BM] = ra[i].y; da[2 * BM] = ra[i].z; da[3 * BM] = ra[i].w;
+      float* db = &Bs[buf][(r4 * 4) * BN + m];
+      db[0] = rb[i].x; db[BN] = rb[i].y; db[2 * BN] = rb[i].z; db[3 * BN] = rb[i].w;
+    }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    if (kt + 1 < nk) gload(kt + 1);
+    tile_mma<BM, BN, TM, TN>(As[kt & 1], Bs[kt & 1], tx, ty, acc);
+    if (kt + 1 < nk) sstore((kt + 1) & 1);
+    __syncthreads();
+  }
+  const float* Hs = HPREV + (int64_t)seed * h_seed_stride;
+  float* Os = OUT + (int64_t)seed * h_seed_stride;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int row = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+    if (row >= rows) continue;
+#pragma unroll
+    for (int c = 0; c < TN / 4; ++c) {
+      const int col = c0 + c * 64 + tx * 4;
+      const float4 hv = *reinterpret_cast<const float4*>(Hs + (int64_t)row * Kprev + col);
+      float4 o;
+      o.x = hv.x > 0.f ? acc[i][4 * c] : 0.f;
+      o.y = hv.y > 0.f ? acc[i][4 * c + 1] : 0.f;
+      o.z = hv.z > 0.f ? acc[i][4 * c + 2] : 0.f;
+      o.w = hv.w > 0.f ? acc[i][4 * c + 3] : 0.f;
+      *reinterpret_cast<float4*>(Os + (int64_t)row * Kprev + col) = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// row backward: one warp per sample.
+//   HEAD=1: q = h @ Wh + bh, loss/qsa accumulation, dq, dWh, dbh, dh = dq*Wh[:,a],
+//           ReLU mask from h.      HEAD=0: dy read from DH (already ReLU-masked).
+//   then LayerNorm backward -> DZ, accumulating dscale, dbias and db (= sum dz).
+// grid = (ceil(rows/ROWS_PER_CTA), S)
+// ---------------------------------------------------------------------------
+constexpr int RB_ROWS = 128;  // rows per CTA (8 warps x 16)
+
+template <int N, bool HEAD>
+__global__ void __launch_bounds__(256) row_bwd_kernel(
+    const float* __restrict__ Hh, const float* __restrict__ XHAT, const float* __restrict__ RSTD,
+    const float* DH, float* DZ, const float* __restrict__ params, float* __restrict__ grads, int64_t P,
+    int64_t off_scale, int64_t off_dscale, int64_t off_dbias, int64_t off_db, int64_t off_hw, int64_t off_hb, int A,
+    const int32_t* __restrict__ gather, const int32_t* __restrict__ action, const float* __restrict__ target,
+    int64_t tr_rows_per_seed, float* __restrict__ loss_sum, float* __restrict__ qsa_sum, int rows) {
+  constexpr int F = N / 32;  // features per lane, in float4 chunks at lane*4 + c*128
+  extern __shared__ float smem[];
+  float* s_dsc = smem;            // [N]
+  float* s_dbi = smem + N;        // [N]
+  float* s_db = smem + 2 * N;     // [N]
+  float* s_dhw = smem + 3 * N;    // [A*N]  (HEAD)
+  float* s_dhb = s_dhw + (HEAD ? A * N : 0);  // [A]
+  float* s_ls = s_dhb + (HEAD ? A : 0);       // [2] loss, qsa
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seed = blockIdx.y;
+  const int nsm = 3 * N + (HEAD ? A * N + A + 2 : 0);
+  for (int i = tid; i < nsm; i += 256) smem[i] = 0.f;
+  __syncthreads();
+  const float* __restrict__ prm = params + (int64_t)seed * P;
+  float scale[F];
+#pragma unroll
+  for (int j = 0; j < F; ++j) scale[j] = __ldg(prm + off_scale + (j >> 2) * 128 + lane * 4 + (j & 3));
+  float a_dsc[F], a_dbi[F], a_db[F];
+#pragma unroll
+  for (int j = 0; j < F; ++j) a_dsc[j] = a_dbi[j] = a_db[j] = 0.f;
+  float a_loss = 0.f, a_qsa = 0.f;
+  const float invB = 1.0f / (float)rows;
+
+  for (int rr = warp; rr < RB_ROWS; rr += 8) {
+    const int row = blockIdx.x * RB_ROWS + rr;
+    if (row >= rows) break;
+    const int64_t grow = (int64_t)seed * rows + row;
+    float h[F], xh[F], dy[F];
+#pragma unroll
+    for (int c = 0; c < F / 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(XHAT + grow * N + c * 128 + lane * 4);
+      xh[4 * c] = v.x; xh[4 * c + 1] = v.y; xh[4 * c + 2] = v.z; xh[4 * c + 3] = v.w;
+    }
+    const float rstd = RSTD[grow];
+    if (HEAD) {
+#pragma unroll
+      for (int c = 0; c < F / 4; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(Hh + grow * N + c * 128 + lane * 4);
+        h[4 * c] = v.x; h[4 * c + 1] = v.y; h[4 * c + 2] = v.z; h[4 * c + 3] = v.w;
+      }
+      const int src = gather ? gather[(int64_t)seed * rows + row] : row;
+      const int act = action[(int64_t)seed * tr_rows_per_seed + src];
+      const float tgt = target[(int64_t)seed * tr_rows_per_seed + src];
+      // q_sa only needs column `act` of the head
+      float pq = 0.f;
+      float wcol[F];
+#pragma unroll
+      for (int j = 0; j < F; ++j) {
+        const int f = (j >> 2) * 128 + lane * 4 + (j & 3);
+        wcol[j] = __ldg(prm + off_hw + (int64_t)f * A + act);
+        pq = fmaf(h[j], wcol[j], pq);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) pq += __shfl_xor_sync(0xffffffffu, pq, o);
+      const float q_sa = pq + __ldg(prm + off_hb + act);
+      const float diff = q_sa - tgt;
+      const float dq = diff * invB;
+      if (lane == 0) {
+        a_loss += 0.5f * diff * diff * invB;
+        a_qsa += q_sa * invB;
+        atomicAdd(s_dhb + act, dq);
+      }
+#pragma unroll
+      for (int j = 0; j < F; ++j) {
+        const int f = (j >> 2) * 128 + lane * 4 + (j & 3);
+        atomicAdd(s_dhw + act * N + f, h[j] * dq);
+        dy[j] = h[j] > 0.f ? dq * wcol[j] : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < F / 4; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(DH + grow * N + c * 128 + lane * 4);
+        dy[4 * c] = v.x; dy[4 * c + 1] = v.y; dy[4 * c + 2] = v.z; dy[4 * c + 3] = v.w;
+      }
+    }
+    float m1 = 0.f, m2 = 0.f;
+    float dxh[F];
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      a_dsc[j] = fmaf(dy[j], xh[j], a_dsc[j]);
+      a_dbi[j] += dy[j];
+      dxh[j] = dy[j] * scale[j];
+      m1 += dxh[j];
+      m2 = fmaf(dxh[j], xh[j], m2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    }
+    m1 *= (1.0f / N);
+    m2 *= (1.0f / N);
+    float dz[F];
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      dz[j] = rstd * (dxh[j] - m1 - xh[j] * m2);
+      a_db[j] += dz[j];
+    }
+#pragma unroll
+    for (int c = 0; c < F / 4; ++c)
+      *reinterpret_cast<float4*>(DZ + grow * N + c * 128 + lane * 4) =
+          make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
+  }
+  // combine warps in shared memory, then one global atomic per element per CTA
+#pragma unroll
+  for (int j = 0; j < F; ++j) {
+    const int f = (j >> 2) * 128 + lane * 4 + (j & 3);
+    atomicAdd(s_dsc + f, a_dsc[j]);
+    atomicAdd(s_dbi + f, a_dbi[j]);
+    atomicAdd(s_db + f, a_db[j]);
+  }
+  if (HEAD && lane == 0) {
+    atomicAdd(s_ls, a_loss);
+    atomicAdd(s_ls + 1, a_qsa);
+  }
+  __syncthreads();
+  float* __restrict__ g = grads + (int64_t)seed * P;
+  for (int i = tid; i < N; i += 256) {
+    atomicAdd(g + off_dscale + i, s_dsc[i]);
+    atomicAdd(g + off_dbias + i, s_dbi[i]);
+    atomicAdd(g + off_db + i, s_db[i]);
+  }
+  if (HEAD) {
+    // s_dhw is [A][N]; the parameter is [N][A]
+    for (int i = tid; i < A * N; i += 256) {
+      const int a = i / N, f = i - a * N;
+      const float v = s_dhw[i];
+      if (v != 0.f) atomicAdd(g + off_hw + (int64_t)f * A + a, v);
+    }
+    if (tid < A) atomicAdd(g + off_hb + tid, s_dhb[tid]);
+    if (tid == 0) {
+      atomicAdd(loss_sum + seed, s_ls[0]);
+      atomicAdd(qsa_sum + seed, s_ls[1]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// MinAtar conv 3x3 (C -> 16, VALID) + LayerNorm(16) + ReLU from bit-packed obs.
+// thread = (sample, output pixel); block = 4 samples; grid = (ceil(rows/4), S)
+// ---------------------------------------------------------------------------
+template <int C>
+struct ConvCfg {
+  static constexpr int TAPS = 9 * C;
+  static constexpr int OBS_BITS = 100 * C;
+  static constexpr int OBS_WORDS = (OBS_BITS + 31) / 32;
+  static constexpr int PW = (OBS_WORDS + 3) / 4 * 4;       // packed row words (matches env OBS_WORDS_PAD)
+  static constexpr int SW = PW + 1;                        // smem row (+1 so the funnel shift may read past the end)
+};
+
+// the C channel bits of input pixel p of a packed row held in shared memory
+template <int C>
+__device__ __forceinline__ uint32_t pixel_bits(const uint32_t* __restrict__ so, int p) {
+  const int f0 = p * C;
+  const uint32_t lo = so[f0 >> 5], hi = so[(f0 >> 5) + 1];
+  return __funnelshift_r(lo, hi, f0 & 31) & ((1u << C) - 1u);
+}
+
+// conv pre-activation for one output pixel; ws = conv kernel * (1/255), [tap][16]
+template <int C>
+__device__ __forceinline__ void conv_pixel(const uint32_t* __restrict__ so, const float* __restrict__ ws,
+                                           const float* __restrict__ cb, int y, int x, float (&acc)[CONV_O]) {
+#pragma unroll
+  for (int o = 0; o < CONV_O; ++o) acc[o] = cb[o];
+#pragma unroll
+  for (int di = 0; di < 3; ++di)
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj) {
+      const uint32_t nib = pixel_bits<C>(so, (y + di) * 10 + (x + dj));
+      if (__ballot_sync(0xffffffffu, nib != 0u) == 0u) continue;  // nobody in the warp has this patch cell set
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const bool bit = (nib >> c) & 1u;
+        if (__ballot_sync(0xffffffffu, bit) == 0u) continue;
+        const float* __restrict__ w = ws + ((di * 3 + dj) * C + c) * CONV_O;
+#pragma unroll
+        for (int o4 = 0; o4 < CONV_O / 4; ++o4) {
+          const float4 wv = *reinterpret_cast<const float4*>(w + 4 * o4);
+          if (bit) {
+            acc[4 * o4] += wv.x; acc[4 * o4 + 1] += wv.y; acc[4 * o4 + 2] += wv.z; acc[4 * o4 + 3] += wv.w;
+          }
+        }
+      }
+    }
+}
+
+__device__ __forceinline__ void ln16(const float (&z)[CONV_O], float& mean, float& rstd) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int o = 0; o < CONV_O; ++o) { s1 += z[o]; s2 = fmaf(z[o], z[o], s2); }
+  mean = s1 * (1.0f / CONV_O);
+  const float var = fmaxf(s2 * (1.0f / CONV_O) - mean * mean, 0.f);
+  rstd = 1.0f / sqrtf(var + LN_EPS);
+}
+
+template <int C>
+__device__ __forceinline__ void conv_load_consts(const float* __restrict__ prm, const pqn_net_layout_t& L, float* ws,
+                                                 float* cb, float* sc, float* bi) {
+  const float inv255 = 1.0f / 255.0f;  // x/255 for x in {0,1}  (pqn_minatar.py:66)
+  for (int i = threadIdx.x; i < ConvCfg<C>::TAPS * CONV_O; i += blockDim.x) ws[i] = __ldg(prm + L.conv_w + i) * inv255;
+  if (threadIdx.x < CONV_O) {
+    cb[threadIdx.x] = __ldg(prm + L.conv_b + threadIdx.x);
+    sc[threadIdx.x] = __ldg(prm + L.ln0_scale + threadIdx.x);
+    bi[threadIdx.x] = __ldg(prm + L.ln0_bias + threadIdx.x);
+  }
+}
+
+template <int C, bool TRAIN>
+__global__ void __launch_bounds__(256) conv_fwd_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed,
+                                                       const int32_t* __restrict__ gather,
+                                                       const float* __restrict__ params, int64_t P,
+                                                       pqn_net_layout_t L, float* __restrict__ H1,
+                                                       float* __restrict__ bn_sums, int rows) {
+  using Cfg = ConvCfg<C>;
+  __shared__ __align__(16) float ws[Cfg::TAPS * CONV_O];
+  __shared__ float cb[CONV_O], sc[CONV_O], bi[CONV_O];
+  __shared__ uint32_t so[4][Cfg::SW];
+  __shared__ float s_cnt[C];
+  const int tid = threadIdx.x, sl = tid >> 6, pix = tid & 63;
+  const int seed = blockIdx.y;
+  const int row = blockIdx.x * 4 + sl;
+  const bool valid = row < rows;
+  conv_load_consts<C>(params + (int64_t)seed * P, L, ws, cb, sc, bi);
+  if (TRAIN && tid < C) s_cnt[tid] = 0.f;
+  if (pix < Cfg::SW) {
+    uint32_t w = 0u;
+    if (valid && pix < Cfg::PW) {
+      const int64_t src = gather ? gather[(int64_t)seed * rows + row] : row;
+      w = __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + pix);
+    }
+    so[sl][pix] = w;
+  }
+  __syncthreads();
+  const int y = pix >> 3, x = pix & 7;
+  float acc[CONV_O];
+  conv_pixel<C>(so[sl], ws, cb, y, x, acc);
+  float mean, rstd;
+  ln16(acc, mean, rstd);
+  if (valid) {
+    float4* __restrict__ out = reinterpret_cast<float4*>(H1 + ((int64_t)seed * rows + row) * FLAT_CNN + pix * CONV_O);
+#pragma unroll
+    for (int o4 = 0; o4 < CONV_O / 4; ++o4) {
+      float4 v;
+      v.x = fmaxf((acc[4 * o4] - mean) * rstd * sc[4 * o4] + bi[4 * o4], 0.f);
+      v.y = fmaxf((acc[4 * o4 + 1] - mean) * rstd * sc[4 * o4 + 1] + bi[4 * o4 + 1], 0.f);
+      v.z = fmaxf((acc[4 * o4 + 2] - mean) * rstd * sc[4 * o4 + 2] + bi[4 * o4 + 2], 0.f);
+      v.w = fmaxf((acc[4 * o4 + 3] - mean) * rstd * sc[4 * o4 + 3] + bi[4 * o4 + 3], 0.f);
+      out[o4] = v;
+    }
+  }
+  if (TRAIN && bn_sums != nullptr) {
+    // dummy input BatchNorm statistics: per-channel count of set bits (x in {0,1} => sum x == sum x^2)
+    uint32_t b0 = pixel_bits<C>(so[sl], pix);
+    uint32_t b1 = (pix + 64 < 100) ? pixel_bits<C>(so[sl], pix + 64) : 0u;
+    if (!valid) { b0 = 0u; b1 = 0u; }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      int cnt = (int)((b0 >> c) & 1u) + (int)((b1 >> c) & 1u);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if ((tid & 31) == 0 && cnt) atomicAdd(&s_cnt[c], (float)cnt);
+    }
+    __syncthreads();
+    if (tid < C && s_cnt[tid] != 0.f) {
+      atomicAdd(bn_sums + (int64_t)seed * 2 * C + tid, s_cnt[tid]);
+      atomicAdd(bn_sums + (int64_t)seed * 2 * C + C + tid, s_cnt[tid]);
+    }
+  }
+}
+
+// conv backward: recompute z1/LN, LN backward from DY1 (already ReLU-masked),
+// accumulate d(ln0 scale/bias), d(conv bias), d(conv kernel).
+// CTA = CONV_BWD_SPB samples in chunks of 4; grid = (ceil(rows/SPB), S)
+constexpr int CONV_BWD_SPB = 32;
+constexpr int SDZ_LD = 20;  // padded row of the staged dz (conflict-free 128-bit stores)
+
+template <int C>
+__global__ void __launch_bounds__(256) conv_bwd_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed,
+                                                       const int32_t* __restrict__ gather,
+                                                       const float* __restrict__ params, int64_t P,
+                                                       pqn_net_layout_t L, const float* __restrict__ DY1,
+                                                       float* __restrict__ grads, int rows) {
+  using Cfg = ConvCfg<C>;
+  constexpr int TAPS = Cfg::TAPS;
+  constexpr int G = 256 / TAPS;  // entry groups in phase B
+  __shared__ __align__(16) float ws[TAPS * CONV_O];
+  __shared__ float cb[CONV_O], sc[CONV_O], bi[CONV_O];
+  __shared__ uint32_t so[4][Cfg::SW];
+  __shared__ __align__(16) float sdz[256 * SDZ_LD];
+  __shared__ float s_red[3 * CONV_O];
+  const int tid = threadIdx.x, sl = tid >> 6, pix = tid & 63;
+  const int seed = blockIdx.y;
+  const float* __restrict__ prm = params + (int64_t)seed * P;
+  conv_load_consts<C>(prm, L, ws, cb, sc, bi);
+  if (tid < 3 * CONV_O) s_red[tid] = 0.f;
+  const int y = pix >> 3, x = pix & 7;
+  float a_dsc[CONV_O], a_dbi[CONV_O], a_dcb[CONV_O];
+#pragma unroll
+  for (int o = 0; o < CONV_O; ++o) a_dsc[o] = a_dbi[o] = a_dcb[o] = 0.f;
+  // phase-B role
+  const int tap = tid % TAPS, grp = tid / TAPS;
+  const bool b_active = grp < G;
+  const int t_c = tap % C, t_dj = (tap / C) % 3, t_di = tap / (3 * C);
+  float wacc[CONV_O];
+#pragma unroll
+  for (int o = 0; o < CONV_O; ++o) wacc[o] = 0.f;
+
+  const int row_base = blockIdx.x * CONV_BWD_SPB;
+  for (int ch = 0; ch < CONV_BWD_SPB / 4; ++ch) {
+    const int row = row_base + ch * 4 + sl;
+    const bool valid = row < rows;
+    __syncthreads();  // previous chunk's phase B is done with so/sdz (also orders the const loads)
+    if (pix < Cfg::SW) {
+      uint32_t w = 0u;
+      if (valid && pix < Cfg::PW) {
+        const int64_t src = gather ? gather[(int64_t)seed * rows + row] : row;
+        w = __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + pix);
+      }
+      so[sl][pix] = w;
+    }
+    __syncthreads();
+    // ---- phase A: per-pixel LN backward
+    {
+      float acc[CONV_O];
+      conv_pixel<C>(so[sl], ws, cb, y, x, acc);
+      float mean, rstd;
+      ln16(acc, mean, rstd);
+      float dz[CONV_O];
+      if (valid) {
+        const float4* __restrict__ dyp =
+            reinterpret_cast<const float4*>(DY1 + ((int64_t)seed * rows + row) * FLAT_CNN + pix * CONV_O);
+        float dy[CONV_O];
+#pragma unroll
+        for (int o4 = 0; o4 < CONV_O / 4; ++o4) {
+          const float4 v = __ldg(dyp + o4);
+          dy[4 * o4] = v.x; dy[4 * o4 + 1] = v.y; dy[4 * o4 + 2] = v.z; dy[4 * o4 + 3] = v.w;
+        }
+        float m1 = 0.f, m2 = 0.f, xh[CONV_O], dxh[CONV_O];
+#pragma unroll
+        for (int o = 0; o < CONV_O; ++o) {
+          xh[o] = (acc[o] - mean) * rstd;
+          a_dsc[o] = fmaf(dy[o], xh[o], a_dsc[o]);
+          a_dbi[o] += dy[o];
+          dxh[o] = dy[o] * sc[o];
+          m1 += dxh[o];
+          m2 = fmaf(dxh[o], xh[o], m2);
+        }
+        m1 *= (1.0f / CONV_O);
+        m2 *= (1.0f / CONV_O);
+#pragma unroll
+        for (int o = 0; o < CONV_O; ++o) {
+          dz[o] = rstd * (dxh[o] - m1 - xh[o] * m2);
+          a_dcb[o] += dz[o];
+        }
+      } else {
+#pragma unroll
+        for (int o = 0; o < CONV_O; ++o) dz[o] = 0.f;
+      }
+#pragma unroll
+      for (int o4 = 0; o4 < CONV_O / 4; ++o4)
+        *reinterpret_cast<float4*>(&sdz[tid * SDZ_LD + 4 * o4]) =
+            make_float4(dz[4 * o4], dz[4 * o4 + 1], dz[4 * o4 + 2], dz[4 * o4 + 3]);
+    }
+    __syncthreads();
+    // ---- phase B: dWc[tap][:] += x[pixel + tap] * dz[pixel][:]
+    if (b_active) {
+      for (int e = grp; e < 256; e += G) {
+        const int esl = e >> 6, epix = e & 63;
+        const int f = (((epix >> 3) + t_di) * 10 + (epix & 7) + t_dj) * C + t_c;
+        if ((so[esl][f >> 5] >> (f & 31)) & 1u) {
+#pragma unroll
+          for (int o4 = 0; o4 < CONV_O / 4; ++o4) {
+            const float4 v = *reinterpret_cast<const float4*>(&sdz[e * SDZ_LD + 4 * o4]);
+            wacc[4 * o4] += v.x; wacc[4 * o4 + 1] += v.y; wacc[4 * o4 + 2] += v.z; wacc[4 * o4 + 3] += v.w;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- reduce and publish
+  float* s_w = sdz;  // reuse: [TAPS*16]
+  for (int i = tid; i < TAPS * CONV_O; i += 256) s_w[i] = 0.f;
+  __syncthreads();
+  if (b_active) {
+    const float inv255 = 1.0f / 255.0f;
+#pragma unroll
+    for (int o = 0; o < CONV_O; ++o) atomicAdd(&s_w[tap * CONV_O + o], wacc[o] * inv255);
+  }
+#pragma unroll
+  for (int o = 0; o < CONV_O; ++o) {
+    float v0 = a_dsc[o], v1 = a_dbi[o], v2 = a_dcb[o];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, s);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, s);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, s);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(&s_red[o], v0);
+      atomicAdd(&s_red[CONV_O + o], v1);
+      atomicAdd(&s_red[2 * CONV_O + o], v2);
+    }
+  }
+  __syncthreads();
+  float* __restrict__ g = grads + (int64_t)seed * P;
+  for (int i = tid; i < TAPS * CONV_O; i += 256) atomicAdd(g + L.conv_w + i, s_w[i]);
+  if (tid < CONV_O) {
+    atomicAdd(g + L.ln0_scale + tid, s_red[tid]);
+    atomicAdd(g + L.ln0_bias + tid, s_red[CONV_O + tid]);
+    atomicAdd(g + L.conv_b + tid, s_red[2 * CONV_O + tid]);
+  }
+}
+
+// MLP input gather (minibatch rows of float obs) + dummy BatchNorm sums.
+__global__ void gather_rows_kernel(const float* __restrict__ obs, int64_t obs_rows_per_seed,
+                                   const int32_t* __restrict__ gather, float* __restrict__ out,
+                                   float* __restrict__ bn_sums, int rows, int D) {
+  const int seed = blockIdx.y;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (int64_t)rows * D) return;
+  const int r = (int)(g / D), j = (int)(g - (int64_t)r * D);
+  const int64_t src = gather ? gather[(int64_t)seed * rows + r] : r;
+  const float v = __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * D + j);
+  out[((int64_t)seed * rows + r) * D + j] = v;
+  if (bn_sums) {
+    atomicAdd(bn_sums + (int64_t)seed * 2 * D + j, v);
+    atomicAdd(bn_sums + (int64_t)seed * 2 * D + D + j, v * v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host-side orchestration
+// ---------------------------------------------------------------------------
+struct Workspace {
+  // CNN
+  float *h1, *h2, *xhat2, *rstd2, *dz2;
+  // MLP
+  float *xg, *h0, *xhat0, *rstd0, *hh1, *xhat1, *rstd1, *dzl, *dh0;
+};
+
+static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* base, Workspace* w) {
+  int64_t off = 0;
+  auto take = [&](int64_t nfloats) -> float* {
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += (nfloats * 4 + 255) / 256 * 256;
+    return p;
+  };
+  const int64_t R = (int64_t)S * rows;
+  Workspace tmp;
+  Workspace* ww = w ? w : &tmp;
+  if (d->kind == PQN_NET_MINATAR_CNN) {
+    ww->h1 = take(R * FLAT_CNN);
+    ww->h2 = take(R * HID_CNN);
+    ww->xhat2 = take(R * HID_CNN);
+    ww->rstd2 = take(R);
+    ww->dz2 = take(R * HID_CNN);
+  } else {
+    const int H = d->hidden;
+    ww->xg = take(R * d->in_c);
+    ww->h0 = take(R * H);
+    ww->xhat0 = take(R * H);
+    ww->rstd0 = take(R);
+    ww->hh1 = take(R * H);
+    ww->xhat1 = take(R * H);
+    ww->rstd1 = take(R);
+    ww->dzl = take(R * H);
+    ww->dh0 = take(R * H);
+  }
+  return off;
+}
+
+template <int MODE>
+static void launch_dense(int BN, dim3 grid, cudaStream_t st, const float* X, int64_t xss, int ldx, const float* params,
+                         int64_t P, int64_t ow, int64_t ob, int64_t osc, int64_t obi, int64_t ohw, int64_t ohb, int A,
+                         float* H, float* XH, float* RS, float* Q, int rows, int K) {
+  if (BN == 128)
+    dense_fwd_kernel<128, MODE><<<grid, GT, 0, st>>>(X, xss, ldx, params, P, ow, ob, osc, obi, ohw, ohb, A, H, XH, RS, Q, rows, K);
+  else
+    dense_fwd_kernel<256, MODE><<<grid, GT, 0, st>>>(X, xss, ldx, params, P, ow, ob, osc, obi, ohw, ohb, A, H, XH, RS, Q, rows, K);
+}
+
+static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+template <bool TRAIN>
+static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
+                           const float* params, int64_t P, const pqn_net_layout_t& L, float* h1, float* bn, int rows) {
+  switch (C) {
+    case 4: conv_fwd_kernel<4, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); break;
+    case 6: conv_fwd_kernel<6, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); break;
+    case 7: conv_fwd_kernel<7, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); break;
+    case 10: conv_fwd_kernel<10, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); break;
+    default: return -1;
+  }
+  return 0;
+}
+
+static int wgrad_splits(int tiles, int S, int rows) {
+  int s = (2 * 148 + tiles * S - 1) / (tiles * S);
+  const int maxs = (rows + 255) / 256;
+  if (s > maxs) s = maxs;
+  if (s < 1) s = 1;
+  return s;
+}
+
+}  // namespace pqn
+
+using namespace pqn;
+
+extern "C" {
+
+int pqn_net_layout(const pqn_net_desc_t* d, pqn_net_layout_t* out) {
+  int rc = check_desc(d, "pqn_net_layout");
+  if (rc) return rc;
+  if (!out) return set_error(PQN_E_INVALID, "pqn_net_layout: out is NULL");
+  make_layout(d, out);
+  return PQN_OK;
+}
+
+int64_t pqn_net_workspace_bytes(const pqn_net_desc_t* d, int32_t S, int64_t rows) {
+  if (check_desc(d, "pqn_net_workspace_bytes")) return -1;
+  return carve(d, S, rows, nullptr, nullptr);
+}
+
+int pqn_qnet_forward(const pqn_net_desc_t* d, const float* params, const void* obs, const int32_t* gather,
+                     int64_t obs_rows_per_seed, float* q, int32_t S, int64_t rows, void* workspace, void* stream) {
+  int rc = check_desc(d, "pqn_qnet_forward");
+  if (rc) return rc;
+  if (!params || !obs || !q || !workspace || S <= 0 || rows <= 0 || S > 65535)
+    return set_error(PQN_E_INVALID, "pqn_qnet_forward: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  pqn_net_layout_t L;
+  make_layout(d, &L);
+  Workspace w;
+  carve(d, S, rows, (char*)workspace, &w);
+  const int A = d->num_actions;
+  if (d->kind == PQN_NET_MINATAR_CNN) {
+    launch_conv_fwd<false>(d->in_c, dim3(cdiv(rows, 4), S), st, (const uint32_t*)obs, obs_rows_per_seed, gather, params,
+                           L.total, L, w.h1, nullptr, (int)rows);
+    launch_dense<2>(128, dim3(cdiv(rows, 128), S), st, w.h1, rows * FLAT_CNN, FLAT_CNN, params, L.total, L.d0_w, L.d0_b,
+                    L.ln1_scale, L.ln1_bias, L.head_w, L.head_b, A, nullptr, nullptr, nullptr, q, (int)rows, FLAT_CNN);
+  } else {
+    const int D = d->in_c, H = d->hidden;
+    const float* x = (const float*)obs;
+    int64_t xss = obs_rows_per_seed * D;
+    if (gather) {
+      gather_rows_kernel<<<dim3(cdiv(rows * D, 256), S), 256, 0, st>>>(x, obs_rows_per_seed, gather, w.xg, nullptr,
+                                                                      (int)rows, D);
+      x = w.xg;
+      xss = rows * D;
+    }
+    const int BM = (H == 128) ? 128 : 64;
+    if (d->layers == 1) {
+      launch_dense<2>(H, dim3(cdiv(rows, BM), S), st, x, xss, D, params, L.total, L.d0_w, L.d0_b, L.ln0_scale,
+                      L.ln0_bias, L.head_w, L.head_b, A, nullptr, nullptr, nullptr, q, (int)rows, D);
+    } else {
+      launch_dense<0>(H, dim3(cdiv(rows, BM), S), st, x, xss, D, params, L.total, L.d0_w, L.d0_b, L.ln0_scale,
+                      L.ln0_bias, 0, 0, A, w.h0, nullptr, nullptr, nullptr, (int)rows, D);
+      launch_dense<2>(H, dim3(cdiv(rows, BM), S), st, w.h0, rows * H, H, params, L.total, L.d1_w, L.d1_b, L.ln1_scale,
+                      L.ln1_bias, L.head_w, L.head_b, A, nullptr, nullptr, nullptr, q, (int)rows, H);
+    }
+  }
+  return check_launch("pqn_qnet_forward");
+}
+
+int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void* obs, const int32_t* gather,
+                       int64_t obs_rows_per_seed, const int32_t* action, const float* target,
+                       int64_t tr_rows_per_seed, float* grads, float* loss_sum, float* qsa_sum, float* bn_sums,
+                       int32_t S, int64_t rows, void* workspace, void* stream) {
+  int rc = check_desc(d, "pqn_qnet_loss_grad");
+  if (rc) return rc;
+  if (!params || !obs || !action || !target || !grads || !loss_sum || !qsa_sum || !workspace || S <= 0 || rows <= 0 ||
+      S > 65535)
+    return set_error(PQN_E_INVALID, "pqn_qnet_loss_grad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  pqn_net_layout_t L;
+  make_layout(d, &L);
+  const int64_t P = L.total;
+  Workspace w;
+  carve(d, S, rows, (char*)workspace, &w);
+  const int A = d->num_actions;
+  const int R = (int)rows;
+  if (cudaMemsetAsync(grads, 0, (size_t)S * P * sizeof(float), st) != cudaSuccess)
+    return check_launch("pqn_qnet_loss_grad(memset)");
+
+  if (d->kind == PQN_NET_MINATAR_CNN) {
+    const uint32_t* ob = (const uint32_t*)obs;
+    launch_conv_fwd<true>(d->in_c, dim3(cdiv(rows, 4), S), st, ob, obs_rows_per_seed, gather, params, P, L, w.h1,
+                          bn_sums, R);
+    launch_dense<1>(128, dim3(cdiv(rows, 128), S), st, w.h1, rows * FLAT_CNN, FLAT_CNN, params, P, L.d0_w, L.d0_b,
+                    L.ln1_scale, L.ln1_bias, 0, 0, A, w.h2, w.xhat2, w.rstd2, nullptr, R, FLAT_CNN);
+    const size_t sm = (size_t)(3 * 128 + A * 128 + A + 2) * sizeof(float);
+    row_bwd_kernel<128, true><<<dim3(cdiv(rows, RB_ROWS), S), 256, sm, st>>>(
+        w.h2, w.xhat2, w.rstd2, nullptr, w.dz2, params, grads, P, L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d0_b,
+        L.head_w, L.head_b, A, gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, R);
+    const int splits = wgrad_splits(FLAT_CNN / 128, S, R);
+    wgrad_kernel<<<dim3(FLAT_CNN / 128, 1, S * splits), GT, 0, st>>>(w.h1, rows * FLAT_CNN, FLAT_CNN, w.dz2,
+                                                                     rows * HID_CNN, HID_CNN, grads, P, L.d0_w, R,
+                                                                     FLAT_CNN, splits);
+    dgrad_kernel<<<dim3(cdiv(rows, 128), FLAT_CNN / 128, S), GT, 0, st>>>(w.dz2, rows * HID_CNN, HID_CNN, params, P,
+                                                                          L.d0_w, w.h1, w.h1, rows * FLAT_CNN, R,
+                                                                          FLAT_CNN);
+    dim3 cg(cdiv(rows, CONV_BWD_SPB), S);
+    switch (d->in_c) {
+      case 4: conv_bwd_kernel<4><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
+      case 6: conv_bwd_kernel<6><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
+      case 7: conv_bwd_kernel<7><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
+      case 10: conv_bwd_kernel<10><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
+    }
+  } else {
+    const int D = d->in_c, H = d->hidden;
+    const int BM = (H == 128) ? 128 : 64;
+    gather_rows_kernel<<<dim3(cdiv(rows * D, 256), S), 256, 0, st>>>((const float*)obs, obs_rows_per_seed, gather, w.xg,
+                                                                    bn_sums, R, D);
+    launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.xg, rows * D, D, params, P, L.d0_w, L.d0_b, L.ln0_scale,
+                    L.ln0_bias, 0, 0, A, w.h0, w.xhat0, w.rstd0, nullptr, R, D);
+    const size_t smh = (size_t)(3 * H + A * H + A + 2) * sizeof(float);
+    const size_t sml = (size_t)(3 * H) * sizeof(float);
+    dim3 rg(cdiv(rows, RB_ROWS), S);
+    if (d->layers == 2) {
+      launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.h0, rows * H, H, params, P, L.d1_w, L.d1_b, L.ln1_scale,
+                      L.ln1_bias, 0, 0, A, w.hh1, w.xhat1, w.rstd1, nullptr, R, H);
+      if (H == 128)
+        row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, params, grads, P,
+                                                        L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
+                                                        L.head_b, A, gather, action, target, tr_rows_per_seed,
+                                                        loss_sum, qsa_sum, R);
+      else
+        row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, params, grads, P,
+                                                        L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
+                                                        L.head_b, A, gather, action, target, tr_rows_per_seed,
+                                                        loss_sum, qsa_sum, R);
+      const int tiles = (H / 128) * (H / 128);
+      const int splits = wgrad_splits(tiles, S, R);
+      wgrad_kernel<<<dim3(H / 128, H / 128, S * splits), GT, 0, st>>>(w.h0, rows * H, H, w.dzl, rows * H, H, grads, P,
+                                                                      L.d1_w, R, H, splits);
+      dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(w.dzl, rows * H, H, params, P, L.d1_w, w.h0,
+                                                                     w.dh0, rows * H, R, H);
+      if (H == 128)
+        row_bwd_kernel<128, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, params, grads, P,
+                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
+                                                         nullptr, nullptr, nullptr, 0, nullptr, nullptr, R);
+      else
+        row_bwd_kernel<256, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, params, grads, P,
+                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
+                                                         nullptr, nullptr, nullptr, 0, nullptr, nullptr, R);
+      const int sp0 = wgrad_splits(H / 128, S, R);
+      wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dh0, rows * H, H, grads,
+                                                                        P, L.d0_w, R, D, sp0);
+    } else {
+      if (H == 128)
+        row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, params, grads, P,
+                                                        L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
+                                                        L.head_b, A, gather, action, target, tr_rows_per_seed,
+                                                        loss_sum, qsa_sum, R);
+      else
+        row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, params, grads, P,
+                                                        L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
+                                                        L.head_b, A, gather, action, target, tr_rows_per_seed,
+                                                        loss_sum, qsa_sum, R);
+      const int sp0 = wgrad_splits(H / 128, S, R);
+      wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dzl, rows * H, H, grads,
+                                                                        P, L.d0_w, R, D, sp0);
+    }
+  }
+  return check_launch("pqn_qnet_loss_grad");
+}
+
+}  // extern "C"

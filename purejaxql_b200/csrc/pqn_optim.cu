@@ -1,0 +1,137 @@
+// optax.chain(clip_by_global_norm(max_norm), radam(lr)) + apply_updates, batched
+// over S independent seeds (one flat parameter block per seed).
+//
+// Reference: purejaxql/pqn_minatar.py:159-162 (optimizer wiring), :292
+// (apply_gradients), :140-147 (linear lr schedule).  optax defaults restated
+// (third party): radam b1=.9 b2=.999 eps=1e-8 eps_root=0 threshold=5;
+//   clip: g <- g                     if ||g|| <  max_norm
+//         g <- (g / ||g||) * max_norm otherwise          (global norm over ALL leaves)
+//   mu <- b1 mu + (1-b1) g ; nu <- b2 nu + (1-b2) g^2 ; t <- t+1
+//   mu_hat = mu / (1-b1^t) ; nu_hat = nu / (1-b2^t)
+//   rho_t >= 5 : u = r_t * mu_hat / (sqrt(nu_hat) + eps)   else  u = mu_hat
+//   p <- p - lr_t * u
+// The per-step scalars (lr_t, 1-b1^t, 1-b2^t, r_t or 0) come from a device table
+// indexed by a device step counter so that the whole update can live in a CUDA graph.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pqn_b200.h"
+#include "api_common.h"
+
+namespace pqn {
+
+constexpr int NORM_BLOCKS = 64;  // blocks per seed in the squared-norm reduction
+
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ grads, int64_t P,
+                                                     float* __restrict__ gn) {
+  const int seed = blockIdx.y;
+  const float4* __restrict__ g = reinterpret_cast<const float4*>(grads + (int64_t)seed * P);
+  const int64_t n4 = P / 4;  // P is a multiple of 4 by construction of the layout
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 v = __ldg(g + i);
+    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(gn + seed, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) radam_kernel(float* __restrict__ params, const float* __restrict__ grads,
+                                                    float* __restrict__ mu, float* __restrict__ nu,
+                                                    const float* __restrict__ sched,
+                                                    const int32_t* __restrict__ step_counter,
+                                                    const float* __restrict__ gn, int64_t P, float max_norm, float b1,
+                                                    float b2, float eps) {
+  const int seed = blockIdx.y;
+  const int64_t i4 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i4 * 4 >= P) return;
+  const int t = step_counter[0];
+  const float lr = __ldg(sched + 4 * t + 0);
+  const float bc1 = __ldg(sched + 4 * t + 1);
+  const float bc2 = __ldg(sched + 4 * t + 2);
+  const float rect = __ldg(sched + 4 * t + 3);
+  const float g_norm = sqrtf(gn[seed]);
+  const bool no_clip = g_norm < max_norm;
+  const int64_t off = (int64_t)seed * P + i4 * 4;
+  float4 p = *reinterpret_cast<float4*>(params + off);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(grads + off));
+  float4 m = *reinterpret_cast<float4*>(mu + off);
+  float4 v = *reinterpret_cast<float4*>(nu + off);
+  float* pp = reinterpret_cast<float*>(&p);
+  const float* gp = reinterpret_cast<const float*>(&g);
+  float* mp = reinterpret_cast<float*>(&m);
+  float* vp = reinterpret_cast<float*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float gc = no_clip ? gp[j] : (gp[j] / g_norm) * max_norm;
+    mp[j] = b1 * mp[j] + (1.0f - b1) * gc;
+    vp[j] = b2 * vp[j] + (1.0f - b2) * (gc * gc);
+    const float mhat = mp[j] / bc1;
+    float u;
+    if (rect > 0.f) u = rect * mhat / (sqrtf(vp[j] / bc2) + eps);
+    else u = mhat;
+    pp[j] = pp[j] - lr * u;
+  }
+  *reinterpret_cast<float4*>(params + off) = p;
+  *reinterpret_cast<float4*>(mu + off) = m;
+  *reinterpret_cast<float4*>(nu + off) = v;
+}
+
+__global__ void advance_kernel(int32_t* step_counter) { step_counter[0] += 1; }
+
+__global__ void bn_update_kernel(float* __restrict__ batch_stats, float* __restrict__ bn_sums, int F, float count,
+                                 float momentum) {
+  const int seed = blockIdx.x;
+  const int f = threadIdx.x;
+  if (f >= F) return;
+  float* bs = batch_stats + (int64_t)seed * 2 * F;
+  float* sm = bn_sums + (int64_t)seed * 2 * F;
+  const float mean = sm[f] / count;
+  const float var = fmaxf(sm[F + f] / count - mean * mean, 0.f);
+  bs[f] = momentum * bs[f] + (1.0f - momentum) * mean;
+  bs[F + f] = momentum * bs[F + f] + (1.0f - momentum) * var;
+  sm[f] = 0.f;
+  sm[F + f] = 0.f;
+}
+
+}  // namespace pqn
+
+using namespace pqn;
+
+extern "C" {
+
+int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu, const float* sched,
+                        int32_t* step_counter, float* gnorm_scratch, int32_t S, int64_t P, float max_norm, float b1,
+                        float b2, float eps, void* stream) {
+  if (!params || !grads || !mu || !nu || !sched || !step_counter || !gnorm_scratch || S <= 0 || P <= 0 || (P & 3) ||
+      S > 65535)
+    return set_error(PQN_E_INVALID, "pqn_radam_clip_step: bad argument (P must be a multiple of 4)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(gnorm_scratch, 0, (size_t)S * sizeof(float), st) != cudaSuccess)
+    return check_launch("pqn_radam_clip_step(memset)");
+  sqnorm_kernel<<<dim3(NORM_BLOCKS, S), 256, 0, st>>>(grads, P, gnorm_scratch);
+  const unsigned nb = (unsigned)((P / 4 + 255) / 256);
+  radam_kernel<<<dim3(nb, S), 256, 0, st>>>(params, grads, mu, nu, sched, step_counter, gnorm_scratch, P, max_norm, b1,
+                                            b2, eps);
+  advance_kernel<<<1, 1, 0, st>>>(step_counter);
+  return check_launch("pqn_radam_clip_step");
+}
+
+int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F, float count, float momentum,
+                        void* stream) {
+  if (!batch_stats || !bn_sums || S <= 0 || F <= 0 || F > 1024 || count <= 0.f)
+    return set_error(PQN_E_INVALID, "pqn_bn_stats_update: bad argument");
+  bn_update_kernel<<<S, ((F + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(batch_stats, bn_sums, F, count, momentum);
+  return check_launch("pqn_bn_stats_update");
+}
+
+}  // extern "C"

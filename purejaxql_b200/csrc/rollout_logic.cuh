@@ -36,13 +36,14 @@ PQN_HD int eps_greedy_one(Key k, const float* __restrict__ q, int A, float eps, 
 }
 
 // Q(lambda) for one env: bootstrap from q_last, reverse scan over T
-// (purejaxql/pqn_minatar.py:227-260).
+// (purejaxql/pqn_minatar.py:227-260).  reward/done/maxq/targets are [T][N] views, env column i.
 PQN_HD void qlambda_one(const float* __restrict__ reward, const uint8_t* __restrict__ done,
                         const float* __restrict__ maxq, const float* __restrict__ q_last,
                         float* __restrict__ targets, int T, int64_t N, int A, float gamma, float lambda,
                         int64_t i) {
-  float lq = q_last[i * A];
-  for (int a = 1; a < A; ++a) lq = lq > q_last[i * A + a] ? lq : q_last[i * A + a];
+  // q_last points at this env's A bootstrap q-values
+  float lq = q_last[0];
+  for (int a = 1; a < A; ++a) lq = lq > q_last[a] ? lq : q_last[a];
   const int64_t last = (int64_t)(T - 1) * N + i;
   const float dl = done[last] ? 1.f : 0.f;
   float next_q = lq * (1.f - dl);                       // :252

@@ -1,0 +1,364 @@
+"""The PQN training program: ``make_train(config) -> train(rngs)``.
+
+Host-side restatement of ``make_train`` in purejaxql/pqn_minatar.py:89-431 and
+purejaxql/pqn_gymnax.py:78-424 (identical modulo the network and the flatten
+wrapper), with the seed axis taken natively — the reference wraps ``train`` in
+``jax.jit(jax.vmap(...))`` over ``rngs[S,2]`` (pqn_minatar.py:459-461); here
+``train(rngs)`` receives the whole ``[S,2]`` key array and every kernel launch
+covers all S seeds.
+
+All compute is libpqn_b200 kernels (include/pqn_b200.h).  This module only
+allocates buffers (torch), walks the reference's PRNG key chain (SURVEY
+Appendix B) and sequences the launches:
+
+  per update (``_update_step``, :176-369):
+    rollout   T x [ Q-network forward ; fused eps-greedy + env step + stores ]
+    bootstrap forward on the last obs ; Q(lambda) reverse scan
+    epochs x minibatches x [ permutation gather ; loss/grad ; clip+RAdam ; BN stats ]
+"""
+from __future__ import annotations
+
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _lib, envs, jaxrandom as jr
+from .networks import NET_CNN, NET_MLP, QNetworkSpec
+
+INFO_KEYS = ("returned_episode_returns", "returned_episode_lengths", "timestep", "returned_episode", "discount")
+
+
+def _f32(x):
+    return np.float32(x)
+
+
+def linear_schedule(init, end, transition_steps, count):
+    """optax.linear_schedule evaluated in float32 (pqn_minatar.py:134-146)."""
+    if transition_steps <= 0:
+        return _f32(init)
+    c = np.clip(_f32(count), _f32(0), _f32(transition_steps))
+    frac = _f32(1) - c / _f32(transition_steps)
+    return _f32(_f32(init - end) * frac + _f32(end))
+
+
+def radam_schedule_table(num_steps, lr_fn, b1=0.9, b2=0.999, threshold=5.0):
+    """[num_steps,4] float32 rows (lr_t, 1-b1^t, 1-b2^t, rect_t or 0) of
+    optax.scale_by_radam + scale_by_learning_rate for optimizer steps t=1.."""
+    tab = np.zeros((max(num_steps, 1), 4), np.float32)
+    ro_inf = 2.0 / (1.0 - b2) - 1.0
+    for i in range(num_steps):
+        t = i + 1
+        b2t = b2 ** t
+        ro = ro_inf - 2.0 * t * b2t / (1.0 - b2t)
+        rect = 0.0
+        if ro >= threshold:
+            rect = float(np.sqrt((ro - 4) * (ro - 2) * ro_inf / ((ro_inf - 4) * (ro_inf - 2) * ro)))
+        tab[i] = (lr_fn(i), 1.0 - b1 ** t, 1.0 - b2t, rect)
+    return tab
+
+
+class TrainState(SimpleNamespace):
+    """Mirror of CustomTrainState (pqn_minatar.py:82-86): params / batch_stats
+    nested dicts with a leading seed axis, plus timesteps, n_updates, grad_steps
+    and the optimizer moments."""
+
+
+class PQNEngine:
+    def __init__(self, config: dict, network: str, flatten_obs: bool, device=None):
+        self.cfg = config
+        self.device = torch.device(device or "cuda")
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise _lib.PqnError("purejaxql_b200 needs a CUDA device: there is no CPU fallback")
+        _lib.lib()
+        c = config
+        if c.get("NORM_TYPE", "layer_norm") != "layer_norm" or c.get("NORM_INPUT", False):
+            raise NotImplementedError("only NORM_TYPE=layer_norm, NORM_INPUT=False are built (shipped defaults)")
+        self.rng_mode = int(c.get("JAX_THREEFRY_PARTITIONABLE", 0))
+        self.env, self.env_params = envs.make(c["ENV_NAME"], flatten_obs=flatten_obs, rng_mode=self.rng_mode)
+        self.max_steps = int(self.env_params.max_steps_in_episode)
+        self.T = int(c["NUM_STEPS"])
+        self.E = int(c["NUM_ENVS"])
+        self.NU = int(c["NUM_UPDATES"])
+        self.A = self.env.num_actions
+        self.binary = self.env.binary_obs
+        if network == "cnn":
+            if not self.binary:
+                raise ValueError("the MinAtar CNN needs a (10,10,C) binary-observation env")
+            self.spec = QNetworkSpec(NET_CNN, self.env.info.obs_shape[2], self.A)
+            self.row_words = self.env.packed_obs_words          # int32 words per obs row
+            self.obs_dtype = torch.int32
+        else:
+            self.spec = QNetworkSpec(NET_MLP, self.env.obs_dim, self.A, int(c.get("HIDDEN_SIZE", 128)),
+                                     int(c.get("NUM_LAYERS", 2)))
+            if self.binary:
+                raise NotImplementedError("MLP on packed MinAtar observations is not built")
+            self.row_words = self.env.obs_dim
+            self.obs_dtype = torch.float32
+        self.nmb = int(c["NUM_MINIBATCHES"])
+        self.epochs = int(c["NUM_EPOCHS"])
+        self.mb = self.T * self.E // self.nmb
+        self.gamma = float(c["GAMMA"])
+        self.lam = float(c["LAMBDA"])
+        self.rew_scale = float(c.get("REW_SCALE", 1))
+        self.test = bool(c.get("TEST_DURING_TRAINING", False))
+        self._ws = None
+
+    # ------------------------------------------------------------------ #
+    def _workspace(self, S, rows):
+        need = int(_lib.lib().pqn_net_workspace_bytes(self.spec.desc, S, rows))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def forward(self, params, obs, S, rows, obs_rows_per_seed, q_out, gather=None):
+        ws = self._workspace(S, rows)
+        _lib.check(_lib.lib().pqn_qnet_forward(self.spec.desc, _lib.p(params), _lib.raw(obs), _lib.p(gather),
+                                               obs_rows_per_seed, _lib.p(q_out), S, rows, _lib.p(ws),
+                                               _lib.stream_ptr()), "pqn_qnet_forward")
+        return q_out
+
+    # ------------------------------------------------------------------ #
+    def train(self, rngs):
+        c, dev, L = self.cfg, self.device, _lib.lib()
+        T, E, A, NU = self.T, self.E, self.A, self.NU
+        keys = jr.as_key_tensor(rngs, dev)
+        assert keys.dim() == 2 and keys.shape[1] == 2, "train(rngs) takes the [NUM_SEEDS, 2] key array"
+        S = keys.shape[0]
+        mode = self.rng_mode
+        spec, P = self.spec, self.spec.total
+        W = self.row_words
+
+        # ---- schedules (pqn_minatar.py:134-147)
+        nud = c["NUM_UPDATES_DECAY"]
+        eps_table = torch.tensor([linear_schedule(c["EPS_START"], c["EPS_FINISH"], c["EPS_DECAY"] * nud, n)
+                                  for n in range(max(NU, 1))], dtype=torch.float32, device=dev)
+        total_grad_steps = NU * self.nmb * self.epochs
+        if c.get("LR_LINEAR_DECAY", False):
+            lr_fn = lambda i: linear_schedule(c["LR"], 1e-20, nud * self.nmb * self.epochs, i)
+        else:
+            lr_fn = lambda i: _f32(c["LR"])
+        sched = torch.from_numpy(radam_schedule_table(total_grad_steps, lr_fn)).to(dev)
+
+        # ---- key chain (pqn_minatar.py:172-173,415-423)
+        k = jr.split(keys, 2, mode)
+        K1 = k[:, 0].contiguous()                                   # :172 rng (also the init key, :173)
+        params = spec.init(jr.to_numpy_u32(K1), dev)                # :156-170
+        mu = torch.zeros_like(params)
+        nu = torch.zeros_like(params)
+        grads = torch.zeros_like(params)
+        F = spec.in_c
+        batch_stats = torch.cat([torch.zeros(S, F), torch.ones(S, F)], 1).to(dev).contiguous()  # mean 0, var 1
+        bn_sums = torch.zeros(S, 2 * F, device=dev)
+        step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        gnorm = torch.zeros(S, device=dev)
+
+        k = jr.split(K1, 2, mode)
+        K2, kT0 = k[:, 0].contiguous(), k[:, 1].contiguous()        # :415
+        test_metrics = self.get_test_metrics(params, kT0) if self.test else None
+        k = jr.split(K2, 2, mode)
+        K3, kR = k[:, 0].contiguous(), k[:, 1].contiguous()         # :418
+        # ---- rollout buffers: obs rows [S][T+1][E], transitions [S][T][E]
+        obs_buf = torch.zeros((S, T + 1, E, W), dtype=self.obs_dtype, device=dev)
+        act_buf = torch.zeros((S, T, E), dtype=torch.int32, device=dev)
+        rew_buf = torch.zeros((S, T, E), dtype=torch.float32, device=dev)
+        done_buf = torch.zeros((S, T, E), dtype=torch.uint8, device=dev)
+        maxq_buf = torch.zeros((S, T, E), dtype=torch.float32, device=dev)
+        targets = torch.zeros((S, T, E), dtype=torch.float32, device=dev)
+        q_buf = torch.zeros((S * E, A), dtype=torch.float32, device=dev)
+        info_sums = torch.zeros((S, 5), dtype=torch.float64, device=dev)
+        loss_sum = torch.zeros(S, device=dev)
+        qsa_sum = torch.zeros(S, device=dev)
+        step_keys = torch.zeros((T, S, 2, 2), dtype=torch.int32, device=dev)
+        eps_dev = torch.zeros(1, device=dev)
+        # ---- reset (vmap_reset, :107-109,419)
+        reset_keys = jr.split(kR, E, mode).reshape(S * E, 2).contiguous()
+        state = torch.empty((self.env.state_words, S * E), dtype=torch.int32, device=dev)
+        _lib.check(L.pqn_env_reset(self.env.env_id, _lib.p(reset_keys), _lib.p(state), None, S * E, self.max_steps,
+                                   mode, _lib.stream_ptr()), "pqn_env_reset")
+        self._write_obs(state, obs_buf, 0, S)
+        rng = jr.split(K3, 2, mode)[:, 1].contiguous()              # :422-423 runner rng
+
+        metric_names = ["env_step", "update_steps", "env_frame", "grad_steps", "td_loss", "qvals", *INFO_KEYS]
+        metrics = {m: torch.zeros((S, max(NU, 1)), dtype=torch.float64, device=dev) for m in metric_names}
+        test_hist = None
+        test_every = None
+        if self.test:
+            test_every = int(NU * c["TEST_INTERVAL"])
+            test_hist = {kk: torch.zeros((S, max(NU, 1)), dtype=torch.float64, device=dev) for kk in INFO_KEYS}
+        obs_channels = self.env.observation_space().shape[-1]
+        sp = _lib.stream_ptr
+        timesteps = 0
+        grad_steps = 0
+        seed_stride_obs = (T + 1) * E
+        seed_stride_tr = T * E
+        perm_view = None
+
+        for n_updates in range(NU):
+            # ================= SAMPLE PHASE (:181-219)
+            eps_dev.copy_(eps_table[n_updates:n_updates + 1])
+            carry = jr.split(rng, 2, mode)[:, 1].contiguous()        # :213  `_rng`
+            _lib.check(L.pqn_rollout_keys(_lib.p(carry), _lib.p(step_keys), S, T, mode, sp()), "pqn_rollout_keys")
+            info_sums.zero_()
+            for t in range(T):
+                self.forward(params, obs_buf[:, t], S, E, seed_stride_obs, q_buf)
+                _lib.check(L.pqn_rollout_act_step(
+                    self.env.env_id, _lib.p(step_keys[t]), _lib.p(q_buf), _lib.p(eps_dev), _lib.p(state),
+                    _lib.raw(obs_buf[:, t + 1]), seed_stride_obs,
+                    _lib.raw(act_buf[:, t]), _lib.raw(rew_buf[:, t]),
+                    _lib.raw(done_buf[:, t]), _lib.raw(maxq_buf[:, t]),
+                    seed_stride_tr, _lib.p(info_sums), 0, S, E, self.max_steps, self.rew_scale, mode, sp()),
+                    "pqn_rollout_act_step")
+            rng = carry                                              # scan's final carry (:214)
+            timesteps += T * E                                       # :222-225
+            # ================= bootstrap + Q(lambda) (:227-260)
+            self.forward(params, obs_buf[:, T], S, E, seed_stride_obs, q_buf)
+            _lib.check(L.pqn_qlambda(_lib.p(rew_buf), _lib.p(done_buf), _lib.p(maxq_buf), _lib.p(q_buf),
+                                     _lib.p(targets), T, S, E, A, self.gamma, self.lam, sp()), "pqn_qlambda")
+            # ================= NETWORKS UPDATE (:263-327)
+            rng = jr.split(rng, 2, mode)[:, 0].contiguous()          # :324
+            loss_sum.zero_()
+            qsa_sum.zero_()
+            ws = self._workspace(S, max(self.mb, E))
+            for _ in range(self.epochs):
+                k = jr.split(rng, 2, mode)                           # :309
+                rng, kperm = k[:, 0].contiguous(), k[:, 1].contiguous()
+                perm = jr.permutation_indices(kperm, T * E, mode)    # :299-315 same perm for every leaf
+                perm_view = perm.view(S, self.nmb, self.mb).transpose(0, 1).contiguous()
+                rng = jr.split(rng, 2, mode)[:, 0].contiguous()      # :317
+                for mbi in range(self.nmb):
+                    _lib.check(L.pqn_qnet_loss_grad(
+                        spec.desc, _lib.p(params), _lib.p(obs_buf), _lib.p(perm_view[mbi]), seed_stride_obs,
+                        _lib.p(act_buf), _lib.p(targets), seed_stride_tr, _lib.p(grads), _lib.p(loss_sum),
+                        _lib.p(qsa_sum), _lib.p(bn_sums), S, self.mb, _lib.p(ws), sp()), "pqn_qnet_loss_grad")
+                    _lib.check(L.pqn_radam_clip_step(_lib.p(params), _lib.p(grads), _lib.p(mu), _lib.p(nu),
+                                                     _lib.p(sched), _lib.p(step_counter), _lib.p(gnorm), S, P,
+                                                     float(c["MAX_GRAD_NORM"]), 0.9, 0.999, 1e-8, sp()),
+                               "pqn_radam_clip_step")
+                    count = float(self.mb * (100 if self.binary else 1))
+                    _lib.check(L.pqn_bn_stats_update(_lib.p(batch_stats), _lib.p(bn_sums), S, F, count, 0.99, sp()),
+                               "pqn_bn_stats_update")
+                    grad_steps += 1
+            # ================= metrics (:329-338)
+            n_done = n_updates + 1
+            col = n_updates
+            metrics["env_step"][:, col] = timesteps
+            metrics["update_steps"][:, col] = n_done
+            metrics["env_frame"][:, col] = timesteps * obs_channels
+            metrics["grad_steps"][:, col] = grad_steps
+            denom = float(self.epochs * self.nmb)
+            metrics["td_loss"][:, col] = loss_sum.double() / denom
+            metrics["qvals"][:, col] = qsa_sum.double() / denom
+            for j, kk in enumerate(INFO_KEYS):
+                metrics[kk][:, col] = info_sums[:, j] / float(T * E)
+            # ================= evaluation (:340-350)
+            if self.test:
+                k = jr.split(rng, 2, mode)
+                rng, kT = k[:, 0].contiguous(), k[:, 1].contiguous()
+                if test_every > 0 and n_done % test_every == 0:
+                    test_metrics = self.get_test_metrics(params, kT)
+                for kk in INFO_KEYS:
+                    test_hist[kk][:, col] = test_metrics[kk]
+            if c.get("WANDB_MODE", "disabled") != "disabled":
+                self._wandb_log(metrics, test_hist, col, jr.to_numpy_u32(keys)[:, 0])
+
+        torch.cuda.synchronize(dev)
+        out_metrics = {m: v[:, :NU].float() if m in ("td_loss", "qvals", *INFO_KEYS) else v[:, :NU].to(torch.int64)
+                       for m, v in metrics.items()}
+        if self.test:
+            out_metrics.update({f"test/{kk}": v[:, :NU].float() for kk, v in test_hist.items()})
+        train_state = TrainState(
+            params=spec.unflatten(params), params_flat=params,
+            batch_stats={"BatchNorm_0": {"mean": batch_stats[:, :F], "var": batch_stats[:, F:]}},
+            opt_state=SimpleNamespace(mu=mu, nu=nu, count=grad_steps),
+            timesteps=torch.full((S,), timesteps, dtype=torch.int64), n_updates=torch.full((S,), NU),
+            grad_steps=torch.full((S,), grad_steps))
+        expl_state = (self._final_obs(obs_buf, S), state)
+        return {"runner_state": (train_state, expl_state, test_metrics, rng), "metrics": out_metrics}
+
+    # ------------------------------------------------------------------ #
+    def _write_obs(self, state, obs_buf, t, S):
+        """obs rows of `state` into obs_buf[:, t] (the reset observation)."""
+        L = _lib.lib()
+        E = obs_buf.shape[2]
+        tmp = torch.empty((S * E, self.row_words), dtype=self.obs_dtype, device=self.device)
+        if self.binary:
+            _lib.check(L.pqn_env_obs_packed(self.env.env_id, _lib.p(state), _lib.p(tmp), S * E, _lib.stream_ptr()),
+                       "pqn_env_obs_packed")
+        else:
+            _lib.check(L.pqn_env_obs(self.env.env_id, _lib.p(state), _lib.p(tmp), S * E, _lib.stream_ptr()),
+                       "pqn_env_obs")
+        obs_buf[:, t] = tmp.view(S, E, self.row_words)
+
+    def _final_obs(self, obs_buf, S):
+        st_obs = obs_buf[:, -1]
+        return st_obs.contiguous()
+
+    # ------------------------------------------------------------------ #
+    def get_test_metrics(self, params, rng):
+        """Greedy evaluation rollout (pqn_minatar.py:371-413), incl. its key quirks:
+        the scan carry starts at the reset key `_rng`, and each step uses the same
+        sub-key for the action keys and the env keys."""
+        c, dev, L, mode = self.cfg, self.device, _lib.lib(), self.rng_mode
+        S = rng.shape[0]
+        N = int(c["TEST_NUM_ENVS"])
+        steps = int(c["TEST_NUM_STEPS"])
+        W, A = self.row_words, self.A
+        k = jr.split(rng, 2, mode)
+        kr = k[:, 1].contiguous()                                    # :396 `_rng`
+        state = torch.empty((self.env.state_words, S * N), dtype=torch.int32, device=dev)
+        _lib.check(L.pqn_env_reset(self.env.env_id, _lib.p(jr.split(kr, N, mode).reshape(S * N, 2).contiguous()),
+                                   _lib.p(state), None, S * N, self.max_steps, mode, _lib.stream_ptr()),
+                   "pqn_env_reset")
+        obs = torch.zeros((S, 2, N, W), dtype=self.obs_dtype, device=dev)   # ping-pong rows
+        self._write_obs(state, obs, 0, S)
+        q = torch.zeros((S * N, A), dtype=torch.float32, device=dev)
+        scratch_i = torch.zeros((S, N), dtype=torch.int32, device=dev)
+        scratch_f = torch.zeros((S, N), dtype=torch.float32, device=dev)
+        scratch_f2 = torch.zeros((S, N), dtype=torch.float32, device=dev)
+        scratch_b = torch.zeros((S, N), dtype=torch.uint8, device=dev)
+        sums = torch.zeros((S, 5), dtype=torch.float64, device=dev)
+        eps = torch.full((1,), float(c["EPS_TEST"]), device=dev)
+        carry = kr                                                   # :399-401
+        for t in range(steps):
+            k = jr.split(carry, 2, mode)                             # :378
+            carry, ku = k[:, 0].contiguous(), k[:, 1].contiguous()
+            sk = torch.stack([ku, ku], 1).contiguous()               # same key for actions and env (:388-393)
+            cur, nxt = t & 1, (t + 1) & 1
+            self.forward(params, obs[:, cur], S, N, 2 * N, q)
+            _lib.check(L.pqn_rollout_act_step(
+                self.env.env_id, _lib.p(sk), _lib.p(q), _lib.p(eps), _lib.p(state),
+                _lib.raw(obs[:, nxt]), 2 * N, _lib.p(scratch_i), _lib.p(scratch_f), _lib.p(scratch_b),
+                _lib.p(scratch_f2), N, _lib.p(sums), 1, S, N, self.max_steps, 1.0, mode, _lib.stream_ptr()),
+                "pqn_rollout_act_step")
+        cnt = sums[:, 3]
+        out = {}
+        for j, kk in enumerate(INFO_KEYS):
+            out[kk] = torch.where(cnt > 0, sums[:, j] / cnt.clamp(min=1), torch.full_like(cnt, float("nan")))
+        return out
+
+    def _wandb_log(self, metrics, test_hist, col, seed_labels):
+        import wandb
+        S = metrics["td_loss"].shape[0]
+        row = {m: v[:, col].mean().item() for m, v in metrics.items()}
+        if test_hist is not None:
+            row.update({f"test/{kk}": v[:, col].nanmean().item() for kk, v in test_hist.items()})
+        if self.cfg.get("WANDB_LOG_ALL_SEEDS", False):
+            for s in range(S):
+                for m, v in metrics.items():
+                    row[f"rng{int(seed_labels[s])}/{m}"] = v[s, col].item()
+        wandb.log(row, step=int(row["update_steps"]))
+
+
+def prepare_config(config: dict, env_max_steps: int, allow_test_steps_override: bool):
+    """The config mutations of make_train (pqn_minatar.py:91-105 / pqn_gymnax.py:80-97)."""
+    config["NUM_UPDATES"] = config["TOTAL_TIMESTEPS"] // config["NUM_STEPS"] // config["NUM_ENVS"]
+    config["NUM_UPDATES_DECAY"] = config["TOTAL_TIMESTEPS_DECAY"] // config["NUM_STEPS"] // config["NUM_ENVS"]
+    assert (config["NUM_STEPS"] * config["NUM_ENVS"]) % config["NUM_MINIBATCHES"] == 0, \
+        "NUM_MINIBATCHES must divide NUM_STEPS*NUM_ENVS"
+    if allow_test_steps_override:
+        config["TEST_NUM_STEPS"] = config.get("TEST_NUM_STEPS", env_max_steps)
+    else:
+        config["TEST_NUM_STEPS"] = env_max_steps
+    return config

@@ -107,6 +107,6 @@ void h_eps_greedy(const uint32_t* keys, const float* q, float eps, int32_t* acti
 }
 void h_qlambda(const float* reward, const uint8_t* done, const float* maxq, const float* q_last, float* targets, int T,
                int64_t N, int A, float gamma, float lambda) {
-  for (int64_t i = 0; i < N; ++i) qlambda_one(reward, done, maxq, q_last, targets, T, N, A, gamma, lambda, i);
+  for (int64_t i = 0; i < N; ++i) qlambda_one(reward, done, maxq, q_last + i * A, targets, T, N, A, gamma, lambda, i);
 }
 }
