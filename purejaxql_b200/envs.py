@@ -125,6 +125,22 @@ def fields_to_state(env_name: str, f: dict) -> torch.Tensor:
     return torch.stack(core + log).contiguous()
 
 
+def pack_observation(obs: torch.Tensor) -> torch.Tensor:
+    """{0,1} observations [N, ...] (e.g. the float32 (10,10,C) rows gymnax returns) ->
+    int32[N, packed_obs_words] rows in the bit layout the CNN kernels read
+    (bit f of a row = element f of the flattened observation; rows padded to 16 bytes)."""
+    n = obs.shape[0]
+    flat = (obs.reshape(n, -1) != 0).to(torch.int64)
+    nb = flat.shape[1]
+    pw = ((nb + 31) // 32 + 3) // 4 * 4
+    padded = torch.zeros((n, pw * 32), dtype=torch.int64, device=obs.device)
+    padded[:, :nb] = flat
+    sh = torch.arange(32, device=obs.device, dtype=torch.int64)
+    words = (padded.view(n, pw, 32) << sh).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)
+    return words.to(torch.int32).contiguous()
+
+
 # --------------------------------------------------------------------------- #
 # the batched environment
 # --------------------------------------------------------------------------- #
