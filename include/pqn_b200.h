@@ -57,6 +57,17 @@ typedef struct pqn_env_info_t {
 const char* pqn_last_error(void);
 int pqn_version(void);
 
+/* ---- launch accounting (bench.py: gpu_launches, per-kernel roofline) -------
+ * pqn_launch_count: kernels launched by this library since load.
+ * pqn_profile_enable(1): bracket every kernel launch with CUDA events on the
+ * launching stream; pqn_profile_read sums elapsed ms / launch counts per kernel
+ * id (arrays of pqn_num_kernels() entries on the host) and optionally resets. */
+long long pqn_launch_count(void);
+int pqn_num_kernels(void);
+const char* pqn_kernel_name(int id);
+int pqn_profile_enable(int on);
+int pqn_profile_read(double* ms_host, long long* count_host, int reset);
+
 /* gymnax.make(name) metadata — pqn_minatar.py:103-105,151,157. */
 int pqn_env_info(int env_id, pqn_env_info_t* out_host);
 

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longlong, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpqn_b200.so")
@@ -38,6 +38,11 @@ class PqnError(RuntimeError):
 _SIGS = {
     "pqn_last_error": (c_char_p, []),
     "pqn_version": (c_int, []),
+    "pqn_launch_count": (c_longlong, []),
+    "pqn_num_kernels": (c_int, []),
+    "pqn_kernel_name": (c_char_p, [c_int]),
+    "pqn_profile_enable": (c_int, [c_int]),
+    "pqn_profile_read": (c_int, [POINTER(c_double), POINTER(c_longlong), c_int]),
     "pqn_env_info": (c_int, [c_int, POINTER(EnvInfo)]),
     "pqn_rng_split": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int, c_void_p]),
     "pqn_threefry2x32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
@@ -116,3 +121,13 @@ def raw(t):
 def stream_ptr():
     import torch
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def profile_read(reset=True):
+    """{kernel name: (total ms, launches)} from the library's CUDA-event spans."""
+    l = lib()
+    n = l.pqn_num_kernels()
+    ms = (c_double * n)()
+    cnt = (c_longlong * n)()
+    check(l.pqn_profile_read(ms, cnt, 1 if reset else 0), "pqn_profile_read")
+    return {l.pqn_kernel_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}

@@ -1,4 +1,5 @@
-// Error plumbing shared by the translation units of libpqn_b200.so.
+// Error plumbing + launch accounting shared by the translation units of
+// libpqn_b200.so.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -7,4 +8,23 @@ namespace pqn {
 int set_error(int code, const char* fmt, ...);
 // cudaPeekAtLastError() after a launch: 0 or PQN_E_CUDA (message recorded)
 int check_launch(const char* what);
+
+// kernel ids for the launch counter / per-kernel CUDA-event timing (pqn_profile_*)
+enum KernelId : int {
+  K_ENV_RESET = 0, K_ENV_STEP, K_ENV_OBS, K_EPS_GREEDY, K_ROLLOUT_ACT_STEP, K_ROLLOUT_KEYS, K_QLAMBDA, K_RNG,
+  K_CONV_FWD, K_DENSE_FWD, K_ROW_BWD, K_WGRAD, K_DGRAD, K_CONV_BWD, K_GATHER_ROWS, K_SQNORM, K_RADAM, K_ADVANCE,
+  K_BN_UPDATE, K_COUNT
+};
+
+void prof_begin(int id, cudaStream_t st);
+void prof_end(int id, cudaStream_t st);
+
+// Wrap exactly one kernel launch: counts it and, when profiling is on, brackets
+// it with CUDA events on the launching stream.
+struct LaunchScope {
+  int id;
+  cudaStream_t st;
+  LaunchScope(int id_, cudaStream_t st_) : id(id_), st(st_) { prof_begin(id, st); }
+  ~LaunchScope() { prof_end(id, st); }
+};
 }  // namespace pqn

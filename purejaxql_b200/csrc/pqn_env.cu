@@ -365,14 +365,14 @@ int pqn_env_info(int env_id, pqn_env_info_t* out) {
 int pqn_rng_split(const uint32_t* keys, int64_t n, int32_t num, uint32_t* out, int rng_mode, void* stream) {
   if (!keys || !out || n < 0 || num <= 0) return set_error(PQN_E_INVALID, "pqn_rng_split: bad argument");
   if (n == 0) return PQN_OK;
-  rng_split_kernel<<<blocks_for(n * num, 256), 256, 0, (cudaStream_t)stream>>>(keys, n, num, out, rng_mode);
+  { LaunchScope _ls(K_RNG, (cudaStream_t)stream); rng_split_kernel<<<blocks_for(n * num, 256), 256, 0, (cudaStream_t)stream>>>(keys, n, num, out, rng_mode); }
   return check_launch("pqn_rng_split");
 }
 
 int pqn_rng_bits(const uint32_t* keys, int64_t n, int64_t len, uint32_t* out, int rng_mode, void* stream) {
   if (!keys || !out || n < 0 || len <= 0) return set_error(PQN_E_INVALID, "pqn_rng_bits: bad argument");
   if (n == 0) return PQN_OK;
-  rng_bits_kernel<<<blocks_for(n * len, 256), 256, 0, (cudaStream_t)stream>>>(keys, n, len, out, rng_mode);
+  { LaunchScope _ls(K_RNG, (cudaStream_t)stream); rng_bits_kernel<<<blocks_for(n * len, 256), 256, 0, (cudaStream_t)stream>>>(keys, n, len, out, rng_mode); }
   return check_launch("pqn_rng_bits");
 }
 
@@ -380,18 +380,18 @@ int pqn_threefry2x32(const uint32_t* key_pairs, const uint32_t* ctr_pairs, uint3
                      void* stream) {
   if (!key_pairs || !ctr_pairs || !out_pairs || n < 0) return set_error(PQN_E_INVALID, "pqn_threefry2x32: bad argument");
   if (n == 0) return PQN_OK;
-  threefry_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(key_pairs, ctr_pairs, out_pairs, n);
+  { LaunchScope _ls(K_RNG, (cudaStream_t)stream); threefry_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(key_pairs, ctr_pairs, out_pairs, n); }
   return check_launch("pqn_threefry2x32");
 }
 
 int pqn_env_reset(int env_id, const uint32_t* keys, uint32_t* state, float* obs, int64_t N, int max_steps,
                   int rng_mode, void* stream) {
-  if (!keys || !state || N < 0) return set_error(PQN_E_INVALID, "pqn_env_reset: bad argument");
   if (N == 0) return PQN_OK;
+  if (!keys || !state || N < 0) return set_error(PQN_E_INVALID, "pqn_env_reset: bad argument");
   PQN_ENV_DISPATCH(env_id, {
     const int ms = max_steps > 0 ? max_steps : EnvT::DEFAULT_MAX_STEPS;
-    env_reset_kernel<EnvT><<<blocks_for(N, ENV_BLOCK), ENV_BLOCK, 0, (cudaStream_t)stream>>>(keys, state, obs, N,
-                                                                                             ms, rng_mode);
+    { LaunchScope _ls(K_ENV_RESET, (cudaStream_t)stream); env_reset_kernel<EnvT><<<blocks_for(N, ENV_BLOCK), ENV_BLOCK, 0, (cudaStream_t)stream>>>(keys, state, obs, N,
+                                                                                             ms, rng_mode); }
   });
   return check_launch("pqn_env_reset");
 }
@@ -399,13 +399,13 @@ int pqn_env_reset(int env_id, const uint32_t* keys, uint32_t* state, float* obs,
 int pqn_env_step(int env_id, const uint32_t* keys, uint32_t* state, const int32_t* action, float* obs,
                  float* reward, uint8_t* done, float* info_discount, float* info_ret, int32_t* info_len,
                  int32_t* info_t, int64_t N, int max_steps, int rng_mode, void* stream) {
+  if (N == 0) return PQN_OK;
   if (!keys || !state || !action || !reward || !done || N < 0)
     return set_error(PQN_E_INVALID, "pqn_env_step: bad argument");
-  if (N == 0) return PQN_OK;
   PQN_ENV_DISPATCH(env_id, {
     const int ms = max_steps > 0 ? max_steps : EnvT::DEFAULT_MAX_STEPS;
-    env_step_kernel<EnvT><<<blocks_for(N, ENV_BLOCK), ENV_BLOCK, 0, (cudaStream_t)stream>>>(
-        keys, state, action, obs, reward, done, info_discount, info_ret, info_len, info_t, N, ms, rng_mode);
+    { LaunchScope _ls(K_ENV_STEP, (cudaStream_t)stream); env_step_kernel<EnvT><<<blocks_for(N, ENV_BLOCK), ENV_BLOCK, 0, (cudaStream_t)stream>>>(
+        keys, state, action, obs, reward, done, info_discount, info_ret, info_len, info_t, N, ms, rng_mode); }
   });
   return check_launch("pqn_env_step");
 }
@@ -415,8 +415,8 @@ int pqn_env_obs_packed(int env_id, const uint32_t* state, uint32_t* obs_packed, 
   if (N == 0) return PQN_OK;
   PQN_ENV_DISPATCH(env_id, {
     if (!EnvT::BINARY_OBS) return set_error(PQN_E_UNSUPPORTED, "pqn_env_obs_packed: env %d has float observations", env_id);
-    env_obs_kernel<EnvT><<<blocks_for(N, ENV_BLOCK), ENV_BLOCK, 0, (cudaStream_t)stream>>>(state, nullptr,
-                                                                                           obs_packed, N);
+    { LaunchScope _ls(K_ENV_OBS, (cudaStream_t)stream); env_obs_kernel<EnvT><<<blocks_for(N, ENV_BLOCK), ENV_BLOCK, 0, (cudaStream_t)stream>>>(state, nullptr,
+                                                                                           obs_packed, N); }
   });
   return check_launch("pqn_env_obs_packed");
 }
@@ -425,7 +425,7 @@ int pqn_env_obs(int env_id, const uint32_t* state, float* obs, int64_t N, void* 
   if (!state || !obs || N < 0) return set_error(PQN_E_INVALID, "pqn_env_obs: bad argument");
   if (N == 0) return PQN_OK;
   PQN_ENV_DISPATCH(env_id, {
-    env_obs_kernel<EnvT><<<blocks_for(N, ENV_BLOCK), ENV_BLOCK, 0, (cudaStream_t)stream>>>(state, obs, nullptr, N);
+    { LaunchScope _ls(K_ENV_OBS, (cudaStream_t)stream); env_obs_kernel<EnvT><<<blocks_for(N, ENV_BLOCK), ENV_BLOCK, 0, (cudaStream_t)stream>>>(state, obs, nullptr, N); }
   });
   return check_launch("pqn_env_obs");
 }
@@ -435,7 +435,7 @@ int pqn_eps_greedy(const uint32_t* keys, const float* q, const float* eps, int32
   if (!keys || !q || !eps || !action || N < 0 || A <= 0 || A >= 65536)
     return set_error(PQN_E_INVALID, "pqn_eps_greedy: bad argument");
   if (N == 0) return PQN_OK;
-  eps_greedy_kernel<<<blocks_for(N, 256), 256, 0, (cudaStream_t)stream>>>(keys, q, eps, action, N, A, rng_mode);
+  { LaunchScope _ls(K_EPS_GREEDY, (cudaStream_t)stream); eps_greedy_kernel<<<blocks_for(N, 256), 256, 0, (cudaStream_t)stream>>>(keys, q, eps, action, N, A, rng_mode); }
   return check_launch("pqn_eps_greedy");
 }
 
@@ -449,16 +449,16 @@ int pqn_rollout_act_step(int env_id, const uint32_t* step_keys, const float* q, 
   PQN_ENV_DISPATCH(env_id, {
     const int ms = max_steps > 0 ? max_steps : EnvT::DEFAULT_MAX_STEPS;
     dim3 grid(blocks_for(E, ENV_BLOCK), (unsigned)S);
-    rollout_act_step_kernel<EnvT><<<grid, ENV_BLOCK, 0, (cudaStream_t)stream>>>(
+    { LaunchScope _ls(K_ROLLOUT_ACT_STEP, (cudaStream_t)stream); rollout_act_step_kernel<EnvT><<<grid, ENV_BLOCK, 0, (cudaStream_t)stream>>>(
         step_keys, q, eps, state, obs_next, action, reward, done, maxq, info_sums, E, ms, rew_scale, rng_mode,
-        obs_seed_stride, tr_seed_stride, info_done_only);
+        obs_seed_stride, tr_seed_stride, info_done_only); }
   });
   return check_launch("pqn_rollout_act_step");
 }
 
 int pqn_rollout_keys(uint32_t* rng_inout, uint32_t* keys_out, int32_t S, int32_t T, int rng_mode, void* stream) {
   if (!rng_inout || !keys_out || S <= 0 || T <= 0) return set_error(PQN_E_INVALID, "pqn_rollout_keys: bad argument");
-  rollout_keys_kernel<<<blocks_for(S, 64), 64, 0, (cudaStream_t)stream>>>(rng_inout, keys_out, S, T, rng_mode);
+  { LaunchScope _ls(K_ROLLOUT_KEYS, (cudaStream_t)stream); rollout_keys_kernel<<<blocks_for(S, 64), 64, 0, (cudaStream_t)stream>>>(rng_inout, keys_out, S, T, rng_mode); }
   return check_launch("pqn_rollout_keys");
 }
 
@@ -466,8 +466,8 @@ int pqn_qlambda(const float* reward, const uint8_t* done, const float* maxq, con
                 int32_t T, int32_t S, int32_t E, int32_t A, float gamma, float lambda, void* stream) {
   if (!reward || !done || !maxq || !q_last || !targets || T <= 0 || S <= 0 || E <= 0 || A <= 0)
     return set_error(PQN_E_INVALID, "pqn_qlambda: bad argument");
-  qlambda_kernel<<<blocks_for((int64_t)S * E, 256), 256, 0, (cudaStream_t)stream>>>(reward, done, maxq, q_last,
-                                                                                    targets, T, S, E, A, gamma, lambda);
+  { LaunchScope _ls(K_QLAMBDA, (cudaStream_t)stream); qlambda_kernel<<<blocks_for((int64_t)S * E, 256), 256, 0, (cudaStream_t)stream>>>(reward, done, maxq, q_last,
+                                                                                    targets, T, S, E, A, gamma, lambda); }
   return check_launch("pqn_qlambda");
 }
 

@@ -905,9 +905,9 @@ static void launch_dense(int BN, dim3 grid, cudaStream_t st, const float* X, int
                          int64_t P, int64_t ow, int64_t ob, int64_t osc, int64_t obi, int64_t ohw, int64_t ohb, int A,
                          float* H, float* XH, float* RS, float* Q, int rows, int K) {
   if (BN == 128)
-    dense_fwd_kernel<128, MODE><<<grid, GT, 0, st>>>(X, xss, ldx, params, P, ow, ob, osc, obi, ohw, ohb, A, H, XH, RS, Q, rows, K);
+    { LaunchScope _ls(K_DENSE_FWD, st); dense_fwd_kernel<128, MODE><<<grid, GT, 0, st>>>(X, xss, ldx, params, P, ow, ob, osc, obi, ohw, ohb, A, H, XH, RS, Q, rows, K); }
   else
-    dense_fwd_kernel<256, MODE><<<grid, GT, 0, st>>>(X, xss, ldx, params, P, ow, ob, osc, obi, ohw, ohb, A, H, XH, RS, Q, rows, K);
+    { LaunchScope _ls(K_DENSE_FWD, st); dense_fwd_kernel<256, MODE><<<grid, GT, 0, st>>>(X, xss, ldx, params, P, ow, ob, osc, obi, ohw, ohb, A, H, XH, RS, Q, rows, K); }
 }
 
 static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
@@ -916,10 +916,10 @@ template <bool TRAIN>
 static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
                            const float* params, int64_t P, const pqn_net_layout_t& L, float* h1, float* bn, int rows) {
   switch (C) {
-    case 4: conv_fwd_kernel<4, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); break;
-    case 6: conv_fwd_kernel<6, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); break;
-    case 7: conv_fwd_kernel<7, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); break;
-    case 10: conv_fwd_kernel<10, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); break;
+    case 4: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<4, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); } break;
+    case 6: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<6, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); } break;
+    case 7: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<7, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); } break;
+    case 10: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<10, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); } break;
     default: return -1;
   }
   return 0;
@@ -974,8 +974,8 @@ int pqn_qnet_forward(const pqn_net_desc_t* d, const float* params, const void* o
     const float* x = (const float*)obs;
     int64_t xss = obs_rows_per_seed * D;
     if (gather) {
-      gather_rows_kernel<<<dim3(cdiv(rows * D, 256), S), 256, 0, st>>>(x, obs_rows_per_seed, gather, w.xg, nullptr,
-                                                                      (int)rows, D);
+      { LaunchScope _ls(K_GATHER_ROWS, st); gather_rows_kernel<<<dim3(cdiv(rows * D, 256), S), 256, 0, st>>>(x, obs_rows_per_seed, gather, w.xg, nullptr,
+                                                                      (int)rows, D); }
       x = w.xg;
       xss = rows * D;
     }
@@ -1020,28 +1020,28 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
     launch_dense<1>(128, dim3(cdiv(rows, 128), S), st, w.h1, rows * FLAT_CNN, FLAT_CNN, params, P, L.d0_w, L.d0_b,
                     L.ln1_scale, L.ln1_bias, 0, 0, A, w.h2, w.xhat2, w.rstd2, nullptr, R, FLAT_CNN);
     const size_t sm = (size_t)(3 * 128 + A * 128 + A + 2) * sizeof(float);
-    row_bwd_kernel<128, true><<<dim3(cdiv(rows, RB_ROWS), S), 256, sm, st>>>(
+    { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, true><<<dim3(cdiv(rows, RB_ROWS), S), 256, sm, st>>>(
         w.h2, w.xhat2, w.rstd2, nullptr, w.dz2, params, grads, P, L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d0_b,
-        L.head_w, L.head_b, A, gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, R);
+        L.head_w, L.head_b, A, gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, R); }
     const int splits = wgrad_splits(FLAT_CNN / 128, S, R);
-    wgrad_kernel<<<dim3(FLAT_CNN / 128, 1, S * splits), GT, 0, st>>>(w.h1, rows * FLAT_CNN, FLAT_CNN, w.dz2,
+    { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(FLAT_CNN / 128, 1, S * splits), GT, 0, st>>>(w.h1, rows * FLAT_CNN, FLAT_CNN, w.dz2,
                                                                      rows * HID_CNN, HID_CNN, grads, P, L.d0_w, R,
-                                                                     FLAT_CNN, splits);
-    dgrad_kernel<<<dim3(cdiv(rows, 128), FLAT_CNN / 128, S), GT, 0, st>>>(w.dz2, rows * HID_CNN, HID_CNN, params, P,
+                                                                     FLAT_CNN, splits); }
+    { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), FLAT_CNN / 128, S), GT, 0, st>>>(w.dz2, rows * HID_CNN, HID_CNN, params, P,
                                                                           L.d0_w, w.h1, w.h1, rows * FLAT_CNN, R,
-                                                                          FLAT_CNN);
+                                                                          FLAT_CNN); }
     dim3 cg(cdiv(rows, CONV_BWD_SPB), S);
     switch (d->in_c) {
-      case 4: conv_bwd_kernel<4><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
-      case 6: conv_bwd_kernel<6><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
-      case 7: conv_bwd_kernel<7><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
-      case 10: conv_bwd_kernel<10><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
+      case 4: { LaunchScope _ls(K_CONV_BWD, st); conv_bwd_kernel<4><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); } break;
+      case 6: { LaunchScope _ls(K_CONV_BWD, st); conv_bwd_kernel<6><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); } break;
+      case 7: { LaunchScope _ls(K_CONV_BWD, st); conv_bwd_kernel<7><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); } break;
+      case 10: { LaunchScope _ls(K_CONV_BWD, st); conv_bwd_kernel<10><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); } break;
     }
   } else {
     const int D = d->in_c, H = d->hidden;
     const int BM = (H == 128) ? 128 : 64;
-    gather_rows_kernel<<<dim3(cdiv(rows * D, 256), S), 256, 0, st>>>((const float*)obs, obs_rows_per_seed, gather, w.xg,
-                                                                    bn_sums, R, D);
+    { LaunchScope _ls(K_GATHER_ROWS, st); gather_rows_kernel<<<dim3(cdiv(rows * D, 256), S), 256, 0, st>>>((const float*)obs, obs_rows_per_seed, gather, w.xg,
+                                                                    bn_sums, R, D); }
     launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.xg, rows * D, D, params, P, L.d0_w, L.d0_b, L.ln0_scale,
                     L.ln0_bias, 0, 0, A, w.h0, w.xhat0, w.rstd0, nullptr, R, D);
     const size_t smh = (size_t)(3 * H + A * H + A + 2) * sizeof(float);
@@ -1051,46 +1051,46 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
       launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.h0, rows * H, H, params, P, L.d1_w, L.d1_b, L.ln1_scale,
                       L.ln1_bias, 0, 0, A, w.hh1, w.xhat1, w.rstd1, nullptr, R, H);
       if (H == 128)
-        row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, params, grads, P,
                                                         L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
-                                                        loss_sum, qsa_sum, R);
+                                                        loss_sum, qsa_sum, R); }
       else
-        row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, params, grads, P,
                                                         L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
-                                                        loss_sum, qsa_sum, R);
+                                                        loss_sum, qsa_sum, R); }
       const int tiles = (H / 128) * (H / 128);
       const int splits = wgrad_splits(tiles, S, R);
-      wgrad_kernel<<<dim3(H / 128, H / 128, S * splits), GT, 0, st>>>(w.h0, rows * H, H, w.dzl, rows * H, H, grads, P,
-                                                                      L.d1_w, R, H, splits);
-      dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(w.dzl, rows * H, H, params, P, L.d1_w, w.h0,
-                                                                     w.dh0, rows * H, R, H);
+      { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(H / 128, H / 128, S * splits), GT, 0, st>>>(w.h0, rows * H, H, w.dzl, rows * H, H, grads, P,
+                                                                      L.d1_w, R, H, splits); }
+      { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(w.dzl, rows * H, H, params, P, L.d1_w, w.h0,
+                                                                     w.dh0, rows * H, R, H); }
       if (H == 128)
-        row_bwd_kernel<128, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, params, grads, P,
                                                          L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
-                                                         nullptr, nullptr, nullptr, 0, nullptr, nullptr, R);
+                                                         nullptr, nullptr, nullptr, 0, nullptr, nullptr, R); }
       else
-        row_bwd_kernel<256, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, params, grads, P,
                                                          L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
-                                                         nullptr, nullptr, nullptr, 0, nullptr, nullptr, R);
+                                                         nullptr, nullptr, nullptr, 0, nullptr, nullptr, R); }
       const int sp0 = wgrad_splits(H / 128, S, R);
-      wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dh0, rows * H, H, grads,
-                                                                        P, L.d0_w, R, D, sp0);
+      { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dh0, rows * H, H, grads,
+                                                                        P, L.d0_w, R, D, sp0); }
     } else {
       if (H == 128)
-        row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, params, grads, P,
                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
-                                                        loss_sum, qsa_sum, R);
+                                                        loss_sum, qsa_sum, R); }
       else
-        row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, params, grads, P,
                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
-                                                        loss_sum, qsa_sum, R);
+                                                        loss_sum, qsa_sum, R); }
       const int sp0 = wgrad_splits(H / 128, S, R);
-      wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dzl, rows * H, H, grads,
-                                                                        P, L.d0_w, R, D, sp0);
+      { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dzl, rows * H, H, grads,
+                                                                        P, L.d0_w, R, D, sp0); }
     }
   }
   return check_launch("pqn_qnet_loss_grad");

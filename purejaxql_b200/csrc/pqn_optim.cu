@@ -118,11 +118,11 @@ int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu,
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(gnorm_scratch, 0, (size_t)S * sizeof(float), st) != cudaSuccess)
     return check_launch("pqn_radam_clip_step(memset)");
-  sqnorm_kernel<<<dim3(NORM_BLOCKS, S), 256, 0, st>>>(grads, P, gnorm_scratch);
+  { LaunchScope _ls(K_SQNORM, st); sqnorm_kernel<<<dim3(NORM_BLOCKS, S), 256, 0, st>>>(grads, P, gnorm_scratch); }
   const unsigned nb = (unsigned)((P / 4 + 255) / 256);
-  radam_kernel<<<dim3(nb, S), 256, 0, st>>>(params, grads, mu, nu, sched, step_counter, gnorm_scratch, P, max_norm, b1,
-                                            b2, eps);
-  advance_kernel<<<1, 1, 0, st>>>(step_counter);
+  { LaunchScope _ls(K_RADAM, st); radam_kernel<<<dim3(nb, S), 256, 0, st>>>(params, grads, mu, nu, sched, step_counter, gnorm_scratch, P, max_norm, b1,
+                                            b2, eps); }
+  { LaunchScope _ls(K_ADVANCE, st); advance_kernel<<<1, 1, 0, st>>>(step_counter); }
   return check_launch("pqn_radam_clip_step");
 }
 
@@ -130,7 +130,7 @@ int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F
                         void* stream) {
   if (!batch_stats || !bn_sums || S <= 0 || F <= 0 || F > 1024 || count <= 0.f)
     return set_error(PQN_E_INVALID, "pqn_bn_stats_update: bad argument");
-  bn_update_kernel<<<S, ((F + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(batch_stats, bn_sums, F, count, momentum);
+  { LaunchScope _ls(K_BN_UPDATE, (cudaStream_t)stream); bn_update_kernel<<<S, ((F + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(batch_stats, bn_sums, F, count, momentum); }
   return check_launch("pqn_bn_stats_update");
 }
 

@@ -195,7 +195,10 @@ class PQNEngine:
         seed_stride_tr = T * E
         perm_view = None
 
+        on_update_begin = getattr(self, "on_update_begin", None)      # bench/profiling hook
         for n_updates in range(NU):
+            if on_update_begin is not None:
+                on_update_begin(n_updates)
             # ================= SAMPLE PHASE (:181-219)
             eps_dev.copy_(eps_table[n_updates:n_updates + 1])
             carry = jr.split(rng, 2, mode)[:, 1].contiguous()        # :213  `_rng`

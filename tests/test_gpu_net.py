@@ -60,8 +60,9 @@ def test_cnn_forward_matches_oracle_1e5(rows):
     obs = np.stack([breakout_obs(rows, seed=s + 1) for s in range(S)])          # [S,rows,10,10,4]
     packed = torch.from_numpy(np.stack([pack_obs(obs[s] != 0) for s in range(S)])).to(dev()).contiguous()
     q = torch.zeros((S * rows, 3), device=dev())
+    ws = _ws(spec, S, rows)
     _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), _lib.p(packed), None, rows, _lib.p(q), S, rows,
-                                           _lib.p(_ws(spec, S, rows)), _lib.stream_ptr()))
+                                           _lib.p(ws), _lib.stream_ptr()))
     q = q.cpu().numpy().reshape(S, rows, 3)
     for s in range(S):
         ref32 = R.cnn_forward(ps[s], obs[s])
@@ -80,9 +81,9 @@ def test_cnn_forward_other_channel_counts_and_gather():
         packed = torch.from_numpy(np.stack([pack_obs(obs[s]) for s in range(S)])).to(dev()).contiguous()
         gather = np.stack([rng.permutation(total)[:rows] for _ in range(S)]).astype(np.int32)
         q = torch.zeros((S * rows, 5), device=dev())
-        _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), _lib.p(packed),
-                                               _lib.p(torch.from_numpy(gather).to(dev())), total, _lib.p(q), S, rows,
-                                               _lib.p(_ws(spec, S, rows)), _lib.stream_ptr()))
+        tg_, ws = torch.from_numpy(gather).to(dev()), _ws(spec, S, rows)
+        _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), _lib.p(packed), _lib.p(tg_), total, _lib.p(q),
+                                               S, rows, _lib.p(ws), _lib.stream_ptr()))
         q = q.cpu().numpy().reshape(S, rows, 5)
         for s in range(S):
             ref = R.cnn_forward(ps[s], obs[s][gather[s]].astype(np.float32))
@@ -100,8 +101,9 @@ def test_mlp_forward_matches_oracle(D, H, layers, A):
     flat = torch.cat([spec.flatten(p, 1, dev()) for p in ps], 0).contiguous()
     obs = rng.standard_normal((S, rows, D)).astype(np.float32)
     q = torch.zeros((S * rows, A), device=dev())
-    _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), _lib.p(torch.from_numpy(obs).to(dev())), None, rows,
-                                           _lib.p(q), S, rows, _lib.p(_ws(spec, S, rows)), _lib.stream_ptr()))
+    to_, ws = torch.from_numpy(obs).to(dev()), _ws(spec, S, rows)
+    _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), _lib.p(to_), None, rows,
+                                           _lib.p(q), S, rows, _lib.p(ws), _lib.stream_ptr()))
     q = q.cpu().numpy().reshape(S, rows, A)
     for s in range(S):
         assert np.abs(q[s] - R.mlp_forward(ps[s], obs[s])).max() < 1e-5
@@ -113,10 +115,12 @@ def _loss_grad(spec, flat, obs_t, gather, total, act, tgt, S, rows, F):
     ls = torch.zeros(S, device=dev()); qs = torch.zeros(S, device=dev())
     bn = torch.zeros((S, 2 * F), device=dev())
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev(), dt)
+    tg_, ta_, tt_, ws = t(gather, torch.int32), t(act, torch.int32), t(tgt, torch.float32), _ws(spec, S, rows)
     _lib.check(_lib.lib().pqn_qnet_loss_grad(
-        spec.desc, _lib.p(flat), _lib.p(obs_t), _lib.p(t(gather, torch.int32)), total, _lib.p(t(act, torch.int32)),
-        _lib.p(t(tgt, torch.float32)), total, _lib.p(grads), _lib.p(ls), _lib.p(qs), _lib.p(bn), S, rows,
-        _lib.p(_ws(spec, S, rows)), _lib.stream_ptr()))
+        spec.desc, _lib.p(flat), _lib.p(obs_t), _lib.p(tg_), total, _lib.p(ta_),
+        _lib.p(tt_), total, _lib.p(grads), _lib.p(ls), _lib.p(qs), _lib.p(bn), S, rows,
+        _lib.p(ws), _lib.stream_ptr()))
+    torch.cuda.synchronize()
     return grads, ls.cpu().numpy(), qs.cpu().numpy(), bn.cpu().numpy()
 
 
@@ -186,11 +190,14 @@ def test_radam_clip_matches_oracle():
     tp = torch.from_numpy(p.copy()).to(dev()); mu = torch.zeros_like(tp); nu = torch.zeros_like(tp)
     cnt = torch.zeros(1, dtype=torch.int32, device=dev()); gn = torch.zeros(S, device=dev())
     refs = [({"w": p[s].copy()}, R.opt_init({"w": p[s]})) for s in range(S)]
+    ttab = torch.from_numpy(tab).to(dev())
     for i in range(steps):
         g = (rng.standard_normal((S, P)) * (1.0 if i % 2 else 0.05)).astype(np.float32)   # alternate clipped / unclipped
-        _lib.check(_lib.lib().pqn_radam_clip_step(_lib.p(tp), _lib.p(torch.from_numpy(g).to(dev())), _lib.p(mu),
-                                                  _lib.p(nu), _lib.p(torch.from_numpy(tab).to(dev())), _lib.p(cnt),
+        tgr = torch.from_numpy(g).to(dev())
+        _lib.check(_lib.lib().pqn_radam_clip_step(_lib.p(tp), _lib.p(tgr), _lib.p(mu),
+                                                  _lib.p(nu), _lib.p(ttab), _lib.p(cnt),
                                                   _lib.p(gn), S, P, 10.0, 0.9, 0.999, 1e-8, _lib.stream_ptr()))
+        torch.cuda.synchronize()
         for s in range(S):
             pp, oo = refs[s]
             pp, oo, _ = R.radam_clip_step(pp, {"w": g[s]}, oo, tab[i, 0], 10.0)
