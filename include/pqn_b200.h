@@ -202,6 +202,15 @@ int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu,
 int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F, float count, float momentum,
                         void* stream);
 
+/* ---- tcgen05 (5th-gen tensor core) path of the dense contractions ----------
+ * lo[i] = x[i] - trunc_tf32(x[i]): the error-compensation operand of 3xTF32. */
+int pqn_tc_split_lo(const float* x, float* lo, int64_t n, void* stream);
+/* Test hook: D[s] = A[s].B[s] through the TMA -> tcgen05.mma(kind::tf32) -> TMEM pipeline.
+ *  a_mn=0: A is [S][M][K]; a_mn=1: A is [S][K][M].  b_mn=0: B is [S][N][K]; b_mn=1: B is [S][K][N].
+ *  split3: 3xTF32 with the *_lo operands from pqn_tc_split_lo; else one TF32 pass.  N % 128 == 0. */
+int pqn_tc_gemm_test(const float* a, const float* a_lo, const float* b, const float* b_lo, float* d, int32_t S,
+                     int32_t M, int32_t N, int32_t K, int a_mn, int b_mn, int split3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,415 @@
+// tcgen05 / TMEM / TMA path for the dense contractions of the Q-network
+// (sm_100a only): one warp-specialised, persistent GEMM kernel used for
+//   forward   Z  = H1 [rows,1024] . W1 [1024,128]        (A K-major,  B MN-major)
+//   wgrad     dW = H1^T [1024,rows] . dZ [rows,128]      (A MN-major, B MN-major)
+//   dgrad     dX = dZ [rows,128] . W1^T [128,1024]       (A K-major,  B K-major)
+// with fp32 accuracy from 3xTF32 error compensation: every operand x is fed as
+// hi = x (the tensor core reads the top 19 bits) and lo = x - trunc_tf32(x),
+// and D += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi accumulates in fp32 in TMEM.
+//
+// Reference arithmetic: nn.Dense(128) of CNN (purejaxql/pqn_minatar.py:48) and
+// its autodiff; XLA itself runs these as TF32 tensor-core GEMMs on GPU.
+//
+// Pipeline (per CTA, 192 threads):
+//   warp 0   TMA producer   cp.async.bulk.tensor (SWIZZLE_128B boxes) -> smem ring
+//   warp 1   MMA issuer     tcgen05.mma.cta_group::1.kind::tf32 (one thread), TMEM accumulators
+//   warps 2-5 epilogue      tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+// Barriers: full[stage]/empty[stage] (TMA <-> MMA), tmem_full/tmem_empty[2] (MMA <-> epilogue).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pqn_b200.h"
+#include "api_common.h"
+#include "tc_common.cuh"
+
+namespace pqn {
+namespace tc {
+
+// ---------------------------------------------------------------------------
+// epilogues: each epilogue thread owns one row (TMEM lane) of the 128x128 tile
+// ---------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue_row(const EpiParams& ep, uint32_t tmem_row_addr, int seed, int m, int n0,
+                                             bool row_ok) {
+  if constexpr (EPI == EPI_STORE || EPI == EPI_RELU_MASK) {
+    // plain (or ReLU-masked) store of the fp32 tile row
+    float* __restrict__ out = ep.out + (int64_t)seed * ep.out_seed_stride + (int64_t)m * ep.ld_out + n0;
+    const float* __restrict__ msk =
+        (EPI == EPI_RELU_MASK) ? ep.mask + (int64_t)seed * ep.out_seed_stride + (int64_t)m * ep.ld_out + n0 : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_row_addr + c * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          if constexpr (EPI == EPI_RELU_MASK) {
+            const float4 h = *reinterpret_cast<const float4*>(msk + c * 32 + 4 * j);
+            o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f;
+            o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
+          }
+          *reinterpret_cast<float4*>(out + c * 32 + 4 * j) = o;
+        }
+      }
+    }
+  } else {
+    // bias + LayerNorm(128) + ReLU, then either (h, xhat, rstd[, lo-splits]) or the fused Q-head
+    const float* __restrict__ prm = ep.params + (int64_t)seed * ep.P;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_row_addr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float z = __uint_as_float(v[j]) + __ldg(prm + ep.off_b + c * 32 + j);
+        s1 += z;
+        s2 = fmaf(z, z, s2);
+      }
+    }
+    const float mean = s1 * (1.0f / 128.f);
+    const float var = fmaxf(s2 * (1.0f / 128.f) - mean * mean, 0.f);
+    const float rstd = 1.0f / sqrtf(var + 1e-6f);
+    float q[PQN_TC_MAX_A];
+#pragma unroll
+    for (int a = 0; a < PQN_TC_MAX_A; ++a) q[a] = 0.f;
+    const int64_t grow = (int64_t)seed * ep.rows + m;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_row_addr + c * 32, v);
+      tmem_ld_wait();
+      float h[32], xh[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j;
+        const float z = __uint_as_float(v[j]) + __ldg(prm + ep.off_b + col);
+        xh[j] = (z - mean) * rstd;
+        h[j] = fmaxf(xh[j] * __ldg(prm + ep.off_scale + col) + __ldg(prm + ep.off_bias + col), 0.f);
+      }
+      if constexpr (EPI == EPI_LN_TRAIN) {
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            *reinterpret_cast<float4*>(ep.H + grow * 128 + c * 32 + 4 * j) =
+                make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+            *reinterpret_cast<float4*>(ep.XHAT + grow * 128 + c * 32 + 4 * j) =
+                make_float4(xh[4 * j], xh[4 * j + 1], xh[4 * j + 2], xh[4 * j + 3]);
+          }
+        }
+      } else {  // EPI_LN_HEAD
+#pragma unroll
+        for (int a = 0; a < PQN_TC_MAX_A; ++a) {
+          if (a < ep.A) {
+            float acc = q[a];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              acc = fmaf(h[j], __ldg(prm + ep.off_hw + (int64_t)(c * 32 + j) * ep.A + a), acc);
+            q[a] = acc;
+          }
+        }
+      }
+    }
+    if (row_ok) {
+      if constexpr (EPI == EPI_LN_TRAIN) ep.RSTD[grow] = rstd;
+      else {
+#pragma unroll
+        for (int a = 0; a < PQN_TC_MAX_A; ++a)
+          if (a < ep.A) ep.Q[grow * ep.A + a] = q[a] + __ldg(prm + ep.off_hb + a);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+template <int A_MN, int B_MN, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   const GemmShape gs, const EpiParams ep) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte aligned operand ring (SWIZZLE_128B atoms), then barriers
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full = bars;                      // [TC_STAGES]
+  uint64_t* empty = bars + TC_STAGES;         // [TC_STAGES]
+  uint64_t* tmem_full = bars + 2 * TC_STAGES; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int passes = gs.split3 ? 3 : 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_b_hi);
+    if (gs.split3) { prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_b_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);  // 2 accumulator stages x 128 fp32 columns
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_seed = gs.m_tiles * gs.n_tiles;
+  const int num_tiles = tiles_per_seed * gs.S;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int seed = tile / tiles_per_seed;
+        const int rem = tile - seed * tiles_per_seed;
+        const int m0 = (rem / gs.n_tiles) * 128, n0 = (rem % gs.n_tiles) * 128;
+        for (int kb = 0; kb < gs.k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
+          mbar_expect_tx(&full[stage], gs.split3 ? TC_STAGE_BYTES : TC_STAGE_BYTES / 2);
+          const int k0 = kb * TC_BK;
+          // A tiles
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              tma_load_3d(sb + TC_A_HI + j * 4096, &tm_a_hi, &full[stage], m0 + 32 * j, k0, seed);
+              if (gs.split3) tma_load_3d(sb + TC_A_LO + j * 4096, &tm_a_lo, &full[stage], m0 + 32 * j, k0, seed);
+            }
+          } else {
+            tma_load_3d(sb + TC_A_HI, &tm_a_hi, &full[stage], k0, m0, seed);
+            if (gs.split3) tma_load_3d(sb + TC_A_LO, &tm_a_lo, &full[stage], k0, m0, seed);
+          }
+          // B tiles
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              tma_load_3d(sb + TC_B_HI + j * 4096, &tm_b_hi, &full[stage], n0 + 32 * j, k0, seed);
+              if (gs.split3) tma_load_3d(sb + TC_B_LO + j * 4096, &tm_b_lo, &full[stage], n0 + 32 * j, k0, seed);
+            }
+          } else {
+            tma_load_3d(sb + TC_B_HI, &tm_b_hi, &full[stage], k0, n0, seed);
+            if (gs.split3) tma_load_3d(sb + TC_B_LO, &tm_b_lo, &full[stage], k0, n0, seed);
+          }
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, 128, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 128;
+        bool first = true;
+        for (int kb = 0; kb < gs.k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            // smallest terms first
+            for (int p = 0; p < passes; ++p) {
+              const bool a_lo = gs.split3 && (p == 0);
+              const bool b_lo = gs.split3 && (p == 1);
+              const uint64_t da = make_sdesc<A_MN>(sb + (a_lo ? TC_A_LO : TC_A_HI), ks);
+              const uint64_t db = make_sdesc<B_MN>(sb + (b_lo ? TC_B_LO : TC_B_HI), ks);
+              umma_tf32(d_tmem, da, db, idesc, first ? 0u : 1u);
+              first = false;
+            }
+          }
+          umma_commit(&empty[stage]);  // smem slot free once these MMAs retire
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access (warp id % 4)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int seed = tile / tiles_per_seed;
+      const int rem = tile - seed * tiles_per_seed;
+      const int m0 = (rem / gs.n_tiles) * 128, n0 = (rem % gs.n_tiles) * 128;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int m = m0 + quad * 32 + lane;
+      const uint32_t row_addr = tmem_base + acc * 128 + ((uint32_t)(quad * 32) << 16);
+      epilogue_row<EPI>(ep, row_addr, seed, m, n0, m < gs.M);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 3-D fp32 tensor [seeds][mid][inner] with a {32, box_mid, 1} SWIZZLE_128B box.
+int make_tmap(CUtensorMap* tm, const float* base, uint64_t inner, uint64_t mid, uint64_t seeds, uint64_t mid_stride_elems,
+              uint64_t seed_stride_elems, uint32_t box_mid) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(PQN_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {inner, mid, seeds};
+  cuuint64_t strides[2] = {mid_stride_elems * 4, seed_stride_elems * 4};
+  cuuint32_t box[3] = {32, box_mid, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(PQN_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return PQN_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int A_MN, int B_MN, int EPI>
+static int launch_t(const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep, cudaStream_t st) {
+  auto kfn = tc_gemm_kernel<A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+      return check_launch("tc_gemm(cudaFuncSetAttribute)");
+    attr_set = true;
+  }
+  const int tiles = gs.m_tiles * gs.n_tiles * gs.S;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  {
+    LaunchScope _ls(K_TC_GEMM, st);
+    kfn<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(t[0], t[1], t[2], t[3], gs, ep);
+  }
+  return check_launch("tc_gemm");
+}
+
+int launch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep,
+                cudaStream_t st) {
+#define PQN_TC_CASE(A, B, E) \
+  if (a_mn == A && b_mn == B && epi == E) return launch_t<A, B, E>(t, gs, ep, st);
+  PQN_TC_CASE(0, 1, EPI_STORE)
+  PQN_TC_CASE(0, 1, EPI_LN_TRAIN)
+  PQN_TC_CASE(0, 1, EPI_LN_HEAD)
+  PQN_TC_CASE(1, 1, EPI_STORE)
+  PQN_TC_CASE(0, 0, EPI_STORE)
+  PQN_TC_CASE(0, 0, EPI_RELU_MASK)
+#undef PQN_TC_CASE
+  return set_error(PQN_E_UNSUPPORTED, "tc_gemm: combination a_mn=%d b_mn=%d epi=%d not instantiated", a_mn, b_mn, epi);
+}
+
+__global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, int64_t n4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+  float4 o;
+  o.x = tf32_lo(v.x); o.y = tf32_lo(v.y); o.z = tf32_lo(v.z); o.w = tf32_lo(v.w);
+  reinterpret_cast<float4*>(lo)[i] = o;
+}
+
+}  // namespace tc
+}  // namespace pqn
+
+using namespace pqn;
+using namespace pqn::tc;
+
+extern "C" {
+
+int pqn_tc_split_lo(const float* x, float* lo, int64_t n, void* stream) {
+  if (!x || !lo || n < 0 || (n & 3)) return set_error(PQN_E_INVALID, "pqn_tc_split_lo: bad argument (n %% 4 == 0)");
+  if (n == 0) return PQN_OK;
+  {
+    LaunchScope _ls(K_TC_SPLIT, (cudaStream_t)stream);
+    split_lo_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, lo, n / 4);
+  }
+  return check_launch("pqn_tc_split_lo");
+}
+
+// Test hook: D[s] = A[s] . B[s] on the tcgen05 path (fp32 in, fp32 out).
+//   a_mn = 0: A is [S][M][K] (K contiguous)   a_mn = 1: A is [S][K][M] (M contiguous)
+//   b_mn = 0: B is [S][N][K] (K contiguous)   b_mn = 1: B is [S][K][N] (N contiguous)
+//   split3 != 0: 3xTF32 (a_lo / b_lo must hold x - trunc_tf32(x)); else single-pass TF32.
+// M, N multiples of 128 are not required for M (rows are guarded); N % 128 == 0, K % 32 == 0 or zero-filled.
+int pqn_tc_gemm_test(const float* a, const float* a_lo, const float* b, const float* b_lo, float* d, int32_t S,
+                     int32_t M, int32_t N, int32_t K, int a_mn, int b_mn, int split3, void* stream) {
+  if (!a || !b || !d || S <= 0 || M <= 0 || N <= 0 || K <= 0 || (N % 128) || (split3 && (!a_lo || !b_lo)))
+    return set_error(PQN_E_INVALID, "pqn_tc_gemm_test: bad argument");
+  CUtensorMap t[4];
+  int rc;
+  const float* al = split3 ? a_lo : a;
+  const float* bl = split3 ? b_lo : b;
+  if (a_mn) {
+    if ((rc = make_tmap(&t[0], a, M, K, S, M, (uint64_t)M * K, 32))) return rc;
+    if ((rc = make_tmap(&t[1], al, M, K, S, M, (uint64_t)M * K, 32))) return rc;
+  } else {
+    if ((rc = make_tmap(&t[0], a, K, M, S, K, (uint64_t)M * K, 128))) return rc;
+    if ((rc = make_tmap(&t[1], al, K, M, S, K, (uint64_t)M * K, 128))) return rc;
+  }
+  if (b_mn) {
+    if ((rc = make_tmap(&t[2], b, N, K, S, N, (uint64_t)N * K, 32))) return rc;
+    if ((rc = make_tmap(&t[3], bl, N, K, S, N, (uint64_t)N * K, 32))) return rc;
+  } else {
+    if ((rc = make_tmap(&t[2], b, K, N, S, K, (uint64_t)N * K, 128))) return rc;
+    if ((rc = make_tmap(&t[3], bl, K, N, S, K, (uint64_t)N * K, 128))) return rc;
+  }
+  GemmShape gs;
+  gs.S = S; gs.M = M; gs.m_tiles = (M + 127) / 128; gs.n_tiles = N / 128; gs.k_blocks = (K + TC_BK - 1) / TC_BK;
+  gs.split3 = split3 ? 1 : 0;
+  EpiParams ep = {};
+  ep.out = d; ep.ld_out = N; ep.out_seed_stride = (int64_t)M * N;
+  return launch_gemm(a_mn, b_mn, EPI_STORE, t, gs, ep, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// PTX wrappers and constants of the tcgen05 / TMEM / TMA GEMM path (sm_100a).
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace pqn {
+namespace tc {
+
+constexpr int TC_THREADS = 192;          // warp0 TMA, warp1 MMA, warps 2-5 epilogue (warp2 also owns TMEM alloc)
+constexpr int TC_BK = 32;                // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = 128 * TC_BK * 4;   // 16 KB
+constexpr int TC_A_HI = 0, TC_A_LO = TC_TILE_BYTES, TC_B_HI = 2 * TC_TILE_BYTES, TC_B_LO = 3 * TC_TILE_BYTES;
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;  // 64 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+#define PQN_TC_MAX_A 8
+
+enum Epilogue : int { EPI_STORE = 0, EPI_LN_TRAIN = 1, EPI_LN_HEAD = 2, EPI_RELU_MASK = 3 };
+
+struct GemmShape {
+  int S;         // batch (seeds)
+  int M;         // rows of D that exist (rows >= M are not stored)
+  int m_tiles, n_tiles, k_blocks;
+  int split3;    // 1: 3xTF32, 0: single TF32 pass
+};
+
+struct EpiParams {
+  // EPI_STORE / EPI_RELU_MASK
+  float* out;
+  const float* mask;
+  int64_t ld_out, out_seed_stride;
+  // EPI_LN_*
+  const float* params;
+  int64_t P, off_b, off_scale, off_bias, off_hw, off_hb;
+  int A, rows;
+  float *H, *XHAT, *RSTD, *Q;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);  // what the tensor core reads of x
+  return x - hi;                                                       // exact in fp32
+}
+
+// ---- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// ---- TMA
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// ---- tcgen05
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bits 4-5 = 1), a/b format TF32 (= 2,
+// bits 7-9 / 10-12), a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor) for a 128 x 32 fp32 operand tile in SWIZZLE_128B
+// atoms (8 rows x 128 B = 1024 B), k-step `ks` selects 8 of the 32 k values:
+//   K-major  tile: row r (MN index) at r*128 B; 8-row atoms every 1024 B (SBO); the k-step advances 32 B in the row.
+//   MN-major tile: 4 boxes of [32 k rows][32 mn] at 4096 B (LBO between MN atoms); k atoms (8 rows) every 1024 B (SBO).
+template <int MN>
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t tile_addr, int ks) {
+  const uint32_t addr = MN ? tile_addr + ks * 1024 : tile_addr + ks * 32;
+  const uint64_t lbo = MN ? (4096u >> 4) : 1u;
+  const uint64_t sbo = 1024u >> 4;
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) /*version*/ | (2ull << 61) /*SWIZZLE_128B*/;
+}
+
+// host-side pieces used by other translation units (pqn_net.cu)
+int make_tmap(CUtensorMap* tm, const float* base, uint64_t inner, uint64_t mid, uint64_t seeds, uint64_t mid_stride_elems,
+              uint64_t seed_stride_elems, uint32_t box_mid);
+int launch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace pqn
