@@ -211,6 +211,10 @@ int pqn_tc_split_lo(const float* x, float* lo, int64_t n, void* stream);
 int pqn_tc_gemm_test(const float* a, const float* a_lo, const float* b, const float* b_lo, float* d, int32_t S,
                      int32_t M, int32_t N, int32_t K, int a_mn, int b_mn, int split3, void* stream);
 
+/* Debug hook: one 128x128x32 tile; dumps the TMA-written smem tiles and the TMEM accumulator. */
+int pqn_tc_debug(const float* a, const float* b, float* dump_a, float* dump_b, float* out_d, uint32_t* info,
+                 int a_mn, int b_mn, int nk, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -359,6 +359,81 @@ __global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__
   reinterpret_cast<float4*>(lo)[i] = o;
 }
 
+// Debug kernel: one CTA, one 128x128x32 tile, no pipelining.  Dumps the smem tiles TMA produced and the TMEM
+// accumulator after `nk` k-steps so that descriptor/layout problems can be diagnosed from the host.
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(128, 1)
+    tc_debug_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                    float* __restrict__ dump_a, float* __restrict__ dump_b, float* __restrict__ out_d, int nk,
+                    uint32_t* __restrict__ info) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + 2 * TC_TILE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    info[0] = tmem_base;
+    info[1] = smem_base;
+    mbar_expect_tx(&bars[0], 2 * TC_TILE_BYTES);
+    if (A_MN) {
+      for (int j = 0; j < 4; ++j) tma_load_3d(smem_base + j * 4096, &tm_a, &bars[0], 32 * j, 0, 0);
+    } else {
+      tma_load_3d(smem_base, &tm_a, &bars[0], 0, 0, 0);
+    }
+    if (B_MN) {
+      for (int j = 0; j < 4; ++j) tma_load_3d(smem_base + TC_TILE_BYTES + j * 4096, &tm_b, &bars[0], 32 * j, 0, 0);
+    } else {
+      tma_load_3d(smem_base + TC_TILE_BYTES, &tm_b, &bars[0], 0, 0, 0);
+    }
+  }
+  mbar_wait(&bars[0], 0);
+  const float* sa = reinterpret_cast<const float*>(smem_al);
+  const float* sb = reinterpret_cast<const float*>(smem_al + TC_TILE_BYTES);
+  for (int i = threadIdx.x; i < 4096; i += 128) { dump_a[i] = sa[i]; dump_b[i] = sb[i]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tcgen05_fence_after();
+    const uint32_t idesc = make_idesc_tf32(128, 128, A_MN, B_MN);
+    info[2] = idesc;
+    for (int ks = 0; ks < nk; ++ks) {
+      const uint64_t da = make_sdesc<A_MN>(smem_base, ks);
+      const uint64_t db = make_sdesc<B_MN>(smem_base + TC_TILE_BYTES, ks);
+      if (ks == 0) { info[4] = (uint32_t)da; info[5] = (uint32_t)(da >> 32); info[6] = (uint32_t)db; info[7] = (uint32_t)(db >> 32); }
+      umma_tf32(tmem_base, da, db, idesc, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  tcgen05_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out_d[row * 128 + c * 32 + j] = __uint_as_float(v[j]);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
 }  // namespace tc
 }  // namespace pqn
 
@@ -375,6 +450,27 @@ int pqn_tc_split_lo(const float* x, float* lo, int64_t n, void* stream) {
     split_lo_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, lo, n / 4);
   }
   return check_launch("pqn_tc_split_lo");
+}
+
+// Debug hook (tests only): single 128x128x32 tile; a: [128][32] (a_mn=0) or [32][128] (a_mn=1); same for b.
+int pqn_tc_debug(const float* a, const float* b, float* dump_a, float* dump_b, float* out_d, uint32_t* info, int a_mn,
+                 int b_mn, int nk, void* stream) {
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn) { if ((rc = make_tmap(&ta, a, 128, 32, 1, 128, 4096, 32))) return rc; }
+  else { if ((rc = make_tmap(&ta, a, 32, 128, 1, 32, 4096, 128))) return rc; }
+  if (b_mn) { if ((rc = make_tmap(&tb, b, 128, 32, 1, 128, 4096, 32))) return rc; }
+  else { if ((rc = make_tmap(&tb, b, 32, 128, 1, 32, 4096, 128))) return rc; }
+  const int smem = 2 * TC_TILE_BYTES + 1024 + 64;
+  cudaStream_t st = (cudaStream_t)stream;
+#define PQN_DBG(A, B)                                                                                        \
+  if (a_mn == A && b_mn == B) {                                                                              \
+    cudaFuncSetAttribute(tc_debug_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
+    tc_debug_kernel<A, B><<<1, 128, smem, st>>>(ta, tb, dump_a, dump_b, out_d, nk, info);                    \
+  }
+  PQN_DBG(0, 0) PQN_DBG(0, 1) PQN_DBG(1, 0) PQN_DBG(1, 1)
+#undef PQN_DBG
+  return check_launch("pqn_tc_debug");
 }
 
 // Test hook: D[s] = A[s] . B[s] on the tcgen05 path (fp32 in, fp32 out).
