@@ -291,9 +291,10 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 3-D fp32 tensor [seeds][mid][inner] with a {32, box_mid, 1} SWIZZLE_128B box.
+// 3-D fp32 tensor [seeds][mid][inner] with a {32, box_mid, 1} box; SWIZZLE_128B for K-major operand tiles,
+// SWIZZLE_128B_ATOM_32B for MN-major ones (see make_sdesc).
 int make_tmap(CUtensorMap* tm, const float* base, uint64_t inner, uint64_t mid, uint64_t seeds, uint64_t mid_stride_elems,
-              uint64_t seed_stride_elems, uint32_t box_mid) {
+              uint64_t seed_stride_elems, uint32_t box_mid, int mn_major) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(PQN_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {inner, mid, seeds};
@@ -301,7 +302,9 @@ int make_tmap(CUtensorMap* tm, const float* base, uint64_t inner, uint64_t mid, 
   cuuint32_t box[3] = {32, box_mid, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(PQN_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return PQN_OK;
@@ -457,10 +460,10 @@ int pqn_tc_debug(const float* a, const float* b, float* dump_a, float* dump_b, f
                  int b_mn, int nk, void* stream) {
   CUtensorMap ta, tb;
   int rc;
-  if (a_mn) { if ((rc = make_tmap(&ta, a, 128, 32, 1, 128, 4096, 32))) return rc; }
-  else { if ((rc = make_tmap(&ta, a, 32, 128, 1, 32, 4096, 128))) return rc; }
-  if (b_mn) { if ((rc = make_tmap(&tb, b, 128, 32, 1, 128, 4096, 32))) return rc; }
-  else { if ((rc = make_tmap(&tb, b, 32, 128, 1, 32, 4096, 128))) return rc; }
+  if (a_mn) { if ((rc = make_tmap(&ta, a, 128, 32, 1, 128, 4096, 32, 1))) return rc; }
+  else { if ((rc = make_tmap(&ta, a, 32, 128, 1, 32, 4096, 128, 0))) return rc; }
+  if (b_mn) { if ((rc = make_tmap(&tb, b, 128, 32, 1, 128, 4096, 32, 1))) return rc; }
+  else { if ((rc = make_tmap(&tb, b, 32, 128, 1, 32, 4096, 128, 0))) return rc; }
   const int smem = 2 * TC_TILE_BYTES + 1024 + 64;
   cudaStream_t st = (cudaStream_t)stream;
 #define PQN_DBG(A, B)                                                                                        \
@@ -487,18 +490,18 @@ int pqn_tc_gemm_test(const float* a, const float* a_lo, const float* b, const fl
   const float* al = split3 ? a_lo : a;
   const float* bl = split3 ? b_lo : b;
   if (a_mn) {
-    if ((rc = make_tmap(&t[0], a, M, K, S, M, (uint64_t)M * K, 32))) return rc;
-    if ((rc = make_tmap(&t[1], al, M, K, S, M, (uint64_t)M * K, 32))) return rc;
+    if ((rc = make_tmap(&t[0], a, M, K, S, M, (uint64_t)M * K, 32, 1))) return rc;
+    if ((rc = make_tmap(&t[1], al, M, K, S, M, (uint64_t)M * K, 32, 1))) return rc;
   } else {
-    if ((rc = make_tmap(&t[0], a, K, M, S, K, (uint64_t)M * K, 128))) return rc;
-    if ((rc = make_tmap(&t[1], al, K, M, S, K, (uint64_t)M * K, 128))) return rc;
+    if ((rc = make_tmap(&t[0], a, K, M, S, K, (uint64_t)M * K, 128, 0))) return rc;
+    if ((rc = make_tmap(&t[1], al, K, M, S, K, (uint64_t)M * K, 128, 0))) return rc;
   }
   if (b_mn) {
-    if ((rc = make_tmap(&t[2], b, N, K, S, N, (uint64_t)N * K, 32))) return rc;
-    if ((rc = make_tmap(&t[3], bl, N, K, S, N, (uint64_t)N * K, 32))) return rc;
+    if ((rc = make_tmap(&t[2], b, N, K, S, N, (uint64_t)N * K, 32, 1))) return rc;
+    if ((rc = make_tmap(&t[3], bl, N, K, S, N, (uint64_t)N * K, 32, 1))) return rc;
   } else {
-    if ((rc = make_tmap(&t[2], b, K, N, S, K, (uint64_t)N * K, 128))) return rc;
-    if ((rc = make_tmap(&t[3], bl, K, N, S, K, (uint64_t)N * K, 128))) return rc;
+    if ((rc = make_tmap(&t[2], b, K, N, S, K, (uint64_t)N * K, 128, 0))) return rc;
+    if ((rc = make_tmap(&t[3], bl, K, N, S, K, (uint64_t)N * K, 128, 0))) return rc;
   }
   GemmShape gs;
   gs.S = S; gs.M = M; gs.m_tiles = (M + 127) / 128; gs.n_tiles = N / 128; gs.k_blocks = (K + TC_BK - 1) / TC_BK;

@@ -124,18 +124,21 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, i
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor) for a 128 x 32 fp32 operand tile in SWIZZLE_128B
 // atoms (8 rows x 128 B = 1024 B), k-step `ks` selects 8 of the 32 k values:
 //   K-major  tile: row r (MN index) at r*128 B; 8-row atoms every 1024 B (SBO); the k-step advances 32 B in the row.
-//   MN-major tile: 4 boxes of [32 k rows][32 mn] at 4096 B (LBO between MN atoms); k atoms (8 rows) every 1024 B (SBO).
+//   MN-major tile (32-bit types need the 32-byte-base swizzle, LayoutType SWIZZLE_128B_BASE32B = 1, written by TMA's
+//                  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4 boxes of [32 k rows][32 mn] at 4096 B (LBO between MN
+//                  atoms); atoms are [4 k][128 B] = 512 B (SBO between k atoms); one k-step (8 k) = 1024 B.
 template <int MN>
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t tile_addr, int ks) {
   const uint32_t addr = MN ? tile_addr + ks * 1024 : tile_addr + ks * 32;
   const uint64_t lbo = MN ? (4096u >> 4) : 1u;
-  const uint64_t sbo = 1024u >> 4;
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) /*version*/ | (2ull << 61) /*SWIZZLE_128B*/;
+  const uint64_t sbo = MN ? (512u >> 4) : (1024u >> 4);
+  const uint64_t layout = MN ? 1ull : 2ull;
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) /*version*/ | (layout << 61);
 }
 
 // host-side pieces used by other translation units (pqn_net.cu)
 int make_tmap(CUtensorMap* tm, const float* base, uint64_t inner, uint64_t mid, uint64_t seeds, uint64_t mid_stride_elems,
-              uint64_t seed_stride_elems, uint32_t box_mid);
+              uint64_t seed_stride_elems, uint32_t box_mid, int mn_major);
 int launch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep, cudaStream_t st);
 
 }  // namespace tc

@@ -37,13 +37,13 @@ for a_mn, b_mn in ((0, 0), (0, 1), (1, 1)):
                 for c in range(8):
                     out[r, c] = t[r, c ^ (r % 8)]
             return out.reshape(128, 32)
-        def unswz_mn(s):   # 4 boxes [32 k][32 mn]
-            t = s.reshape(4, 32, 8, 4)
+        def unswz_mn(s):   # 4 boxes [32 k][32 mn], 32-byte chunks XORed with k%4
+            t = s.reshape(4, 32, 4, 8)
             out = np.zeros((32, 128), np.float32)
             for j in range(4):
                 for k in range(32):
-                    for c in range(8):
-                        out[k, j * 32 + c * 4:j * 32 + c * 4 + 4] = t[j, k, c ^ (k % 8)]
+                    for c in range(4):
+                        out[k, j * 32 + c * 8:j * 32 + c * 8 + 8] = t[j, k, c ^ (k % 4)]
             return out
         ea = np.array_equal(unswz_mn(sa), a_st) if a_mn else np.array_equal(unswz_k(sa), a_st)
         eb = np.array_equal(unswz_mn(sb), b_st) if b_mn else np.array_equal(unswz_k(sb), b_st)
