@@ -27,97 +27,67 @@ namespace pqn {
 namespace tc {
 
 // ---------------------------------------------------------------------------
-// epilogues: each epilogue thread owns one row (TMEM lane) of the 128x128 tile
+// epilogues: each epilogue thread owns one row of the 128x128 tile, already
+// promoted to fp32 registers (acc[128], fully unrolled static indexing)
 // ---------------------------------------------------------------------------
 template <int EPI>
-__device__ __forceinline__ void epilogue_row(const EpiParams& ep, uint32_t tmem_row_addr, int seed, int m, int n0,
+__device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[128], int seed, int m, int n0,
                                              bool row_ok) {
   if constexpr (EPI == EPI_STORE || EPI == EPI_RELU_MASK) {
-    // plain (or ReLU-masked) store of the fp32 tile row
+    if (!row_ok) return;
     float* __restrict__ out = ep.out + (int64_t)seed * ep.out_seed_stride + (int64_t)m * ep.ld_out + n0;
     const float* __restrict__ msk =
         (EPI == EPI_RELU_MASK) ? ep.mask + (int64_t)seed * ep.out_seed_stride + (int64_t)m * ep.ld_out + n0 : nullptr;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_row_addr + c * 32, v);
-      tmem_ld_wait();
-      if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          if constexpr (EPI == EPI_RELU_MASK) {
-            const float4 h = *reinterpret_cast<const float4*>(msk + c * 32 + 4 * j);
-            o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f;
-            o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
-          }
-          *reinterpret_cast<float4*>(out + c * 32 + 4 * j) = o;
-        }
+    for (int j = 0; j < 32; ++j) {
+      float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+      if constexpr (EPI == EPI_RELU_MASK) {
+        const float4 h = *reinterpret_cast<const float4*>(msk + 4 * j);
+        o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f;
+        o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
       }
+      *reinterpret_cast<float4*>(out + 4 * j) = o;
     }
   } else {
-    // bias + LayerNorm(128) + ReLU, then either (h, xhat, rstd[, lo-splits]) or the fused Q-head
+    // bias + LayerNorm(128) + ReLU, then either (h, xhat, rstd) or the fused Q-head
     const float* __restrict__ prm = ep.params + (int64_t)seed * ep.P;
     float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_row_addr + c * 32, v);
-      tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float z = __uint_as_float(v[j]) + __ldg(prm + ep.off_b + c * 32 + j);
-        s1 += z;
-        s2 = fmaf(z, z, s2);
-      }
+    for (int j = 0; j < 128; ++j) {
+      acc[j] += __ldg(prm + ep.off_b + j);
+      s1 += acc[j];
+      s2 = fmaf(acc[j], acc[j], s2);
     }
     const float mean = s1 * (1.0f / 128.f);
     const float var = fmaxf(s2 * (1.0f / 128.f) - mean * mean, 0.f);
     const float rstd = 1.0f / sqrtf(var + 1e-6f);
-    float q[PQN_TC_MAX_A];
-#pragma unroll
-    for (int a = 0; a < PQN_TC_MAX_A; ++a) q[a] = 0.f;
     const int64_t grow = (int64_t)seed * ep.rows + m;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_row_addr + c * 32, v);
-      tmem_ld_wait();
-      float h[32], xh[32];
+    if constexpr (EPI == EPI_LN_TRAIN) {
+      if (!row_ok) return;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int col = c * 32 + j;
-        const float z = __uint_as_float(v[j]) + __ldg(prm + ep.off_b + col);
-        xh[j] = (z - mean) * rstd;
-        h[j] = fmaxf(xh[j] * __ldg(prm + ep.off_scale + col) + __ldg(prm + ep.off_bias + col), 0.f);
-      }
-      if constexpr (EPI == EPI_LN_TRAIN) {
-        if (row_ok) {
+        float xh[4], h[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            *reinterpret_cast<float4*>(ep.H + grow * 128 + c * 32 + 4 * j) =
-                make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-            *reinterpret_cast<float4*>(ep.XHAT + grow * 128 + c * 32 + 4 * j) =
-                make_float4(xh[4 * j], xh[4 * j + 1], xh[4 * j + 2], xh[4 * j + 3]);
-          }
+        for (int t = 0; t < 4; ++t) {
+          xh[t] = (acc[4 * j + t] - mean) * rstd;
+          h[t] = fmaxf(xh[t] * __ldg(prm + ep.off_scale + 4 * j + t) + __ldg(prm + ep.off_bias + 4 * j + t), 0.f);
         }
-      } else {  // EPI_LN_HEAD
-#pragma unroll
-        for (int a = 0; a < PQN_TC_MAX_A; ++a) {
-          if (a < ep.A) {
-            float acc = q[a];
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              acc = fmaf(h[j], __ldg(prm + ep.off_hw + (int64_t)(c * 32 + j) * ep.A + a), acc);
-            q[a] = acc;
-          }
-        }
+        *reinterpret_cast<float4*>(ep.H + grow * 128 + 4 * j) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(ep.XHAT + grow * 128 + 4 * j) = make_float4(xh[0], xh[1], xh[2], xh[3]);
       }
-    }
-    if (row_ok) {
-      if constexpr (EPI == EPI_LN_TRAIN) ep.RSTD[grow] = rstd;
-      else {
+      ep.RSTD[grow] = rstd;
+    } else {  // EPI_LN_HEAD
+      float q[PQN_TC_MAX_A];
+#pragma unroll
+      for (int a = 0; a < PQN_TC_MAX_A; ++a) q[a] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 128; ++j) {
+        const float h = fmaxf((acc[j] - mean) * rstd * __ldg(prm + ep.off_scale + j) + __ldg(prm + ep.off_bias + j), 0.f);
+#pragma unroll
+        for (int a = 0; a < PQN_TC_MAX_A; ++a)
+          if (a < ep.A) q[a] = fmaf(h, __ldg(prm + ep.off_hw + (int64_t)j * ep.A + a), q[a]);
+      }
+      if (row_ok) {
 #pragma unroll
         for (int a = 0; a < PQN_TC_MAX_A; ++a)
           if (a < ep.A) ep.Q[grow * ep.A + a] = q[a] + __ldg(prm + ep.off_hb + a);
@@ -126,8 +96,29 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, uint32_t tmem_
   }
 }
 
+// acc[0..128) += the 128 fp32 columns of this thread's TMEM lane at `row_addr`
+__device__ __forceinline__ void tmem_accumulate_row(uint32_t row_addr, float (&acc)[128]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(row_addr + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // the kernel
+//
+// Accuracy: the tensor core truncates (round-toward-zero) when it accumulates into TMEM, so a long in-TMEM
+// chain drifts (measured: 3e-5 relative at K=1024).  Two-level accumulation fixes it:
+//   * the correction terms A_lo.B_hi + A_hi.B_lo (2^-11 of the result) get their own TMEM accumulator for the
+//     whole K — their truncation error is negligible at that magnitude;
+//   * the main A_hi.B_hi chain is cut every TC_PROMOTE k-blocks (16 MMAs): the partial is added to fp32
+//     registers by the epilogue warps (round-to-nearest FADD) and the MMA warp continues into the other TMEM
+//     buffer with accumulate=0.
+// TMEM columns: main[2] at 0/128, corr[2] at 256/384.
 // ---------------------------------------------------------------------------
 template <int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -135,18 +126,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const GemmShape gs, const EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte aligned operand ring (SWIZZLE_128B atoms), then barriers
+  // 1024-byte aligned operand ring (swizzle atoms), then barriers
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + TC_STAGES * TC_STAGE_BYTES);
-  uint64_t* full = bars;                      // [TC_STAGES]
-  uint64_t* empty = bars + TC_STAGES;         // [TC_STAGES]
-  uint64_t* tmem_full = bars + 2 * TC_STAGES; // [2]
-  uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* full = bars;                        // [TC_STAGES]   TMA -> MMA
+  uint64_t* empty = bars + TC_STAGES;           // [TC_STAGES]   MMA -> TMA
+  uint64_t* main_full = bars + 2 * TC_STAGES;   // [2]           MMA -> epilogue (main partial ready)
+  uint64_t* main_empty = main_full + 2;         // [2]           epilogue -> MMA
+  uint64_t* corr_full = main_empty + 2;         // [2]
+  uint64_t* corr_empty = corr_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int passes = gs.split3 ? 3 : 1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_b_hi);
@@ -154,11 +146,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&main_full[i], 1); mbar_init(&main_empty[i], 4);
+      mbar_init(&corr_full[i], 1); mbar_init(&corr_empty[i], 4);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 256);  // 2 accumulator stages x 128 fp32 columns
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tcgen05_fence_before();
@@ -183,7 +178,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
           mbar_expect_tx(&full[stage], gs.split3 ? TC_STAGE_BYTES : TC_STAGE_BYTES / 2);
           const int k0 = kb * TC_BK;
-          // A tiles
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -194,7 +188,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             tma_load_3d(sb + TC_A_HI, &tm_a_hi, &full[stage], k0, m0, seed);
             if (gs.split3) tma_load_3d(sb + TC_A_LO, &tm_a_lo, &full[stage], k0, m0, seed);
           }
-          // B tiles
           if (B_MN) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -215,61 +208,93 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t idesc = make_idesc_tf32(128, 128, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      int mb = 0, cb = 0;
+      uint32_t mb_phase = 0, cb_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 128;
-        bool first = true;
+        const uint32_t d_corr = tmem_base + 256 + cb * 128;
+        if (gs.split3) {
+          mbar_wait(&corr_empty[cb], cb_phase ^ 1u);
+          tcgen05_fence_after();
+        }
+        bool first_corr = true, first_main = true;
         for (int kb = 0; kb < gs.k_blocks; ++kb) {
+          if (kb % TC_PROMOTE == 0) {
+            mbar_wait(&main_empty[mb], mb_phase ^ 1u);
+            tcgen05_fence_after();
+            first_main = true;
+          }
+          const uint32_t d_main = tmem_base + mb * 128;
           mbar_wait(&full[stage], phase);
           tcgen05_fence_after();
           const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
 #pragma unroll
           for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            // smallest terms first
-            for (int p = 0; p < passes; ++p) {
-              const bool a_lo = gs.split3 && (p == 0);
-              const bool b_lo = gs.split3 && (p == 1);
-              const uint64_t da = make_sdesc<A_MN>(sb + (a_lo ? TC_A_LO : TC_A_HI), ks);
-              const uint64_t db = make_sdesc<B_MN>(sb + (b_lo ? TC_B_LO : TC_B_HI), ks);
-              umma_tf32(d_tmem, da, db, idesc, first ? 0u : 1u);
-              first = false;
+            const uint64_t a_hi = make_sdesc<A_MN>(sb + TC_A_HI, ks);
+            const uint64_t b_hi = make_sdesc<B_MN>(sb + TC_B_HI, ks);
+            if (gs.split3) {
+              const uint64_t a_lo = make_sdesc<A_MN>(sb + TC_A_LO, ks);
+              const uint64_t b_lo = make_sdesc<B_MN>(sb + TC_B_LO, ks);
+              umma_tf32(d_corr, a_lo, b_hi, idesc, first_corr ? 0u : 1u);
+              umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+              first_corr = false;
             }
+            umma_tf32(d_main, a_hi, b_hi, idesc, first_main ? 0u : 1u);
+            first_main = false;
           }
           umma_commit(&empty[stage]);  // smem slot free once these MMAs retire
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+          if ((kb + 1) % TC_PROMOTE == 0 || kb == gs.k_blocks - 1) {
+            umma_commit(&main_full[mb]);  // main partial ready for promotion
+            if (++mb == 2) { mb = 0; mb_phase ^= 1u; }
+          }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (gs.split3) {
+          umma_commit(&corr_full[cb]);
+          if (++cb == 2) { cb = 0; cb_phase ^= 1u; }
+        }
       }
     }
   } else {
     // ===================== epilogue warps (2..5) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access (warp id % 4)
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    int mb = 0, cb = 0;
+    uint32_t mb_phase = 0, cb_phase = 0;
+    const int partials = (gs.k_blocks + TC_PROMOTE - 1) / TC_PROMOTE;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int seed = tile / tiles_per_seed;
       const int rem = tile - seed * tiles_per_seed;
       const int m0 = (rem / gs.n_tiles) * 128, n0 = (rem % gs.n_tiles) * 128;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
+      float acc[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      for (int pi = 0; pi < partials; ++pi) {
+        mbar_wait(&main_full[mb], mb_phase);
+        tcgen05_fence_after();
+        tmem_accumulate_row(tmem_base + mb * 128 + lane_off, acc);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&main_empty[mb]);
+        if (++mb == 2) { mb = 0; mb_phase ^= 1u; }
+      }
+      if (gs.split3) {
+        mbar_wait(&corr_full[cb], cb_phase);
+        tcgen05_fence_after();
+        tmem_accumulate_row(tmem_base + 256 + cb * 128 + lane_off, acc);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&corr_empty[cb]);
+        if (++cb == 2) { cb = 0; cb_phase ^= 1u; }
+      }
       const int m = m0 + quad * 32 + lane;
-      const uint32_t row_addr = tmem_base + acc * 128 + ((uint32_t)(quad * 32) << 16);
-      epilogue_row<EPI>(ep, row_addr, seed, m, n0, m < gs.M);
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      epilogue_row<EPI>(ep, acc, seed, m, n0, m < gs.M);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 

@@ -9,6 +9,7 @@ namespace tc {
 constexpr int TC_THREADS = 192;          // warp0 TMA, warp1 MMA, warps 2-5 epilogue (warp2 also owns TMEM alloc)
 constexpr int TC_BK = 32;                // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int TC_STAGES = 3;
+constexpr int TC_PROMOTE = 4;             // k-blocks (of 32) per in-TMEM main chain before promotion to registers
 constexpr int TC_TILE_BYTES = 128 * TC_BK * 4;   // 16 KB
 constexpr int TC_A_HI = 0, TC_A_LO = TC_TILE_BYTES, TC_B_HI = 2 * TC_TILE_BYTES, TC_B_LO = 3 * TC_TILE_BYTES;
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;  // 64 KB
