@@ -202,6 +202,10 @@ int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu,
 int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F, float count, float momentum,
                         void* stream);
 
+/* The CNN's dense layer (forward, wgrad, dgrad) runs on the tcgen05 3xTF32 path by default; 0 selects the
+ * fp32 FFMA kernels instead (kept as the A/B reference for parity tests). */
+int pqn_set_tensor_core_path(int on);
+
 /* ---- tcgen05 (5th-gen tensor core) path of the dense contractions ----------
  * lo[i] = x[i] - trunc_tf32(x[i]): the error-compensation operand of 3xTF32. */
 int pqn_tc_split_lo(const float* x, float* lo, int64_t n, void* stream);

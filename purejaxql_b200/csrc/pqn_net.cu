@@ -16,6 +16,7 @@
 
 #include "../../include/pqn_b200.h"
 #include "api_common.h"
+#include "tc_common.cuh"
 
 namespace pqn {
 
@@ -26,6 +27,9 @@ constexpr int CONV_O = 16;   // conv output channels
 constexpr int CONV_PIX = 64; // 8x8 output pixels
 constexpr int HID_CNN = 128;
 constexpr int FLAT_CNN = CONV_PIX * CONV_O;  // 1024
+
+// tcgen05 path for the CNN dense layer (pqn_set_tensor_core_path); default on
+static int g_use_tc = 1;
 
 static inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
 
@@ -424,7 +428,7 @@ constexpr int RB_ROWS = 128;  // rows per CTA (8 warps x 16)
 template <int N, bool HEAD>
 __global__ void __launch_bounds__(256) row_bwd_kernel(
     const float* __restrict__ Hh, const float* __restrict__ XHAT, const float* __restrict__ RSTD,
-    const float* DH, float* DZ, const float* __restrict__ params, float* __restrict__ grads, int64_t P,
+    const float* DH, float* DZ, float* DZLO, const float* __restrict__ params, float* __restrict__ grads, int64_t P,
     int64_t off_scale, int64_t off_dscale, int64_t off_dbias, int64_t off_db, int64_t off_hw, int64_t off_hb, int A,
     const int32_t* __restrict__ gather, const int32_t* __restrict__ action, const float* __restrict__ target,
     int64_t tr_rows_per_seed, float* __restrict__ loss_sum, float* __restrict__ qsa_sum, int rows) {
@@ -528,8 +532,14 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
     }
 #pragma unroll
     for (int c = 0; c < F / 4; ++c)
+    {
       *reinterpret_cast<float4*>(DZ + grow * N + c * 128 + lane * 4) =
           make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
+      if (DZLO != nullptr)
+        *reinterpret_cast<float4*>(DZLO + grow * N + c * 128 + lane * 4) =
+            make_float4(tc::tf32_lo(dz[4 * c]), tc::tf32_lo(dz[4 * c + 1]), tc::tf32_lo(dz[4 * c + 2]),
+                        tc::tf32_lo(dz[4 * c + 3]));
+    }
   }
   // combine warps in shared memory, then one global atomic per element per CTA
 #pragma unroll
@@ -640,7 +650,8 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const uint32_t* __restric
                                                        const int32_t* __restrict__ gather,
                                                        const float* __restrict__ params, int64_t P,
                                                        pqn_net_layout_t L, float* __restrict__ H1,
-                                                       float* __restrict__ bn_sums, int rows) {
+                                                       float* __restrict__ H1LO, float* __restrict__ bn_sums,
+                                                       int rows) {
   using Cfg = ConvCfg<C>;
   __shared__ __align__(16) float ws[Cfg::TAPS * CONV_O];
   __shared__ float cb[CONV_O], sc[CONV_O], bi[CONV_O];
@@ -676,6 +687,11 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const uint32_t* __restric
       v.z = fmaxf((acc[4 * o4 + 2] - mean) * rstd * sc[4 * o4 + 2] + bi[4 * o4 + 2], 0.f);
       v.w = fmaxf((acc[4 * o4 + 3] - mean) * rstd * sc[4 * o4 + 3] + bi[4 * o4 + 3], 0.f);
       out[o4] = v;
+      if (H1LO != nullptr) {  // 3xTF32 error-compensation operand for the tcgen05 GEMMs
+        float4* __restrict__ olo =
+            reinterpret_cast<float4*>(H1LO + ((int64_t)seed * rows + row) * FLAT_CNN + pix * CONV_O);
+        olo[o4] = make_float4(tc::tf32_lo(v.x), tc::tf32_lo(v.y), tc::tf32_lo(v.z), tc::tf32_lo(v.w));
+      }
     }
   }
   if (TRAIN && bn_sums != nullptr) {
@@ -865,6 +881,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ obs, int64_t obs_ro
 struct Workspace {
   // CNN
   float *h1, *h2, *xhat2, *rstd2, *dz2;
+  float *h1_lo, *dz2_lo, *w1_lo;  // 3xTF32 "lo" operands of the tcgen05 path
   // MLP
   float *xg, *h0, *xhat0, *rstd0, *hh1, *xhat1, *rstd1, *dzl, *dh0;
 };
@@ -885,6 +902,9 @@ static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* bas
     ww->xhat2 = take(R * HID_CNN);
     ww->rstd2 = take(R);
     ww->dz2 = take(R * HID_CNN);
+    ww->h1_lo = take(R * FLAT_CNN);
+    ww->dz2_lo = take(R * HID_CNN);
+    ww->w1_lo = take((int64_t)S * FLAT_CNN * HID_CNN);
   } else {
     const int H = d->hidden;
     ww->xg = take(R * d->in_c);
@@ -914,12 +934,13 @@ static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1
 
 template <bool TRAIN>
 static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
-                           const float* params, int64_t P, const pqn_net_layout_t& L, float* h1, float* bn, int rows) {
+                           const float* params, int64_t P, const pqn_net_layout_t& L, float* h1, float* h1lo, float* bn,
+                           int rows) {
   switch (C) {
-    case 4: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<4, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); } break;
-    case 6: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<6, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); } break;
-    case 7: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<7, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); } break;
-    case 10: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<10, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, bn, rows); } break;
+    case 4: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<4, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
+    case 6: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<6, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
+    case 7: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<7, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
+    case 10: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<10, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
     default: return -1;
   }
   return 0;
@@ -933,11 +954,85 @@ static int wgrad_splits(int tiles, int S, int rows) {
   return s;
 }
 
+// lo = x - trunc_tf32(x) for the per-seed weight block W1 (source rows at stride P)
+__global__ void split_lo_strided_kernel(const float* __restrict__ src, int64_t src_seed_stride, float* __restrict__ lo,
+                                        int64_t n_per_seed) {
+  const int seed = blockIdx.y;
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n_per_seed) return;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)seed * src_seed_stride) + i4);
+  reinterpret_cast<float4*>(lo + (int64_t)seed * n_per_seed)[i4] =
+      make_float4(tc::tf32_lo(v.x), tc::tf32_lo(v.y), tc::tf32_lo(v.z), tc::tf32_lo(v.w));
+}
+
+static void launch_split_w1(const float* params, int64_t P, int64_t off_w, float* w1_lo, int S, cudaStream_t st) {
+  const int64_t n = (int64_t)FLAT_CNN * HID_CNN;
+  LaunchScope _ls(K_TC_SPLIT, st);
+  split_lo_strided_kernel<<<dim3(cdiv(n / 4, 256), S), 256, 0, st>>>(params + off_w, P, w1_lo, n);
+}
+
+// Z = H1 . W1 on the tcgen05 path with the LayerNorm/ReLU(/head) epilogue.  epi = EPI_LN_TRAIN or EPI_LN_HEAD.
+static int tc_dense_fwd(int epi, const float* params, int64_t P, const pqn_net_layout_t& L, const Workspace& w, int A,
+                        float* q, int S, int rows, cudaStream_t st) {
+  CUtensorMap t[4];
+  int rc;
+  if ((rc = tc::make_tmap(&t[0], w.h1, FLAT_CNN, rows, S, FLAT_CNN, (uint64_t)rows * FLAT_CNN, 128, 0))) return rc;
+  if ((rc = tc::make_tmap(&t[1], w.h1_lo, FLAT_CNN, rows, S, FLAT_CNN, (uint64_t)rows * FLAT_CNN, 128, 0))) return rc;
+  if ((rc = tc::make_tmap(&t[2], params + L.d0_w, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)P, 32, 1))) return rc;
+  if ((rc = tc::make_tmap(&t[3], w.w1_lo, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)FLAT_CNN * HID_CNN, 32, 1))) return rc;
+  tc::GemmShape gs;
+  gs.S = S; gs.M = rows; gs.m_tiles = (rows + 127) / 128; gs.n_tiles = 1; gs.k_blocks = FLAT_CNN / tc::TC_BK; gs.split3 = 1;
+  tc::EpiParams ep = {};
+  ep.params = params; ep.P = P; ep.off_b = L.d0_b; ep.off_scale = L.ln1_scale; ep.off_bias = L.ln1_bias;
+  ep.off_hw = L.head_w; ep.off_hb = L.head_b; ep.A = A; ep.rows = rows;
+  ep.H = w.h2; ep.XHAT = w.xhat2; ep.RSTD = w.rstd2; ep.Q = q;
+  return tc::launch_gemm(0, 1, epi, t, gs, ep, st);
+}
+
+// dW1 = H1^T . dZ2  -> grads[d0_w]
+static int tc_wgrad(float* grads, int64_t P, const pqn_net_layout_t& L, const Workspace& w, int S, int rows,
+                    cudaStream_t st) {
+  CUtensorMap t[4];
+  int rc;
+  if ((rc = tc::make_tmap(&t[0], w.h1, FLAT_CNN, rows, S, FLAT_CNN, (uint64_t)rows * FLAT_CNN, 32, 1))) return rc;
+  if ((rc = tc::make_tmap(&t[1], w.h1_lo, FLAT_CNN, rows, S, FLAT_CNN, (uint64_t)rows * FLAT_CNN, 32, 1))) return rc;
+  if ((rc = tc::make_tmap(&t[2], w.dz2, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 32, 1))) return rc;
+  if ((rc = tc::make_tmap(&t[3], w.dz2_lo, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 32, 1))) return rc;
+  tc::GemmShape gs;
+  gs.S = S; gs.M = FLAT_CNN; gs.m_tiles = FLAT_CNN / 128; gs.n_tiles = 1; gs.k_blocks = (rows + tc::TC_BK - 1) / tc::TC_BK;
+  gs.split3 = 1;
+  tc::EpiParams ep = {};
+  ep.out = grads + L.d0_w; ep.ld_out = HID_CNN; ep.out_seed_stride = P;
+  return tc::launch_gemm(1, 1, tc::EPI_STORE, t, gs, ep, st);
+}
+
+// dY1 = relu_mask(H1) * (dZ2 . W1^T), written in place over H1
+static int tc_dgrad(const float* params, int64_t P, const pqn_net_layout_t& L, const Workspace& w, int S, int rows,
+                    cudaStream_t st) {
+  CUtensorMap t[4];
+  int rc;
+  if ((rc = tc::make_tmap(&t[0], w.dz2, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 128, 0))) return rc;
+  if ((rc = tc::make_tmap(&t[1], w.dz2_lo, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 128, 0))) return rc;
+  if ((rc = tc::make_tmap(&t[2], params + L.d0_w, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)P, 128, 0))) return rc;
+  if ((rc = tc::make_tmap(&t[3], w.w1_lo, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)FLAT_CNN * HID_CNN, 128, 0))) return rc;
+  tc::GemmShape gs;
+  gs.S = S; gs.M = rows; gs.m_tiles = (rows + 127) / 128; gs.n_tiles = FLAT_CNN / 128; gs.k_blocks = HID_CNN / tc::TC_BK;
+  gs.split3 = 1;
+  tc::EpiParams ep = {};
+  ep.out = w.h1; ep.mask = w.h1; ep.ld_out = FLAT_CNN; ep.out_seed_stride = (int64_t)rows * FLAT_CNN;
+  return tc::launch_gemm(0, 0, tc::EPI_RELU_MASK, t, gs, ep, st);
+}
+
 }  // namespace pqn
 
 using namespace pqn;
 
 extern "C" {
+
+int pqn_set_tensor_core_path(int on) {
+  g_use_tc = on ? 1 : 0;
+  return PQN_OK;
+}
 
 int pqn_net_layout(const pqn_net_desc_t* d, pqn_net_layout_t* out) {
   int rc = check_desc(d, "pqn_net_layout");
@@ -965,10 +1060,17 @@ int pqn_qnet_forward(const pqn_net_desc_t* d, const float* params, const void* o
   carve(d, S, rows, (char*)workspace, &w);
   const int A = d->num_actions;
   if (d->kind == PQN_NET_MINATAR_CNN) {
+    const bool use_tc = g_use_tc && A <= PQN_TC_MAX_A;
     launch_conv_fwd<false>(d->in_c, dim3(cdiv(rows, 4), S), st, (const uint32_t*)obs, obs_rows_per_seed, gather, params,
-                           L.total, L, w.h1, nullptr, (int)rows);
-    launch_dense<2>(128, dim3(cdiv(rows, 128), S), st, w.h1, rows * FLAT_CNN, FLAT_CNN, params, L.total, L.d0_w, L.d0_b,
-                    L.ln1_scale, L.ln1_bias, L.head_w, L.head_b, A, nullptr, nullptr, nullptr, q, (int)rows, FLAT_CNN);
+                           L.total, L, w.h1, use_tc ? w.h1_lo : nullptr, nullptr, (int)rows);
+    if (use_tc) {
+      launch_split_w1(params, L.total, L.d0_w, w.w1_lo, S, st);
+      if ((rc = tc_dense_fwd(tc::EPI_LN_HEAD, params, L.total, L, w, A, q, S, (int)rows, st))) return rc;
+    } else {
+      launch_dense<2>(128, dim3(cdiv(rows, 128), S), st, w.h1, rows * FLAT_CNN, FLAT_CNN, params, L.total, L.d0_w,
+                      L.d0_b, L.ln1_scale, L.ln1_bias, L.head_w, L.head_b, A, nullptr, nullptr, nullptr, q, (int)rows,
+                      FLAT_CNN);
+    }
   } else {
     const int D = d->in_c, H = d->hidden;
     const float* x = (const float*)obs;
@@ -1015,21 +1117,32 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
 
   if (d->kind == PQN_NET_MINATAR_CNN) {
     const uint32_t* ob = (const uint32_t*)obs;
+    const bool use_tc = g_use_tc && A <= PQN_TC_MAX_A;
     launch_conv_fwd<true>(d->in_c, dim3(cdiv(rows, 4), S), st, ob, obs_rows_per_seed, gather, params, P, L, w.h1,
-                          bn_sums, R);
-    launch_dense<1>(128, dim3(cdiv(rows, 128), S), st, w.h1, rows * FLAT_CNN, FLAT_CNN, params, P, L.d0_w, L.d0_b,
-                    L.ln1_scale, L.ln1_bias, 0, 0, A, w.h2, w.xhat2, w.rstd2, nullptr, R, FLAT_CNN);
+                          use_tc ? w.h1_lo : nullptr, bn_sums, R);
+    if (use_tc) {
+      launch_split_w1(params, P, L.d0_w, w.w1_lo, S, st);
+      if ((rc = tc_dense_fwd(tc::EPI_LN_TRAIN, params, P, L, w, A, nullptr, S, R, st))) return rc;
+    } else {
+      launch_dense<1>(128, dim3(cdiv(rows, 128), S), st, w.h1, rows * FLAT_CNN, FLAT_CNN, params, P, L.d0_w, L.d0_b,
+                      L.ln1_scale, L.ln1_bias, 0, 0, A, w.h2, w.xhat2, w.rstd2, nullptr, R, FLAT_CNN);
+    }
     const size_t sm = (size_t)(3 * 128 + A * 128 + A + 2) * sizeof(float);
     { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, true><<<dim3(cdiv(rows, RB_ROWS), S), 256, sm, st>>>(
-        w.h2, w.xhat2, w.rstd2, nullptr, w.dz2, params, grads, P, L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d0_b,
+        w.h2, w.xhat2, w.rstd2, nullptr, w.dz2, use_tc ? w.dz2_lo : nullptr, params, grads, P, L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d0_b,
         L.head_w, L.head_b, A, gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, R); }
-    const int splits = wgrad_splits(FLAT_CNN / 128, S, R);
-    { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(FLAT_CNN / 128, 1, S * splits), GT, 0, st>>>(w.h1, rows * FLAT_CNN, FLAT_CNN, w.dz2,
-                                                                     rows * HID_CNN, HID_CNN, grads, P, L.d0_w, R,
-                                                                     FLAT_CNN, splits); }
-    { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), FLAT_CNN / 128, S), GT, 0, st>>>(w.dz2, rows * HID_CNN, HID_CNN, params, P,
-                                                                          L.d0_w, w.h1, w.h1, rows * FLAT_CNN, R,
-                                                                          FLAT_CNN); }
+    if (use_tc) {
+      if ((rc = tc_wgrad(grads, P, L, w, S, R, st))) return rc;
+      if ((rc = tc_dgrad(params, P, L, w, S, R, st))) return rc;
+    } else {
+      const int splits = wgrad_splits(FLAT_CNN / 128, S, R);
+      { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(FLAT_CNN / 128, 1, S * splits), GT, 0, st>>>(w.h1, rows * FLAT_CNN, FLAT_CNN, w.dz2,
+                                                                       rows * HID_CNN, HID_CNN, grads, P, L.d0_w, R,
+                                                                       FLAT_CNN, splits); }
+      { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), FLAT_CNN / 128, S), GT, 0, st>>>(w.dz2, rows * HID_CNN, HID_CNN, params, P,
+                                                                            L.d0_w, w.h1, w.h1, rows * FLAT_CNN, R,
+                                                                            FLAT_CNN); }
+    }
     dim3 cg(cdiv(rows, CONV_BWD_SPB), S);
     switch (d->in_c) {
       case 4: { LaunchScope _ls(K_CONV_BWD, st); conv_bwd_kernel<4><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); } break;
@@ -1051,12 +1164,12 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
       launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.h0, rows * H, H, params, P, L.d1_w, L.d1_b, L.ln1_scale,
                       L.ln1_bias, 0, 0, A, w.hh1, w.xhat1, w.rstd1, nullptr, R, H);
       if (H == 128)
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, params, grads, P,
                                                         L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }
       else
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, params, grads, P,
                                                         L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }
@@ -1067,11 +1180,11 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
       { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(w.dzl, rows * H, H, params, P, L.d1_w, w.h0,
                                                                      w.dh0, rows * H, R, H); }
       if (H == 128)
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, params, grads, P,
                                                          L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
                                                          nullptr, nullptr, nullptr, 0, nullptr, nullptr, R); }
       else
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, params, grads, P,
                                                          L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
                                                          nullptr, nullptr, nullptr, 0, nullptr, nullptr, R); }
       const int sp0 = wgrad_splits(H / 128, S, R);
@@ -1079,12 +1192,12 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
                                                                         P, L.d0_w, R, D, sp0); }
     } else {
       if (H == 128)
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, params, grads, P,
                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }
       else
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, params, grads, P,
+        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, params, grads, P,
                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }

@@ -35,8 +35,9 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[1
                                              bool row_ok) {
   if constexpr (EPI == EPI_STORE || EPI == EPI_RELU_MASK) {
     if (!row_ok) return;
-    float* __restrict__ out = ep.out + (int64_t)seed * ep.out_seed_stride + (int64_t)m * ep.ld_out + n0;
-    const float* __restrict__ msk =
+    // no __restrict__: dgrad runs in place (out == mask)
+    float* out = ep.out + (int64_t)seed * ep.out_seed_stride + (int64_t)m * ep.ld_out + n0;
+    const float* msk =
         (EPI == EPI_RELU_MASK) ? ep.mask + (int64_t)seed * ep.out_seed_stride + (int64_t)m * ep.ld_out + n0 : nullptr;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {

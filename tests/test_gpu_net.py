@@ -52,8 +52,17 @@ def _ws(spec, S, rows):
     return torch.empty(n, dtype=torch.uint8, device=dev())
 
 
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "ffma"])
+def dense_path(request):
+    """Runs the CNN tests on both dense-layer implementations (tcgen05 3xTF32 and fp32 FFMA)."""
+    from purejaxql_b200 import _lib
+    _lib.lib().pqn_set_tensor_core_path(request.param)
+    yield request.param
+    _lib.lib().pqn_set_tensor_core_path(1)
+
+
 @pytest.mark.parametrize("rows", [1, 130, 515])
-def test_cnn_forward_matches_oracle_1e5(rows):
+def test_cnn_forward_matches_oracle_1e5(rows, dense_path):
     from purejaxql_b200 import _lib
     S = 3
     spec, ps, flat = _cnn_setup(S, rows)
@@ -71,7 +80,7 @@ def test_cnn_forward_matches_oracle_1e5(rows):
         assert np.abs(q[s] - ref32).max() < 1e-5
 
 
-def test_cnn_forward_other_channel_counts_and_gather():
+def test_cnn_forward_other_channel_counts_and_gather(dense_path):
     from purejaxql_b200 import _lib
     rng = np.random.default_rng(1)
     for C in (6, 7, 10):
@@ -138,7 +147,7 @@ def _cmp_grads(spec, grads, ref_g, s, tag):
 
 
 @pytest.mark.parametrize("rows,total", [(64, 200), (300, 1000), (1024, 4096)])
-def test_cnn_loss_grad_matches_oracle(rows, total):
+def test_cnn_loss_grad_matches_oracle(rows, total, dense_path):
     S = 2
     spec, ps, flat = _cnn_setup(S, rows)
     rng = np.random.default_rng(rows)
