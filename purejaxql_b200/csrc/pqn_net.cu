@@ -714,143 +714,161 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const uint32_t* __restric
   }
 }
 
-// conv backward: recompute z1/LN, LN backward from DY1 (already ReLU-masked),
-// accumulate d(ln0 scale/bias), d(conv bias), d(conv kernel).
-// CTA = CONV_BWD_SPB samples in chunks of 4; grid = (ceil(rows/SPB), S)
-constexpr int CONV_BWD_SPB = 32;
-constexpr int SDZ_LD = 20;  // padded row of the staged dz (conflict-free 128-bit stores)
+// conv backward, one warp per sample (no block-level sync in the loop):
+//   phase A  lane = output pixel (2 per lane): recompute conv + LN statistics, LN backward from DY1 (already
+//            ReLU-masked by dgrad) -> dz staged in the warp's shared memory; d(ln0 scale/bias) in registers.
+//   phase B  dW[tap][o] += x[pixel+tap] * dz[pixel][o] driven by the SET input bits only (MinAtar observations
+//            are sparse): for each set bit (input pixel q, channel c) the 9 taps that see it add dz[q - tap][:]
+//            into lane-private accumulators; lane = (tap parity, o), accumulators indexed [c][tap/2] statically.
+//   d(conv bias)[o] = sum over pixels of dz, also taken from the staged dz.
+// grid = (CONV_BWD_CTAS_X, S); each CTA strides over the seed's samples 8 at a time.
+constexpr int CONV_BWD_WARPS = 8;
+constexpr int SDZ_LD = 20;  // padded dz row (conflict-free 128-bit stores from 32 pixel-lanes)
 
 template <int C>
-__global__ void __launch_bounds__(256) conv_bwd_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed,
-                                                       const int32_t* __restrict__ gather,
-                                                       const float* __restrict__ params, int64_t P,
-                                                       pqn_net_layout_t L, const float* __restrict__ DY1,
-                                                       float* __restrict__ grads, int rows) {
+__global__ void __launch_bounds__(CONV_BWD_WARPS * 32, 2)
+    conv_bwd_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
+                    const float* __restrict__ params, int64_t P, pqn_net_layout_t L, const float* __restrict__ DY1,
+                    float* __restrict__ grads, int rows) {
   using Cfg = ConvCfg<C>;
   constexpr int TAPS = Cfg::TAPS;
-  constexpr int G = 256 / TAPS;  // entry groups in phase B
   __shared__ __align__(16) float ws[TAPS * CONV_O];
   __shared__ float cb[CONV_O], sc[CONV_O], bi[CONV_O];
-  __shared__ uint32_t so[4][Cfg::SW];
-  __shared__ __align__(16) float sdz[256 * SDZ_LD];
+  __shared__ uint32_t so[CONV_BWD_WARPS][Cfg::SW];
+  __shared__ __align__(16) float sdz[CONV_BWD_WARPS][CONV_PIX * SDZ_LD];
   __shared__ float s_red[3 * CONV_O];
-  const int tid = threadIdx.x, sl = tid >> 6, pix = tid & 63;
+  float* s_w = &sdz[0][0];  // [TAPS*16], aliases the dz staging area once the sample loop is done
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int seed = blockIdx.y;
   const float* __restrict__ prm = params + (int64_t)seed * P;
   conv_load_consts<C>(prm, L, ws, cb, sc, bi);
   if (tid < 3 * CONV_O) s_red[tid] = 0.f;
-  const int y = pix >> 3, x = pix & 7;
-  float a_dsc[CONV_O], a_dbi[CONV_O], a_dcb[CONV_O];
-#pragma unroll
-  for (int o = 0; o < CONV_O; ++o) a_dsc[o] = a_dbi[o] = a_dcb[o] = 0.f;
-  // phase-B role
-  const int tap = tid % TAPS, grp = tid / TAPS;
-  const bool b_active = grp < G;
-  const int t_c = tap % C, t_dj = (tap / C) % 3, t_di = tap / (3 * C);
-  float wacc[CONV_O];
-#pragma unroll
-  for (int o = 0; o < CONV_O; ++o) wacc[o] = 0.f;
+  __syncthreads();
 
-  const int row_base = blockIdx.x * CONV_BWD_SPB;
-  for (int ch = 0; ch < CONV_BWD_SPB / 4; ++ch) {
-    const int row = row_base + ch * 4 + sl;
-    const bool valid = row < rows;
-    __syncthreads();  // previous chunk's phase B is done with so/sdz (also orders the const loads)
-    if (pix < Cfg::SW) {
-      uint32_t w = 0u;
-      if (valid && pix < Cfg::PW) {
-        const int64_t src = gather ? gather[(int64_t)seed * rows + row] : row;
-        w = __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + pix);
-      }
-      so[sl][pix] = w;
-    }
-    __syncthreads();
-    // ---- phase A: per-pixel LN backward
+  float a_dsc[CONV_O], a_dbi[CONV_O];
+#pragma unroll
+  for (int o = 0; o < CONV_O; ++o) a_dsc[o] = a_dbi[o] = 0.f;
+  // phase-B role: lane = (tap parity, output channel); 5 iterations cover the 9 taps
+  const int o_b = lane & 15, tpar = lane >> 4;
+  int t_di[5], t_dj[5];
+#pragma unroll
+  for (int it = 0; it < 5; ++it) {
+    const int tap = it * 2 + tpar;
+    t_di[it] = tap < 9 ? tap / 3 : 100;  // 100 => never valid
+    t_dj[it] = tap < 9 ? tap % 3 : 0;
+  }
+  float wacc[C][5];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int it = 0; it < 5; ++it) wacc[c][it] = 0.f;
+  float a_dcb = 0.f;  // lane (tpar, o): sum of dz[pixel][o] over pixels of parity tpar
+
+  uint32_t* __restrict__ my_so = so[warp];
+  float* __restrict__ my_dz = sdz[warp];
+  for (int row = blockIdx.x * CONV_BWD_WARPS + warp; row < rows; row += gridDim.x * CONV_BWD_WARPS) {
+    __syncwarp();
     {
+      const int64_t src = gather ? gather[(int64_t)seed * rows + row] : row;
+      const uint32_t* __restrict__ orow = obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW;
+      for (int wi = lane; wi < Cfg::SW; wi += 32) my_so[wi] = wi < Cfg::PW ? __ldg(orow + wi) : 0u;
+    }
+    __syncwarp();
+    // ---- phase A: two output pixels per lane
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+      const int pix = lane + 32 * hh;
       float acc[CONV_O];
-      conv_pixel<C>(so[sl], ws, cb, y, x, acc);
+      conv_pixel<C>(my_so, ws, cb, pix >> 3, pix & 7, acc);
       float mean, rstd;
       ln16(acc, mean, rstd);
-      float dz[CONV_O];
-      if (valid) {
-        const float4* __restrict__ dyp =
-            reinterpret_cast<const float4*>(DY1 + ((int64_t)seed * rows + row) * FLAT_CNN + pix * CONV_O);
-        float dy[CONV_O];
+      const float4* __restrict__ dyp =
+          reinterpret_cast<const float4*>(DY1 + ((int64_t)seed * rows + row) * FLAT_CNN + pix * CONV_O);
+      float dy[CONV_O];
 #pragma unroll
-        for (int o4 = 0; o4 < CONV_O / 4; ++o4) {
-          const float4 v = __ldg(dyp + o4);
-          dy[4 * o4] = v.x; dy[4 * o4 + 1] = v.y; dy[4 * o4 + 2] = v.z; dy[4 * o4 + 3] = v.w;
-        }
-        float m1 = 0.f, m2 = 0.f, xh[CONV_O], dxh[CONV_O];
-#pragma unroll
-        for (int o = 0; o < CONV_O; ++o) {
-          xh[o] = (acc[o] - mean) * rstd;
-          a_dsc[o] = fmaf(dy[o], xh[o], a_dsc[o]);
-          a_dbi[o] += dy[o];
-          dxh[o] = dy[o] * sc[o];
-          m1 += dxh[o];
-          m2 = fmaf(dxh[o], xh[o], m2);
-        }
-        m1 *= (1.0f / CONV_O);
-        m2 *= (1.0f / CONV_O);
-#pragma unroll
-        for (int o = 0; o < CONV_O; ++o) {
-          dz[o] = rstd * (dxh[o] - m1 - xh[o] * m2);
-          a_dcb[o] += dz[o];
-        }
-      } else {
-#pragma unroll
-        for (int o = 0; o < CONV_O; ++o) dz[o] = 0.f;
+      for (int o4 = 0; o4 < CONV_O / 4; ++o4) {
+        const float4 v = __ldg(dyp + o4);
+        dy[4 * o4] = v.x; dy[4 * o4 + 1] = v.y; dy[4 * o4 + 2] = v.z; dy[4 * o4 + 3] = v.w;
       }
+      float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-      for (int o4 = 0; o4 < CONV_O / 4; ++o4)
-        *reinterpret_cast<float4*>(&sdz[tid * SDZ_LD + 4 * o4]) =
-            make_float4(dz[4 * o4], dz[4 * o4 + 1], dz[4 * o4 + 2], dz[4 * o4 + 3]);
+      for (int o = 0; o < CONV_O; ++o) {
+        acc[o] = (acc[o] - mean) * rstd;  // xhat
+        a_dsc[o] = fmaf(dy[o], acc[o], a_dsc[o]);
+        a_dbi[o] += dy[o];
+        dy[o] *= sc[o];                   // dxhat
+        m1 += dy[o];
+        m2 = fmaf(dy[o], acc[o], m2);
+      }
+      m1 *= (1.0f / CONV_O);
+      m2 *= (1.0f / CONV_O);
+#pragma unroll
+      for (int o4 = 0; o4 < CONV_O / 4; ++o4) {
+        float4 dz;
+        dz.x = rstd * (dy[4 * o4] - m1 - acc[4 * o4] * m2);
+        dz.y = rstd * (dy[4 * o4 + 1] - m1 - acc[4 * o4 + 1] * m2);
+        dz.z = rstd * (dy[4 * o4 + 2] - m1 - acc[4 * o4 + 2] * m2);
+        dz.w = rstd * (dy[4 * o4 + 3] - m1 - acc[4 * o4 + 3] * m2);
+        *reinterpret_cast<float4*>(&my_dz[pix * SDZ_LD + 4 * o4]) = dz;
+      }
     }
-    __syncthreads();
-    // ---- phase B: dWc[tap][:] += x[pixel + tap] * dz[pixel][:]
-    if (b_active) {
-      for (int e = grp; e < 256; e += G) {
-        const int esl = e >> 6, epix = e & 63;
-        const int f = (((epix >> 3) + t_di) * 10 + (epix & 7) + t_dj) * C + t_c;
-        if ((so[esl][f >> 5] >> (f & 31)) & 1u) {
+    __syncwarp();
+    // ---- d(conv bias): lane (tpar, o) sums dz over the pixels of its parity
+#pragma unroll 8
+    for (int p = tpar; p < CONV_PIX; p += 2) a_dcb += my_dz[p * SDZ_LD + o_b];
+    // ---- phase B: sparse dW accumulation over the set input bits
 #pragma unroll
-          for (int o4 = 0; o4 < CONV_O / 4; ++o4) {
-            const float4 v = *reinterpret_cast<const float4*>(&sdz[e * SDZ_LD + 4 * o4]);
-            wacc[4 * o4] += v.x; wacc[4 * o4 + 1] += v.y; wacc[4 * o4 + 2] += v.z; wacc[4 * o4 + 3] += v.w;
+    for (int c = 0; c < C; ++c) {
+      for (int wi = 0; wi < Cfg::OBS_WORDS; ++wi) {
+        // bits of word wi that belong to channel c: flat index f = wi*32 + b with f % C == c
+        uint32_t bits = my_so[wi];
+        if (C == 4) bits &= 0x11111111u << c;  // 32 % C == 0: channel c sits at a fixed bit phase in every word
+        if (bits == 0u) continue;
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1u;
+          const int f = wi * 32 + b;
+          const int q = f / C;
+          if (f - q * C != c) continue;
+          const int qy = q / 10, qx = q - qy * 10;
+#pragma unroll
+          for (int it = 0; it < 5; ++it) {
+            const int py = qy - t_di[it], px = qx - t_dj[it];
+            if ((unsigned)py < 8u && (unsigned)px < 8u) wacc[c][it] += my_dz[(py * 8 + px) * SDZ_LD + o_b];
           }
         }
       }
     }
   }
-  __syncthreads();
   // ---- reduce and publish
-  float* s_w = sdz;  // reuse: [TAPS*16]
-  for (int i = tid; i < TAPS * CONV_O; i += 256) s_w[i] = 0.f;
   __syncthreads();
-  if (b_active) {
-    const float inv255 = 1.0f / 255.0f;
+  for (int i = tid; i < TAPS * CONV_O; i += blockDim.x) s_w[i] = 0.f;
+  __syncthreads();
+  const float inv255 = 1.0f / 255.0f;
 #pragma unroll
-    for (int o = 0; o < CONV_O; ++o) atomicAdd(&s_w[tap * CONV_O + o], wacc[o] * inv255);
-  }
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int tap = it * 2 + tpar;
+      if (tap < 9) atomicAdd(&s_w[(tap * C + c) * CONV_O + o_b], wacc[c][it] * inv255);
+    }
+  atomicAdd(&s_red[2 * CONV_O + o_b], a_dcb);
 #pragma unroll
   for (int o = 0; o < CONV_O; ++o) {
-    float v0 = a_dsc[o], v1 = a_dbi[o], v2 = a_dcb[o];
+    float v0 = a_dsc[o], v1 = a_dbi[o];
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      v0 += __shfl_xor_sync(0xffffffffu, v0, s);
-      v1 += __shfl_xor_sync(0xffffffffu, v1, s);
-      v2 += __shfl_xor_sync(0xffffffffu, v2, s);
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, sft);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, sft);
     }
-    if ((tid & 31) == 0) {
+    if (lane == 0) {
       atomicAdd(&s_red[o], v0);
       atomicAdd(&s_red[CONV_O + o], v1);
-      atomicAdd(&s_red[2 * CONV_O + o], v2);
     }
   }
   __syncthreads();
   float* __restrict__ g = grads + (int64_t)seed * P;
-  for (int i = tid; i < TAPS * CONV_O; i += 256) atomicAdd(g + L.conv_w + i, s_w[i]);
+  for (int i = tid; i < TAPS * CONV_O; i += blockDim.x) atomicAdd(g + L.conv_w + i, s_w[i]);
   if (tid < CONV_O) {
     atomicAdd(g + L.ln0_scale + tid, s_red[tid]);
     atomicAdd(g + L.ln0_bias + tid, s_red[CONV_O + tid]);
@@ -944,6 +962,15 @@ static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* ob
     default: return -1;
   }
   return 0;
+}
+
+// CTAs per seed for conv_bwd: ~4 waves of 2 CTAs/SM over all seeds, at most one sample-group per CTA
+static unsigned conv_bwd_ctas(int S, int rows) {
+  int per_seed = (148 * 2 * 4 + S - 1) / S;
+  const int maxc = (rows + CONV_BWD_WARPS - 1) / CONV_BWD_WARPS;
+  if (per_seed > maxc) per_seed = maxc;
+  if (per_seed < 1) per_seed = 1;
+  return (unsigned)per_seed;
 }
 
 static int wgrad_splits(int tiles, int S, int rows) {
@@ -1143,7 +1170,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
                                                                             L.d0_w, w.h1, w.h1, rows * FLAT_CNN, R,
                                                                             FLAT_CNN); }
     }
-    dim3 cg(cdiv(rows, CONV_BWD_SPB), S);
+    dim3 cg(conv_bwd_ctas(S, R), S);
     switch (d->in_c) {
       case 4: { LaunchScope _ls(K_CONV_BWD, st); conv_bwd_kernel<4><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); } break;
       case 6: { LaunchScope _ls(K_CONV_BWD, st); conv_bwd_kernel<6><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); } break;
