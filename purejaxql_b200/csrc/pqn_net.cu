@@ -30,6 +30,8 @@ constexpr int FLAT_CNN = CONV_PIX * CONV_O;  // 1024
 
 // tcgen05 path for the CNN dense layer (pqn_set_tensor_core_path); default on
 static int g_use_tc = 1;
+// warp-level tensor-core (mma.sync tf32) conv kernels (pqn_set_conv_mma_path); default on
+static int g_conv_mma = 1;
 
 static inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
 
@@ -876,6 +878,393 @@ __global__ void __launch_bounds__(CONV_BWD_WARPS * 32, 2)
   }
 }
 
+// ---------------------------------------------------------------------------
+// conv on the warp-level tensor-core path (mma.sync.m16n8k8 tf32, fp32 accumulate).
+// The 3x3 conv is a skinny GEMM  Z[64 pixels x 16] = Xcol[64 x 9C] . W[9C x 16]  per sample whose A operand is
+// {0,1}: every lane builds its A-fragment elements straight from the packed observation bits (no im2col in
+// memory), B fragments (weights/255 split into tf32 hi + lo: two passes keep fp32 accuracy, x is exact) come from
+// shared memory, and the 16 channels of a pixel end up in the 4 lanes of a quad, so LayerNorm is two shuffles.
+// The weight gradient is the transposed skinny GEMM dW[9C x 16] = Xcol^T[9C x 64] . dZ[64 x 16], accumulated per
+// sample in fresh MMA accumulators (16-long chains) and added to fp32 registers (FADD) across samples.
+// One warp per sample.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32_16n8k8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int C>
+struct ConvMma {
+  static constexpr int TAPS = 9 * C;
+  static constexpr int KS = (TAPS + 7) / 8;    // k-steps of the forward GEMM (taps)
+  static constexpr int MT = (TAPS + 15) / 16;  // m-blocks of the weight-gradient GEMM (taps)
+  static constexpr int BWD_WARPS = C >= 7 ? 4 : 8;
+};
+
+// bit offset of tap (di,dj,c) relative to the first channel bit of the output pixel's top-left input pixel
+template <int C>
+__device__ __forceinline__ int tap_bit_offset(int tap) {
+  const int c = tap % C, r = tap / C;
+  return ((r / 3) * 10 + (r % 3)) * C + c;
+}
+
+__device__ __forceinline__ uint32_t obs_bit_f32(const uint32_t* __restrict__ so, int idx, bool valid) {
+  const uint32_t bit = (so[idx >> 5] >> (idx & 31)) & 1u;
+  return (valid && bit) ? 0x3F800000u : 0u;  // 1.0f / 0.0f as tf32 bit patterns
+}
+
+// B fragments of the conv weights (scaled by 1/255), hi and lo, laid out [ks][half][lane] as float2 (b0, b1)
+template <int C>
+__device__ __forceinline__ void conv_mma_load_weights(const float* __restrict__ prm, const pqn_net_layout_t& L,
+                                                      float2* wb_hi, float2* wb_lo, float* cb, float* sc, float* bi) {
+  using M = ConvMma<C>;
+  const float inv255 = 1.0f / 255.0f;
+  for (int i = threadIdx.x; i < M::KS * 2 * 32; i += blockDim.x) {
+    const int ln = i & 31, h = (i >> 5) & 1, ks = i >> 6;
+    const int o = h * 8 + (ln >> 2);
+    const int t0 = ks * 8 + (ln & 3), t1 = t0 + 4;
+    const float w0 = t0 < M::TAPS ? __ldg(prm + L.conv_w + t0 * CONV_O + o) * inv255 : 0.f;
+    const float w1 = t1 < M::TAPS ? __ldg(prm + L.conv_w + t1 * CONV_O + o) * inv255 : 0.f;
+    const float h0 = __uint_as_float(__float_as_uint(w0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(w1) & 0xFFFFE000u);
+    wb_hi[i] = make_float2(h0, h1);
+    wb_lo[i] = make_float2(w0 - h0, w1 - h1);
+  }
+  if (threadIdx.x < CONV_O) {
+    cb[threadIdx.x] = __ldg(prm + L.conv_b + threadIdx.x);
+    sc[threadIdx.x] = __ldg(prm + L.ln0_scale + threadIdx.x);
+    bi[threadIdx.x] = __ldg(prm + L.ln0_bias + threadIdx.x);
+  }
+}
+
+// conv pre-activation of the 16 pixels of m-block `mb` (pixel = 16*mb + g [+8]); z[h][0..3] in C-fragment layout:
+// z[h][0],z[h][1] -> pixel g, channels 8h+2t, 8h+2t+1 ; z[h][2],z[h][3] -> pixel g+8, same channels.
+template <int C>
+__device__ __forceinline__ void conv_mma_block(const uint32_t* __restrict__ so, const float2* __restrict__ wb_hi,
+                                               const float2* __restrict__ wb_lo, const float* __restrict__ cb, int mb,
+                                               int lane, const int (&off0)[ConvMma<C>::KS],
+                                               const int (&off1)[ConvMma<C>::KS], float (&z)[2][4]) {
+  using M = ConvMma<C>;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    z[h][0] = z[h][2] = cb[8 * h + 2 * t];
+    z[h][1] = z[h][3] = cb[8 * h + 2 * t + 1];
+  }
+  const int p0 = 16 * mb + g, p1 = p0 + 8;
+  const int base0 = ((p0 >> 3) * 10 + (p0 & 7)) * C, base1 = ((p1 >> 3) * 10 + (p1 & 7)) * C;
+#pragma unroll
+  for (int ks = 0; ks < M::KS; ++ks) {
+    const bool v0 = ks * 8 + t < M::TAPS, v1 = ks * 8 + t + 4 < M::TAPS;
+    uint32_t a[4];
+    a[0] = obs_bit_f32(so, base0 + off0[ks], v0);
+    a[1] = obs_bit_f32(so, base1 + off0[ks], v0);
+    a[2] = obs_bit_f32(so, base0 + off1[ks], v1);
+    a[3] = obs_bit_f32(so, base1 + off1[ks], v1);
+    if (__ballot_sync(0xffffffffu, (a[0] | a[1] | a[2] | a[3]) != 0u) == 0u) continue;  // empty patch slice
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float2 bl = wb_lo[(ks * 2 + h) * 32 + lane];
+      mma_tf32_16n8k8(z[h], a, __float_as_uint(bl.x), __float_as_uint(bl.y));
+      const float2 bh = wb_hi[(ks * 2 + h) * 32 + lane];
+      mma_tf32_16n8k8(z[h], a, __float_as_uint(bh.x), __float_as_uint(bh.y));
+    }
+  }
+}
+
+// LayerNorm statistics over the 16 channels of pixel rows g (z[.][0..1]) and g+8 (z[.][2..3]); quad reduction
+__device__ __forceinline__ void ln16_quad(const float (&z)[2][4], float& mean0, float& rstd0, float& mean1,
+                                          float& rstd1) {
+  float s0 = z[0][0] + z[0][1] + z[1][0] + z[1][1];
+  float q0 = z[0][0] * z[0][0] + z[0][1] * z[0][1] + z[1][0] * z[1][0] + z[1][1] * z[1][1];
+  float s1 = z[0][2] + z[0][3] + z[1][2] + z[1][3];
+  float q1 = z[0][2] * z[0][2] + z[0][3] * z[0][3] + z[1][2] * z[1][2] + z[1][3] * z[1][3];
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+  }
+  mean0 = s0 * (1.0f / CONV_O); mean1 = s1 * (1.0f / CONV_O);
+  rstd0 = 1.0f / sqrtf(fmaxf(q0 * (1.0f / CONV_O) - mean0 * mean0, 0.f) + LN_EPS);
+  rstd1 = 1.0f / sqrtf(fmaxf(q1 * (1.0f / CONV_O) - mean1 * mean1, 0.f) + LN_EPS);
+}
+
+constexpr int CONV_MMA_WARPS = 8;
+
+template <int C, bool TRAIN>
+__global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
+    conv_fwd_mma_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
+                        const float* __restrict__ params, int64_t P, pqn_net_layout_t L, float* __restrict__ H1,
+                        float* __restrict__ H1LO, float* __restrict__ bn_sums, int rows) {
+  using Cfg = ConvCfg<C>;
+  using M = ConvMma<C>;
+  __shared__ float2 wb_hi[M::KS * 2 * 32], wb_lo[M::KS * 2 * 32];
+  __shared__ float cb[CONV_O], sc[CONV_O], bi[CONV_O];
+  __shared__ uint32_t so[CONV_MMA_WARPS][Cfg::SW];
+  __shared__ float s_cnt[C];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int seed = blockIdx.y;
+  conv_mma_load_weights<C>(params + (int64_t)seed * P, L, wb_hi, wb_lo, cb, sc, bi);
+  if (TRAIN && tid < C) s_cnt[tid] = 0.f;
+  int off0[M::KS], off1[M::KS];
+#pragma unroll
+  for (int ks = 0; ks < M::KS; ++ks) {
+    off0[ks] = tap_bit_offset<C>(min(ks * 8 + t, M::TAPS - 1));
+    off1[ks] = tap_bit_offset<C>(min(ks * 8 + t + 4, M::TAPS - 1));
+  }
+  __syncthreads();
+  int cnt[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) cnt[c] = 0;
+  uint32_t* __restrict__ my_so = so[warp];
+  for (int row = blockIdx.x * CONV_MMA_WARPS + warp; row < rows; row += gridDim.x * CONV_MMA_WARPS) {
+    __syncwarp();
+    {
+      const int64_t src = gather ? gather[(int64_t)seed * rows + row] : row;
+      const uint32_t* __restrict__ orow = obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW;
+      for (int wi = lane; wi < Cfg::SW; wi += 32) my_so[wi] = wi < Cfg::PW ? __ldg(orow + wi) : 0u;
+    }
+    __syncwarp();
+    float* __restrict__ hrow = H1 + ((int64_t)seed * rows + row) * FLAT_CNN;
+    float* __restrict__ lrow = H1LO ? H1LO + ((int64_t)seed * rows + row) * FLAT_CNN : nullptr;
+#pragma unroll 1
+    for (int mb = 0; mb < 4; ++mb) {
+      float z[2][4];
+      conv_mma_block<C>(my_so, wb_hi, wb_lo, cb, mb, lane, off0, off1, z);
+      float mean0, rstd0, mean1, rstd1;
+      ln16_quad(z, mean0, rstd0, mean1, rstd1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int o = 8 * h + 2 * t;
+        float2 v0, v1;
+        v0.x = fmaxf((z[h][0] - mean0) * rstd0 * sc[o] + bi[o], 0.f);
+        v0.y = fmaxf((z[h][1] - mean0) * rstd0 * sc[o + 1] + bi[o + 1], 0.f);
+        v1.x = fmaxf((z[h][2] - mean1) * rstd1 * sc[o] + bi[o], 0.f);
+        v1.y = fmaxf((z[h][3] - mean1) * rstd1 * sc[o + 1] + bi[o + 1], 0.f);
+        const int p0 = 16 * mb + g, p1 = p0 + 8;
+        *reinterpret_cast<float2*>(hrow + p0 * CONV_O + o) = v0;
+        *reinterpret_cast<float2*>(hrow + p1 * CONV_O + o) = v1;
+        if (lrow) {
+          *reinterpret_cast<float2*>(lrow + p0 * CONV_O + o) = make_float2(tc::tf32_lo(v0.x), tc::tf32_lo(v0.y));
+          *reinterpret_cast<float2*>(lrow + p1 * CONV_O + o) = make_float2(tc::tf32_lo(v1.x), tc::tf32_lo(v1.y));
+        }
+      }
+    }
+    if (TRAIN && bn_sums != nullptr) {
+      // dummy input BatchNorm statistics: per-channel popcount of the 100 input pixels (x in {0,1})
+      for (int p = lane; p < 100; p += 32) {
+        const uint32_t b = pixel_bits<C>(my_so, p);
+#pragma unroll
+        for (int c = 0; c < C; ++c) cnt[c] += (int)((b >> c) & 1u);
+      }
+    }
+  }
+  if (TRAIN && bn_sums != nullptr) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      int v = cnt[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v) atomicAdd(&s_cnt[c], (float)v);
+    }
+    __syncthreads();
+    if (tid < C && s_cnt[tid] != 0.f) {
+      atomicAdd(bn_sums + (int64_t)seed * 2 * C + tid, s_cnt[tid]);
+      atomicAdd(bn_sums + (int64_t)seed * 2 * C + C + tid, s_cnt[tid]);
+    }
+  }
+}
+
+constexpr int CDZ_LD = 17;  // staged dz row stride (floats): conflict-free B-fragment reads
+
+// (4 warps per CTA for the wide-channel games keep the static shared memory under 48 KB)
+template <int C>
+__global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
+    conv_bwd_mma_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
+                        const float* __restrict__ params, int64_t P, pqn_net_layout_t L, const float* __restrict__ DY1,
+                        float* __restrict__ grads, int rows) {
+  using Cfg = ConvCfg<C>;
+  using M = ConvMma<C>;
+  __shared__ float2 wb_hi[M::KS * 2 * 32], wb_lo[M::KS * 2 * 32];
+  __shared__ float cb[CONV_O], sc[CONV_O], bi[CONV_O];
+  __shared__ uint32_t so[M::BWD_WARPS][Cfg::SW];
+  __shared__ float sdz[M::BWD_WARPS][CONV_PIX * CDZ_LD];
+  __shared__ float s_w[M::MT * 16 * CONV_O];
+  __shared__ float s_red[3 * CONV_O];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int seed = blockIdx.y;
+  conv_mma_load_weights<C>(params + (int64_t)seed * P, L, wb_hi, wb_lo, cb, sc, bi);
+  for (int i = tid; i < M::MT * 16 * CONV_O; i += blockDim.x) s_w[i] = 0.f;
+  if (tid < 3 * CONV_O) s_red[tid] = 0.f;
+  int off0[M::KS], off1[M::KS];
+#pragma unroll
+  for (int ks = 0; ks < M::KS; ++ks) {
+    off0[ks] = tap_bit_offset<C>(min(ks * 8 + t, M::TAPS - 1));
+    off1[ks] = tap_bit_offset<C>(min(ks * 8 + t + 4, M::TAPS - 1));
+  }
+  // weight-gradient A fragments: rows = taps 16*mt + g (+8)
+  int woff0[M::MT], woff1[M::MT];
+#pragma unroll
+  for (int mt = 0; mt < M::MT; ++mt) {
+    woff0[mt] = tap_bit_offset<C>(min(16 * mt + g, M::TAPS - 1));
+    woff1[mt] = tap_bit_offset<C>(min(16 * mt + g + 8, M::TAPS - 1));
+  }
+  __syncthreads();
+  // lane-private accumulators: columns {2t, 2t+1, 8+2t, 8+2t+1}
+  float a_dsc[4] = {0.f, 0.f, 0.f, 0.f}, a_dbi[4] = {0.f, 0.f, 0.f, 0.f}, a_dcb[4] = {0.f, 0.f, 0.f, 0.f};
+  float wrun[M::MT][2][4];
+#pragma unroll
+  for (int mt = 0; mt < M::MT; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wrun[mt][h][j] = 0.f;
+
+  uint32_t* __restrict__ my_so = so[warp];
+  float* __restrict__ my_dz = sdz[warp];
+  for (int row = blockIdx.x * M::BWD_WARPS + warp; row < rows; row += gridDim.x * M::BWD_WARPS) {
+    __syncwarp();
+    {
+      const int64_t src = gather ? gather[(int64_t)seed * rows + row] : row;
+      const uint32_t* __restrict__ orow = obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW;
+      for (int wi = lane; wi < Cfg::SW; wi += 32) my_so[wi] = wi < Cfg::PW ? __ldg(orow + wi) : 0u;
+    }
+    __syncwarp();
+    const float* __restrict__ dyrow = DY1 + ((int64_t)seed * rows + row) * FLAT_CNN;
+    // ---- phase A: recompute conv + LN, LN backward, stage dz
+#pragma unroll 1
+    for (int mb = 0; mb < 4; ++mb) {
+      const int p0 = 16 * mb + g, p1 = p0 + 8;
+      float2 dyv[2][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        dyv[h][0] = __ldg(reinterpret_cast<const float2*>(dyrow + p0 * CONV_O + 8 * h + 2 * t));
+        dyv[h][1] = __ldg(reinterpret_cast<const float2*>(dyrow + p1 * CONV_O + 8 * h + 2 * t));
+      }
+      float z[2][4];
+      conv_mma_block<C>(my_so, wb_hi, wb_lo, cb, mb, lane, off0, off1, z);
+      float mean0, rstd0, mean1, rstd1;
+      ln16_quad(z, mean0, rstd0, mean1, rstd1);
+      float dxh[2][4];
+      float m1a = 0.f, m2a = 0.f, m1b = 0.f, m2b = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int o = 8 * h + 2 * t;
+        const float dy4[4] = {dyv[h][0].x, dyv[h][0].y, dyv[h][1].x, dyv[h][1].y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float mean = j < 2 ? mean0 : mean1, rstd = j < 2 ? rstd0 : rstd1;
+          z[h][j] = (z[h][j] - mean) * rstd;  // xhat
+          const int col = 2 * h + (j & 1);    // index into the lane's 4 columns
+          a_dsc[col] = fmaf(dy4[j], z[h][j], a_dsc[col]);
+          a_dbi[col] += dy4[j];
+          dxh[h][j] = dy4[j] * sc[o + (j & 1)];
+          if (j < 2) { m1a += dxh[h][j]; m2a = fmaf(dxh[h][j], z[h][j], m2a); }
+          else { m1b += dxh[h][j]; m2b = fmaf(dxh[h][j], z[h][j], m2b); }
+        }
+      }
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        m1a += __shfl_xor_sync(0xffffffffu, m1a, o); m2a += __shfl_xor_sync(0xffffffffu, m2a, o);
+        m1b += __shfl_xor_sync(0xffffffffu, m1b, o); m2b += __shfl_xor_sync(0xffffffffu, m2b, o);
+      }
+      m1a *= (1.0f / CONV_O); m2a *= (1.0f / CONV_O); m1b *= (1.0f / CONV_O); m2b *= (1.0f / CONV_O);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int o = 8 * h + 2 * t;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float rstd = j < 2 ? rstd0 : rstd1, m1 = j < 2 ? m1a : m1b, m2 = j < 2 ? m2a : m2b;
+          const float dz = rstd * (dxh[h][j] - m1 - z[h][j] * m2);
+          a_dcb[2 * h + (j & 1)] += dz;
+          my_dz[(j < 2 ? p0 : p1) * CDZ_LD + o + (j & 1)] = dz;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- phase B: dW[tap][o] += sum_pixels x[pixel, tap] * dz[pixel][o]   (fresh accumulators per sample)
+    float wacc[M::MT][2][4];
+#pragma unroll
+    for (int mt = 0; mt < M::MT; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wacc[mt][h][j] = 0.f;
+#pragma unroll 1
+    for (int kk = 0; kk < 8; ++kk) {
+      // B fragments: b0 = dz[pixel 8kk + t][o = 8h + g], b1 = dz[pixel 8kk + t + 4][o]
+      uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float v0 = my_dz[(8 * kk + t) * CDZ_LD + 8 * h + g], v1 = my_dz[(8 * kk + t + 4) * CDZ_LD + 8 * h + g];
+        bh[h][0] = __float_as_uint(v0) & 0xFFFFE000u; bh[h][1] = __float_as_uint(v1) & 0xFFFFE000u;
+        bl[h][0] = __float_as_uint(v0 - __uint_as_float(bh[h][0])); bl[h][1] = __float_as_uint(v1 - __uint_as_float(bh[h][1]));
+      }
+      // A fragments: x[tap, pixel]: a0 = (tap g, pixel 8kk+t), a1 = (tap g+8, same), a2 = (tap g, pixel+4), a3
+      const int pa = 8 * kk + t, pb = pa + 4;
+      const int basea = ((pa >> 3) * 10 + (pa & 7)) * C, baseb = ((pb >> 3) * 10 + (pb & 7)) * C;
+#pragma unroll
+      for (int mt = 0; mt < M::MT; ++mt) {
+        const bool v0 = 16 * mt + g < M::TAPS, v1 = 16 * mt + g + 8 < M::TAPS;
+        uint32_t a[4];
+        a[0] = obs_bit_f32(my_so, basea + woff0[mt], v0);
+        a[1] = obs_bit_f32(my_so, basea + woff1[mt], v1);
+        a[2] = obs_bit_f32(my_so, baseb + woff0[mt], v0);
+        a[3] = obs_bit_f32(my_so, baseb + woff1[mt], v1);
+        if (__ballot_sync(0xffffffffu, (a[0] | a[1] | a[2] | a[3]) != 0u) == 0u) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mma_tf32_16n8k8(wacc[mt][h], a, bl[h][0], bl[h][1]);
+          mma_tf32_16n8k8(wacc[mt][h], a, bh[h][0], bh[h][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < M::MT; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wrun[mt][h][j] += wacc[mt][h][j];
+  }
+  // ---- reduce and publish: wrun[mt][h][j] is dW[tap = 16mt + g (+8 for j>=2)][o = 8h + 2t + (j&1)]
+#pragma unroll
+  for (int mt = 0; mt < M::MT; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int tap = 16 * mt + g + (j >= 2 ? 8 : 0);
+        if (tap < M::TAPS) atomicAdd(&s_w[tap * CONV_O + 8 * h + 2 * t + (j & 1)], wrun[mt][h][j]);
+      }
+#pragma unroll
+  for (int col = 0; col < 4; ++col) {
+    float v0 = a_dsc[col], v1 = a_dbi[col], v2 = a_dcb[col];
+#pragma unroll
+    for (int sft = 4; sft <= 16; sft <<= 1) {  // lanes with the same t (same columns)
+      v0 += __shfl_xor_sync(0xffffffffu, v0, sft);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, sft);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, sft);
+    }
+    if (g == 0) {
+      const int o = 8 * (col >> 1) + 2 * t + (col & 1);
+      atomicAdd(&s_red[o], v0);
+      atomicAdd(&s_red[CONV_O + o], v1);
+      atomicAdd(&s_red[2 * CONV_O + o], v2);
+    }
+  }
+  __syncthreads();
+  float* __restrict__ gout = grads + (int64_t)seed * P;
+  for (int i = tid; i < M::TAPS * CONV_O; i += blockDim.x) atomicAdd(gout + L.conv_w + i, s_w[i]);
+  if (tid < CONV_O) {
+    atomicAdd(gout + L.ln0_scale + tid, s_red[tid]);
+    atomicAdd(gout + L.ln0_bias + tid, s_red[CONV_O + tid]);
+    atomicAdd(gout + L.conv_b + tid, s_red[2 * CONV_O + tid]);
+  }
+}
+
 // MLP input gather (minibatch rows of float obs) + dummy BatchNorm sums.
 __global__ void gather_rows_kernel(const float* __restrict__ obs, int64_t obs_rows_per_seed,
                                    const int32_t* __restrict__ gather, float* __restrict__ out,
@@ -950,10 +1339,30 @@ static void launch_dense(int BN, dim3 grid, cudaStream_t st, const float* X, int
 
 static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
+static unsigned conv_mma_ctas(int S, int rows) {
+  int per_seed = (148 * 2 * 4 + S - 1) / S;
+  const int maxc = (rows + CONV_MMA_WARPS - 1) / CONV_MMA_WARPS;
+  if (per_seed > maxc) per_seed = maxc;
+  if (per_seed < 1) per_seed = 1;
+  return (unsigned)per_seed;
+}
+
 template <bool TRAIN>
 static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
                            const float* params, int64_t P, const pqn_net_layout_t& L, float* h1, float* h1lo, float* bn,
                            int rows) {
+  if (g_conv_mma) {
+    const dim3 mg(conv_mma_ctas((int)grid.y, rows), grid.y);
+    LaunchScope _ls(K_CONV_FWD, st);
+    switch (C) {
+      case 4: conv_fwd_mma_kernel<4, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); break;
+      case 6: conv_fwd_mma_kernel<6, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); break;
+      case 7: conv_fwd_mma_kernel<7, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); break;
+      case 10: conv_fwd_mma_kernel<10, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); break;
+      default: return -1;
+    }
+    return 0;
+  }
   switch (C) {
     case 4: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<4, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
     case 6: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<6, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
@@ -1055,6 +1464,11 @@ static int tc_dgrad(const float* params, int64_t P, const pqn_net_layout_t& L, c
 using namespace pqn;
 
 extern "C" {
+
+int pqn_set_conv_mma_path(int on) {
+  g_conv_mma = on ? 1 : 0;
+  return PQN_OK;
+}
 
 int pqn_set_tensor_core_path(int on) {
   g_use_tc = on ? 1 : 0;
@@ -1171,6 +1585,16 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
                                                                             FLAT_CNN); }
     }
     dim3 cg(conv_bwd_ctas(S, R), S);
+    if (g_conv_mma) {
+      const dim3 mg(conv_mma_ctas(S, R), S);
+      LaunchScope _ls(K_CONV_BWD, st);
+      switch (d->in_c) {
+        case 4: conv_bwd_mma_kernel<4><<<mg, ConvMma<4>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
+        case 6: conv_bwd_mma_kernel<6><<<mg, ConvMma<6>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
+        case 7: conv_bwd_mma_kernel<7><<<mg, ConvMma<7>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
+        case 10: conv_bwd_mma_kernel<10><<<mg, ConvMma<10>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
+      }
+    } else
     switch (d->in_c) {
       case 4: { LaunchScope _ls(K_CONV_BWD, st); conv_bwd_kernel<4><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); } break;
       case 6: { LaunchScope _ls(K_CONV_BWD, st); conv_bwd_kernel<6><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); } break;

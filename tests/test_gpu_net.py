@@ -52,13 +52,16 @@ def _ws(spec, S, rows):
     return torch.empty(n, dtype=torch.uint8, device=dev())
 
 
-@pytest.fixture(params=[1, 0], ids=["tcgen05", "ffma"])
+@pytest.fixture(params=[(1, 1), (0, 0), (1, 0)], ids=["tcgen05+mma_conv", "ffma", "tcgen05+cuda_conv"])
 def dense_path(request):
-    """Runs the CNN tests on both dense-layer implementations (tcgen05 3xTF32 and fp32 FFMA)."""
+    """Runs the CNN tests on the implementation variants: dense layer on tcgen05 3xTF32 or fp32 FFMA,
+    conv on warp-level tf32 MMA or fp32 CUDA cores."""
     from purejaxql_b200 import _lib
-    _lib.lib().pqn_set_tensor_core_path(request.param)
+    _lib.lib().pqn_set_tensor_core_path(request.param[0])
+    _lib.lib().pqn_set_conv_mma_path(request.param[1])
     yield request.param
     _lib.lib().pqn_set_tensor_core_path(1)
+    _lib.lib().pqn_set_conv_mma_path(1)
 
 
 @pytest.mark.parametrize("rows", [1, 130, 515])
