@@ -1237,7 +1237,8 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int tap = 16 * mt + g + (j >= 2 ? 8 : 0);
-        if (tap < M::TAPS) atomicAdd(&s_w[tap * CONV_O + 8 * h + 2 * t + (j & 1)], wrun[mt][h][j]);
+        // x = bit / 255 (pqn_minatar.py:66): the A operand was the raw bit, so scale here
+        if (tap < M::TAPS) atomicAdd(&s_w[tap * CONV_O + 8 * h + 2 * t + (j & 1)], wrun[mt][h][j] * (1.0f / 255.0f));
       }
 #pragma unroll
   for (int col = 0; col < 4; ++col) {
