@@ -46,9 +46,14 @@ METRIC = "MinAtar-Breakout env steps/sec @4096 envs x128 seeds"
 UNIT = "env_steps/s"
 # algorithmic work per env-step (restated in DESIGN.md)
 FLOPS_FWD_PER_SAMPLE = 2 * (64 * 36 * 16 + 1024 * 128 + 128 * 3)        # conv + dense + head MACs x2
-ALG_FLOPS = {  # per launch-unit sample, by kernel
+ALG_FLOPS = {  # per launch-unit sample, by kernel (DESIGN.md section 3)
     "dense_fwd": 2 * 1024 * 128, "wgrad": 2 * 1024 * 128, "dgrad": 2 * 1024 * 128,
+    "tc_dense_fwd": 2 * 1024 * 128, "tc_wgrad": 2 * 1024 * 128, "tc_dgrad": 2 * 1024 * 128,
     "conv_fwd": 2 * 64 * 36 * 16, "conv_bwd": 2 * 2 * 64 * 36 * 16,
+}
+ALG_BYTES = {  # HBM bytes per sample per launch the kernel must move (h1 + its tf32-lo operand etc.)
+    "tc_dense_fwd": 2 * 4096 + 2 * 512, "tc_wgrad": 2 * 4096 + 2 * 512, "tc_dgrad": 2 * 512 + 2 * 4096,
+    "conv_fwd": 64 + 2 * 4096, "conv_bwd": 64 + 4096,
 }
 
 
@@ -253,7 +258,7 @@ def run_gpu(args, rank, world, local_rank):
         # samples per launch: minibatch launches process S*4096 samples (T*E/32), rollout forwards S*E
         d_ms, d_n = prof[dom]
         mb = NUM_STEPS * args.envs // 32
-        if dom in ("dense_fwd", "conv_fwd"):
+        if dom in ("dense_fwd", "conv_fwd", "tc_dense_fwd"):
             n_roll = (NUM_STEPS + 1) * args.steps
             n_mb = d_n - n_roll
             samples = S * (n_roll * args.envs + n_mb * mb)
@@ -262,11 +267,17 @@ def run_gpu(args, rank, world, local_rank):
         flops = ALG_FLOPS[dom] * samples
         achieved = flops / (d_ms / 1e3) / 1e12
         peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        gbs = ALG_BYTES.get(dom, 0) * samples / (d_ms / 1e3) / 1e9
         roof = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
                 "frac": round(achieved / peak, 4), "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PF sustained (of fallback)",
-                "note": "fp32 FFMA register-tiled GEMM (not yet on tcgen05): fraction is against the dense bf16 "
-                        "tensor peak; the FP32 CUDA-core peak of a B200 is ~72 TFLOP/s",
+                "note": ("fp32-accurate 3xTF32 on tcgen05: each algorithmic FLOP costs 3 tf32 MMAs at half the bf16 "
+                         "rate, so the fp32-equivalent tensor peak is peak/6 = %.0f TFLOP/s; the kernel also streams "
+                         "its A operand (x and x_lo) from HBM" % (peak / 6.0)) if dom.startswith("tc_") else
+                        "fp32 CUDA-core kernel; fraction is against the dense bf16 tensor peak",
+                "frac_of_3xtf32_peak": round(achieved / (peak / 6.0), 4) if dom.startswith("tc_") else None,
+                "hbm_gbs": round(gbs, 1), "hbm_frac": round(gbs / hbm, 4),
                 "avg_launch_ms": round(d_ms / d_n, 4), "launches": d_n}
     elif dom is not None:
         d_ms, d_n = prof[dom]

@@ -1423,7 +1423,7 @@ static int tc_dense_fwd(int epi, const float* params, int64_t P, const pqn_net_l
   ep.params = params; ep.P = P; ep.off_b = L.d0_b; ep.off_scale = L.ln1_scale; ep.off_bias = L.ln1_bias;
   ep.off_hw = L.head_w; ep.off_hb = L.head_b; ep.A = A; ep.rows = rows;
   ep.H = w.h2; ep.XHAT = w.xhat2; ep.RSTD = w.rstd2; ep.Q = q;
-  return tc::launch_gemm(0, 1, epi, t, gs, ep, st);
+  return tc::launch_gemm(0, 1, epi, t, gs, ep, st, K_TC_FWD);
 }
 
 // dW1 = H1^T . dZ2  -> grads[d0_w]
@@ -1440,7 +1440,7 @@ static int tc_wgrad(float* grads, int64_t P, const pqn_net_layout_t& L, const Wo
   gs.split3 = 1;
   tc::EpiParams ep = {};
   ep.out = grads + L.d0_w; ep.ld_out = HID_CNN; ep.out_seed_stride = P;
-  return tc::launch_gemm(1, 1, tc::EPI_STORE, t, gs, ep, st);
+  return tc::launch_gemm(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD);
 }
 
 // dY1 = relu_mask(H1) * (dZ2 . W1^T), written in place over H1
@@ -1457,7 +1457,7 @@ static int tc_dgrad(const float* params, int64_t P, const pqn_net_layout_t& L, c
   gs.split3 = 1;
   tc::EpiParams ep = {};
   ep.out = w.h1; ep.mask = w.h1; ep.ld_out = FLAT_CNN; ep.out_seed_stride = (int64_t)rows * FLAT_CNN;
-  return tc::launch_gemm(0, 0, tc::EPI_RELU_MASK, t, gs, ep, st);
+  return tc::launch_gemm(0, 0, tc::EPI_RELU_MASK, t, gs, ep, st, K_TC_DGRAD);
 }
 
 }  // namespace pqn

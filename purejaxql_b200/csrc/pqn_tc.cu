@@ -348,7 +348,7 @@ static int num_sms() {
 }
 
 template <int A_MN, int B_MN, int EPI>
-static int launch_t(const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep, cudaStream_t st) {
+static int launch_t(const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep, cudaStream_t st, int kid) {
   auto kfn = tc_gemm_kernel<A_MN, B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -359,16 +359,16 @@ static int launch_t(const CUtensorMap* t, const GemmShape& gs, const EpiParams& 
   const int tiles = gs.m_tiles * gs.n_tiles * gs.S;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   {
-    LaunchScope _ls(K_TC_GEMM, st);
+    LaunchScope _ls(kid < 0 ? (int)K_TC_GEMM : kid, st);
     kfn<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(t[0], t[1], t[2], t[3], gs, ep);
   }
   return check_launch("tc_gemm");
 }
 
 int launch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep,
-                cudaStream_t st) {
+                cudaStream_t st, int kernel_id) {
 #define PQN_TC_CASE(A, B, E) \
-  if (a_mn == A && b_mn == B && epi == E) return launch_t<A, B, E>(t, gs, ep, st);
+  if (a_mn == A && b_mn == B && epi == E) return launch_t<A, B, E>(t, gs, ep, st, kernel_id);
   PQN_TC_CASE(0, 1, EPI_STORE)
   PQN_TC_CASE(0, 1, EPI_LN_TRAIN)
   PQN_TC_CASE(0, 1, EPI_LN_HEAD)

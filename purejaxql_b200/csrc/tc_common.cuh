@@ -140,7 +140,8 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t tile_addr, int ks) {
 // host-side pieces used by other translation units (pqn_net.cu)
 int make_tmap(CUtensorMap* tm, const float* base, uint64_t inner, uint64_t mid, uint64_t seeds, uint64_t mid_stride_elems,
               uint64_t seed_stride_elems, uint32_t box_mid, int mn_major);
-int launch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep, cudaStream_t st);
+int launch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep, cudaStream_t st,
+                int kernel_id = -1);
 
 }  // namespace tc
 }  // namespace pqn
