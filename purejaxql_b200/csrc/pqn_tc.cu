@@ -30,24 +30,56 @@ namespace tc {
 // epilogues: each epilogue thread owns one row of the 128x128 tile, already
 // promoted to fp32 registers (acc[128], fully unrolled static indexing)
 // ---------------------------------------------------------------------------
-template <int EPI>
-__device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[128], int seed, int m, int n0,
-                                             bool row_ok) {
-  if constexpr (EPI == EPI_STORE || EPI == EPI_RELU_MASK) {
-    if (!row_ok) return;
-    // no __restrict__: dgrad runs in place (out == mask)
-    float* out = ep.out + (int64_t)seed * ep.out_seed_stride + (int64_t)m * ep.ld_out + n0;
-    const float* msk =
-        (EPI == EPI_RELU_MASK) ? ep.mask + (int64_t)seed * ep.out_seed_stride + (int64_t)m * ep.ld_out + n0 : nullptr;
+// Coalesced tile-row-block store: the warp's 32 rows x 32 columns chunk goes through a padded shared-memory
+// stage so that 8 lanes write one 128-byte row segment (4 rows per store instruction) instead of 32 lanes
+// writing 32 different rows.  `vals` = this lane's row, columns [0,32) of the chunk.  MASKED: multiply by
+// (mask > 0) read with the same coalesced addressing (dgrad's fused ReLU mask; may alias dst).
+constexpr int STG_LD = 36;  // floats per staged row (16-byte aligned, conflict-free for 128-bit accesses)
+
+template <bool MASKED>
+__device__ __forceinline__ void store_chunk_coalesced(float* stage, const float (&vals)[32], int lane, float* dst,
+                                                      const float* msk, int64_t ld, int m_base, int M) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-      if constexpr (EPI == EPI_RELU_MASK) {
-        const float4 h = *reinterpret_cast<const float4*>(msk + 4 * j);
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stage + lane * STG_LD + 4 * j) =
+        make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
+  __syncwarp();
+  const int r_in = lane >> 3, c4 = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + r_in;
+    if (m_base + r < M) {
+      float4 o = *reinterpret_cast<const float4*>(stage + r * STG_LD + 4 * c4);
+      const int64_t off = (int64_t)r * ld + 4 * c4;
+      if (MASKED) {
+        const float4 h = *reinterpret_cast<const float4*>(msk + off);
         o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f;
         o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
       }
-      *reinterpret_cast<float4*>(out + 4 * j) = o;
+      *reinterpret_cast<float4*>(dst + off) = o;
+    }
+  }
+  __syncwarp();
+}
+
+// `m_base` = first row of this warp's 32-row block; the lane's own row is m_base + lane.
+template <int EPI>
+__device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[128], float* stage, int lane, int seed,
+                                             int m_base, int n0, int M) {
+  const int m = m_base + lane;
+  const bool row_ok = m < M;
+  if constexpr (EPI == EPI_STORE || EPI == EPI_RELU_MASK) {
+    // no __restrict__: dgrad runs in place (out == mask)
+    float* out = ep.out + (int64_t)seed * ep.out_seed_stride + (int64_t)m_base * ep.ld_out + n0;
+    const float* msk =
+        (EPI == EPI_RELU_MASK) ? ep.mask + (int64_t)seed * ep.out_seed_stride + (int64_t)m_base * ep.ld_out + n0 : nullptr;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
+      store_chunk_coalesced<EPI == EPI_RELU_MASK>(stage, v, lane, out + c * 32, msk ? msk + c * 32 : nullptr, ep.ld_out,
+                                                  m_base, M);
     }
   } else {
     // bias + LayerNorm(128) + ReLU, then either (h, xhat, rstd) or the fused Q-head
@@ -64,19 +96,21 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[1
     const float rstd = 1.0f / sqrtf(var + 1e-6f);
     const int64_t grow = (int64_t)seed * ep.rows + m;
     if constexpr (EPI == EPI_LN_TRAIN) {
-      if (!row_ok) return;
+      float* hbase = ep.H + ((int64_t)seed * ep.rows + m_base) * 128;
+      float* xbase = ep.XHAT + ((int64_t)seed * ep.rows + m_base) * 128;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float xh[4], h[4];
+      for (int c = 0; c < 4; ++c) {
+        float xh[32], h[32];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          xh[t] = (acc[4 * j + t] - mean) * rstd;
-          h[t] = fmaxf(xh[t] * __ldg(prm + ep.off_scale + 4 * j + t) + __ldg(prm + ep.off_bias + 4 * j + t), 0.f);
+        for (int j = 0; j < 32; ++j) {
+          const int col = c * 32 + j;
+          xh[j] = (acc[col] - mean) * rstd;
+          h[j] = fmaxf(xh[j] * __ldg(prm + ep.off_scale + col) + __ldg(prm + ep.off_bias + col), 0.f);
         }
-        *reinterpret_cast<float4*>(ep.H + grow * 128 + 4 * j) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(ep.XHAT + grow * 128 + 4 * j) = make_float4(xh[0], xh[1], xh[2], xh[3]);
+        store_chunk_coalesced<false>(stage, h, lane, hbase + c * 32, nullptr, 128, m_base, M);
+        store_chunk_coalesced<false>(stage, xh, lane, xbase + c * 32, nullptr, 128, m_base, M);
       }
-      ep.RSTD[grow] = rstd;
+      if (row_ok) ep.RSTD[grow] = rstd;
     } else {  // EPI_LN_HEAD
       float q[PQN_TC_MAX_A];
 #pragma unroll
@@ -138,6 +172,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint64_t* corr_full = main_empty + 2;         // [2]
   uint64_t* corr_empty = corr_full + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_empty + 2);
+  float* stage_all = reinterpret_cast<float*>(smem_al + TC_STAGES * TC_STAGE_BYTES + 256);  // 4 x [32][STG_LD]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -287,8 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) mbar_arrive(&corr_empty[cb]);
         if (++cb == 2) { cb = 0; cb_phase ^= 1u; }
       }
-      const int m = m0 + quad * 32 + lane;
-      epilogue_row<EPI>(ep, acc, seed, m, n0, m < gs.M);
+      epilogue_row<EPI>(ep, acc, stage_all + (warp - 2) * 32 * STG_LD, lane, seed, m0 + quad * 32, n0, gs.M);
     }
   }
   tcgen05_fence_before();
