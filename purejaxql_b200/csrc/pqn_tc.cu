@@ -38,7 +38,7 @@ constexpr int STG_LD = 36;  // floats per staged row (16-byte aligned, conflict-
 
 template <bool MASKED>
 __device__ __forceinline__ void store_chunk_coalesced(float* stage, const float (&vals)[32], int lane, float* dst,
-                                                      const float* msk, int64_t ld, int m_base, int M) {
+                                                      uint32_t mask_bits, int64_t ld, int m_base, int M) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     *reinterpret_cast<float4*>(stage + lane * STG_LD + 4 * j) =
@@ -52,9 +52,9 @@ __device__ __forceinline__ void store_chunk_coalesced(float* stage, const float 
       float4 o = *reinterpret_cast<const float4*>(stage + r * STG_LD + 4 * c4);
       const int64_t off = (int64_t)r * ld + 4 * c4;
       if (MASKED) {
-        const float4 h = *reinterpret_cast<const float4*>(msk + off);
-        o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f;
-        o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
+        const uint32_t b = mask_bits >> (it * 4);
+        o.x = (b & 1u) ? o.x : 0.f; o.y = (b & 2u) ? o.y : 0.f;
+        o.z = (b & 4u) ? o.z : 0.f; o.w = (b & 8u) ? o.w : 0.f;
       }
       *reinterpret_cast<float4*>(dst + off) = o;
     }
@@ -62,24 +62,46 @@ __device__ __forceinline__ void store_chunk_coalesced(float* stage, const float 
   __syncwarp();
 }
 
+// ReLU mask of dgrad, fetched BEFORE the tile's MMAs are awaited (it does not depend on them) so the HBM latency
+// overlaps the tensor-core work: bit (it*4 + j) of bits[c] = (mask[row it*4 + lane/8][c*32 + 4*(lane%8) + j] > 0),
+// i.e. exactly the elements this lane stores in store_chunk_coalesced.
+__device__ __forceinline__ void prefetch_mask_bits(const EpiParams& ep, int seed, int m_base, int n0, int lane, int M,
+                                                   uint32_t (&bits)[4]) {
+  const float* msk = ep.mask + (int64_t)seed * ep.out_seed_stride + (int64_t)m_base * ep.ld_out + n0;
+  const int r_in = lane >> 3, c4 = lane & 7;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float4 h[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + r_in;
+      h[it] = (m_base + r < M) ? *reinterpret_cast<const float4*>(msk + (int64_t)r * ep.ld_out + c * 32 + 4 * c4)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t b = 0u;
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      b |= ((h[it].x > 0.f ? 1u : 0u) | (h[it].y > 0.f ? 2u : 0u) | (h[it].z > 0.f ? 4u : 0u) | (h[it].w > 0.f ? 8u : 0u))
+           << (it * 4);
+    bits[c] = b;
+  }
+}
+
 // `m_base` = first row of this warp's 32-row block; the lane's own row is m_base + lane.
 template <int EPI>
 __device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[128], float* stage, int lane, int seed,
-                                             int m_base, int n0, int M) {
+                                             int m_base, int n0, int M, const uint32_t (&mask_bits)[4]) {
   const int m = m_base + lane;
   const bool row_ok = m < M;
   if constexpr (EPI == EPI_STORE || EPI == EPI_RELU_MASK) {
     // no __restrict__: dgrad runs in place (out == mask)
     float* out = ep.out + (int64_t)seed * ep.out_seed_stride + (int64_t)m_base * ep.ld_out + n0;
-    const float* msk =
-        (EPI == EPI_RELU_MASK) ? ep.mask + (int64_t)seed * ep.out_seed_stride + (int64_t)m_base * ep.ld_out + n0 : nullptr;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
-      store_chunk_coalesced<EPI == EPI_RELU_MASK>(stage, v, lane, out + c * 32, msk ? msk + c * 32 : nullptr, ep.ld_out,
-                                                  m_base, M);
+      store_chunk_coalesced<EPI == EPI_RELU_MASK>(stage, v, lane, out + c * 32, mask_bits[c], ep.ld_out, m_base, M);
     }
   } else {
     // bias + LayerNorm(128) + ReLU, then either (h, xhat, rstd) or the fused Q-head
@@ -107,8 +129,8 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[1
           xh[j] = (acc[col] - mean) * rstd;
           h[j] = fmaxf(xh[j] * __ldg(prm + ep.off_scale + col) + __ldg(prm + ep.off_bias + col), 0.f);
         }
-        store_chunk_coalesced<false>(stage, h, lane, hbase + c * 32, nullptr, 128, m_base, M);
-        store_chunk_coalesced<false>(stage, xh, lane, xbase + c * 32, nullptr, 128, m_base, M);
+        store_chunk_coalesced<false>(stage, h, lane, hbase + c * 32, 0u, 128, m_base, M);
+        store_chunk_coalesced<false>(stage, xh, lane, xbase + c * 32, 0u, 128, m_base, M);
       }
       if (row_ok) ep.RSTD[grow] = rstd;
     } else {  // EPI_LN_HEAD
@@ -301,6 +323,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int seed = tile / tiles_per_seed;
       const int rem = tile - seed * tiles_per_seed;
       const int m0 = (rem / gs.n_tiles) * 128, n0 = (rem % gs.n_tiles) * 128;
+      uint32_t mask_bits[4] = {0u, 0u, 0u, 0u};
+      if constexpr (EPI == EPI_RELU_MASK) prefetch_mask_bits(ep, seed, m0 + quad * 32, n0, lane, gs.M, mask_bits);
       float acc[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) acc[j] = 0.f;
@@ -322,7 +346,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) mbar_arrive(&corr_empty[cb]);
         if (++cb == 2) { cb = 0; cb_phase ^= 1u; }
       }
-      epilogue_row<EPI>(ep, acc, stage_all + (warp - 2) * 32 * STG_LD, lane, seed, m0 + quad * 32, n0, gs.M);
+      epilogue_row<EPI>(ep, acc, stage_all + (warp - 2) * 32 * STG_LD, lane, seed, m0 + quad * 32, n0, gs.M, mask_bits);
     }
   }
   tcgen05_fence_before();
