@@ -116,6 +116,195 @@ class Breakout:
 
 
 # --------------------------------------------------------------------------- #
+# MinAtar Freeway  (gymnax/environments/minatar/freeway.py)
+# --------------------------------------------------------------------------- #
+class Freeway:
+    """Restated from gymnax 0.0.6 `MinFreeway` (a JAX port of MinAtar freeway.py): chicken at column 4,
+    8 cars [x, y, timer, signed speed]; cars are re-randomised (speed 1..5, direction) at reset and
+    whenever the chicken reaches the top; time-limit termination only (2500 steps)."""
+    name = "Freeway-MinAtar"
+    obs_shape = (10, 10, 7)
+    num_actions = 3                        # minimal action set [0, 2, 4] = noop/up/down
+    action_set = np.array([0, 2, 4], dtype=I32)
+    max_steps_in_episode = 2500
+    player_speed = 3
+    state_fields = ("pos", "cars", "move_timer", "time", "terminal")
+
+    @staticmethod
+    def _draw(key):
+        ks = jr.split(key, 2)
+        speeds = jr.randint(ks[:, 0], (8,), 1, 6)                  # jax.random.randint(key_speed, (8,), 1, 6)
+        dirs = jr.choice_index(ks[:, 1], 2, (8,)) * 2 - 1           # jax.random.choice(key_dirs, [-1, 1], (8,))
+        return (speeds * dirs).astype(I32)
+
+    def reset_env(self, key):
+        n = key.shape[0]
+        sp = self._draw(key)
+        cars = np.zeros((n, 8, 4), I32)
+        cars[:, :, 1] = np.arange(1, 9)
+        cars[:, :, 2] = np.abs(sp)
+        cars[:, :, 3] = sp
+        s = dict(pos=np.full(n, 9, I32), cars=cars, move_timer=np.full(n, self.player_speed, I32),
+                 time=np.zeros(n, I32), terminal=np.zeros(n, bool))
+        return self.get_obs(s), s
+
+    def get_obs(self, s):
+        n = s["pos"].shape[0]
+        idx = np.arange(n)
+        obs = np.zeros((n, 10, 10, 7), bool)
+        obs[idx, s["pos"], 4, 0] = True
+        for c in range(8):
+            x, y, spd = s["cars"][:, c, 0], s["cars"][:, c, 1], s["cars"][:, c, 3]
+            obs[idx, y, x, 1] = True
+            back = np.where(spd > 0, x - 1, x + 1)
+            back = np.where(back < 0, 9, back)
+            back = np.where(back > 9, 0, back)
+            obs[idx, y, back, 1 + np.abs(spd)] = True               # |speed| 1..5 -> trail channels 2..6
+        return obs.astype(F32)
+
+    def step_env(self, key, s, action):
+        a = self.action_set[action]
+        pos, mt = s["pos"].copy(), s["move_timer"].copy()
+        up = (a == 2) & (mt == 0)
+        down = (a == 4) & (mt == 0)
+        mt = np.where(up | down, self.player_speed, mt).astype(I32)
+        pos = np.where(up, np.maximum(0, pos - 1), np.where(down, np.minimum(9, pos + 1), pos)).astype(I32)
+        win = pos == 0
+        reward = win.astype(F32)
+        pos = np.where(win, 9, pos).astype(I32)
+        sp = self._draw(key)                                          # always sampled, applied on win
+        cars = s["cars"].copy()
+        cars[:, :, 2] = np.where(win[:, None], np.abs(sp), cars[:, :, 2])
+        cars[:, :, 3] = np.where(win[:, None], sp, cars[:, :, 3])
+        for c in range(8):                                            # sequential: pos carries across cars
+            hit = (cars[:, c, 0] == 4) & (cars[:, c, 1] == pos)
+            pos = np.where(hit, 9, pos).astype(I32)
+            mv = cars[:, c, 2] == 0
+            nx = cars[:, c, 0] + np.where(cars[:, c, 3] > 0, 1, -1)
+            nx = np.where(nx < 0, 9, np.where(nx > 9, 0, nx))
+            cars[:, c, 0] = np.where(mv, nx, cars[:, c, 0])
+            cars[:, c, 2] = np.where(mv, np.abs(cars[:, c, 3]), cars[:, c, 2] - 1)
+            hit2 = mv & (cars[:, c, 0] == 4) & (cars[:, c, 1] == pos)
+            pos = np.where(hit2, 9, pos).astype(I32)
+        mt = (mt - (mt > 0)).astype(I32)
+        time = (s["time"] + 1).astype(I32)
+        done = time >= self.max_steps_in_episode
+        ns = dict(pos=pos, cars=cars.astype(I32), move_timer=mt, time=time, terminal=done)
+        info = {"discount": np.where(done, F32(0.0), F32(1.0)).astype(F32)}
+        return self.get_obs(ns), ns, reward, done, info
+
+
+# --------------------------------------------------------------------------- #
+# MinAtar SpaceInvaders  (gymnax/environments/minatar/space_invaders.py)
+# --------------------------------------------------------------------------- #
+class SpaceInvaders:
+    """Restated from gymnax 0.0.6 `MinSpaceInvaders` (JAX port of MinAtar space_invaders.py).  Fully
+    deterministic: neither step nor reset consumes randomness."""
+    name = "SpaceInvaders-MinAtar"
+    obs_shape = (10, 10, 6)
+    num_actions = 4                        # minimal action set [0, 1, 3, 5] = noop/left/right/fire
+    action_set = np.array([0, 1, 3, 5], dtype=I32)
+    max_steps_in_episode = 1000
+    shot_cool_down = 5
+    enemy_move_interval = 12
+    enemy_shot_interval = 10
+    state_fields = ("pos", "f_bullet_map", "e_bullet_map", "alien_map", "alien_dir", "enemy_move_interval",
+                    "alien_move_timer", "alien_shot_timer", "ramp_index", "shot_timer", "time", "terminal")
+
+    def reset_env(self, key):
+        n = key.shape[0]
+        alien = np.zeros((n, 10, 10), I32)
+        alien[:, 0:4, 2:8] = 1
+        s = dict(pos=np.full(n, 5, I32), f_bullet_map=np.zeros((n, 10, 10), I32),
+                 e_bullet_map=np.zeros((n, 10, 10), I32), alien_map=alien, alien_dir=np.full(n, -1, I32),
+                 enemy_move_interval=np.full(n, self.enemy_move_interval, I32),
+                 alien_move_timer=np.full(n, self.enemy_move_interval, I32),
+                 alien_shot_timer=np.full(n, self.enemy_shot_interval, I32), ramp_index=np.zeros(n, I32),
+                 shot_timer=np.zeros(n, I32), time=np.zeros(n, I32), terminal=np.zeros(n, bool))
+        return self.get_obs(s), s
+
+    def get_obs(self, s):
+        n = s["pos"].shape[0]
+        idx = np.arange(n)
+        obs = np.zeros((n, 10, 10, 6), bool)
+        obs[idx, 9, s["pos"], 0] = True
+        al = s["alien_map"] != 0
+        obs[:, :, :, 1] = al
+        left = (s["alien_dir"] < 0)[:, None, None]
+        obs[:, :, :, 2] = al & left
+        obs[:, :, :, 3] = al & ~left
+        obs[:, :, :, 4] = s["f_bullet_map"] != 0
+        obs[:, :, :, 5] = s["e_bullet_map"] != 0
+        return obs.astype(F32)
+
+    def step_env(self, key, s, action):
+        n = action.shape[0]
+        idx = np.arange(n)
+        a = self.action_set[action]
+        pos = s["pos"].copy()
+        fb, eb, al = s["f_bullet_map"].copy(), s["e_bullet_map"].copy(), s["alien_map"].copy()
+        shot_timer = s["shot_timer"].copy()
+        # ---- player action
+        fire = (a == 5) & (shot_timer == 0)
+        fb[idx[fire], 9, pos[fire]] = 1
+        shot_timer = np.where(fire, self.shot_cool_down, shot_timer).astype(I32)
+        pos = np.where(~fire & (a == 1), np.maximum(0, pos - 1), pos)
+        pos = np.where(~fire & (a == 3), np.minimum(9, pos + 1), pos).astype(I32)
+        # ---- bullets
+        fb = np.roll(fb, -1, axis=1); fb[:, 9, :] = 0
+        eb = np.roll(eb, 1, axis=1); eb[:, 0, :] = 0
+        terminal = eb[idx, 9, pos] != 0
+        # ---- aliens
+        terminal |= al[idx, 9, pos] != 0
+        move = s["alien_move_timer"] == 0
+        amt = np.where(move, np.minimum(np.count_nonzero(al.reshape(n, -1), axis=1), s["enemy_move_interval"]),
+                       s["alien_move_timer"]).astype(I32)
+        adir = s["alien_dir"].copy()
+        edge = ((al[:, :, 0].sum(1) > 0) & (adir < 0)) | ((al[:, :, 9].sum(1) > 0) & (adir > 0))
+        rev = move & edge
+        terminal |= rev & (al[:, 9, :].sum(1) > 0)
+        adir = np.where(rev, -adir, adir).astype(I32)
+        al_down = np.roll(al, 1, axis=1)
+        al_left = np.roll(al, -1, axis=2)
+        al_right = np.roll(al, 1, axis=2)
+        side = move & ~edge
+        al = np.where(rev[:, None, None], al_down, al)
+        al = np.where((side & (s["alien_dir"] < 0))[:, None, None], al_left, al)
+        al = np.where((side & (s["alien_dir"] > 0))[:, None, None], al_right, al)
+        terminal |= move & (al[idx, 9, pos] != 0)
+        # ---- alien shot from the alien nearest to the cannon (ties: lower column first)
+        shoot = s["alien_shot_timer"] == 0
+        ast = np.where(shoot, self.enemy_shot_interval, s["alien_shot_timer"]).astype(I32)
+        cols = np.arange(10)
+        for i in np.nonzero(shoot)[0]:
+            order = np.argsort(np.abs(cols - pos[i]), kind="stable")
+            for c in order:
+                if al[i, :, c].sum() > 0:
+                    eb[i, np.max(np.nonzero(al[i, :, c])[0]), c] = 1
+                    break
+        # ---- kills
+        kill = (al != 0) & (fb != 0)
+        reward = kill.reshape(n, -1).sum(1).astype(F32)
+        al = np.where(kill, 0, al); fb = np.where(kill, 0, fb)
+        # ---- timers, ramping, respawn
+        shot_timer = (shot_timer - (shot_timer > 0)).astype(I32)
+        amt = (amt - 1).astype(I32)
+        ast = (ast - 1).astype(I32)
+        empty = np.count_nonzero(al.reshape(n, -1), axis=1) == 0
+        ramp = empty & (s["enemy_move_interval"] > 6)
+        emi = np.where(ramp, s["enemy_move_interval"] - 1, s["enemy_move_interval"]).astype(I32)
+        ridx = np.where(ramp, s["ramp_index"] + 1, s["ramp_index"]).astype(I32)
+        al[empty, 0:4, 2:8] = 1
+        time = (s["time"] + 1).astype(I32)
+        done = terminal | (time >= self.max_steps_in_episode)
+        ns = dict(pos=pos, f_bullet_map=fb.astype(I32), e_bullet_map=eb.astype(I32), alien_map=al.astype(I32),
+                  alien_dir=adir, enemy_move_interval=emi, alien_move_timer=amt, alien_shot_timer=ast,
+                  ramp_index=ridx, shot_timer=shot_timer, time=time, terminal=done)
+        info = {"discount": np.where(done, F32(0.0), F32(1.0)).astype(F32)}
+        return self.get_obs(ns), ns, reward, done, info
+
+
+# --------------------------------------------------------------------------- #
 # CartPole-v1  (gymnax/environments/classic_control/cartpole.py)
 # --------------------------------------------------------------------------- #
 class CartPole:
@@ -350,7 +539,7 @@ def register(cls):
     return cls
 
 
-for _c in (Breakout, CartPole, Acrobot):
+for _c in (Breakout, Freeway, SpaceInvaders, CartPole, Acrobot):
     register(_c)
 
 

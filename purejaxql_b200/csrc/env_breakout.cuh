@@ -26,6 +26,7 @@ struct BreakoutEnv {
   static constexpr int OBS_H = 10, OBS_W = 10, OBS_C = 4;
   static constexpr int OBS_DIM = 400;
   static constexpr bool BINARY_OBS = true;
+  static constexpr bool OBS_IN_REGS = true;  // obs_bits() fills a register array (fixed cell count)
   static constexpr int OBS_WORDS = 13;      // ceil(400/32)
   static constexpr int OBS_WORDS_PAD = 16;  // 64-byte rows in the packed rollout buffer
   static constexpr int DEFAULT_MAX_STEPS = 1000;

@@ -19,6 +19,8 @@ struct CartPoleEnv {
   static constexpr int NUM_ACTIONS = 2;
   static constexpr int OBS_DIM = 4;
   static constexpr bool BINARY_OBS = false;
+  static constexpr bool OBS_IN_REGS = false;
+  static constexpr int OBS_WORDS = 1, OBS_WORDS_PAD = 1;
   static constexpr int DEFAULT_MAX_STEPS = 500;
 
   struct State {
@@ -86,6 +88,8 @@ struct AcrobotEnv {
   static constexpr int NUM_ACTIONS = 3;
   static constexpr int OBS_DIM = 6;
   static constexpr bool BINARY_OBS = false;
+  static constexpr bool OBS_IN_REGS = false;
+  static constexpr int OBS_WORDS = 1, OBS_WORDS_PAD = 1;
   static constexpr int DEFAULT_MAX_STEPS = 500;
 
   struct State {

@@ -17,6 +17,7 @@
 #include "api_common.h"
 #include "env_breakout.cuh"
 #include "env_classic.cuh"
+#include "env_minatar_more.cuh"
 #include "rollout_logic.cuh"
 
 namespace pqn {
@@ -26,16 +27,36 @@ constexpr int ENV_BLOCK = 128;
 // ---------------------------------------------------------------------------
 // observation writers
 // ---------------------------------------------------------------------------
-// Binary obs -> float32[N][OBS_DIM]: each warp stages its 32 packed rows in
-// shared memory (word-major: conflict-free), then writes the 32*OBS_DIM floats
-// as consecutive float4 — 512 contiguous bytes per store instruction.
+// Shared-memory scratch of a block for binary observations: word-major [OBS_WORDS_PAD][ENV_BLOCK] (thread t owns
+// column t: conflict-free).  Env::OBS_IN_REGS games (Breakout) build the words in registers and copy them in;
+// the others set bits directly in their column.
 template <class Env>
-__device__ __forceinline__ void write_obs_float_binary(const uint32_t (&bits)[Env::OBS_WORDS_PAD],
-                                                       uint32_t* __restrict__ smem_warp, float* __restrict__ obs,
+struct ObsScratch {
+  static constexpr int WORDS = Env::BINARY_OBS ? Env::OBS_WORDS_PAD * ENV_BLOCK : 1;
+};
+
+template <class Env>
+__device__ __forceinline__ void obs_to_scratch(const typename Env::State& s, bool active, uint32_t* __restrict__ scratch) {
+  uint32_t* col = scratch + threadIdx.x;
+  if constexpr (Env::OBS_IN_REGS) {
+    uint32_t bits[Env::OBS_WORDS_PAD];
+    if (active) Env::obs_bits(s, bits);
+#pragma unroll
+    for (int w = 0; w < Env::OBS_WORDS_PAD; ++w) col[w * ENV_BLOCK] = active ? bits[w] : 0u;
+  } else {
+#pragma unroll
+    for (int w = 0; w < Env::OBS_WORDS_PAD; ++w) col[w * ENV_BLOCK] = 0u;
+    if (active) Env::obs_bits_mem(s, col, ENV_BLOCK);
+  }
+}
+
+// Binary obs -> float32[N][OBS_DIM]: each warp expands its 32 staged rows and writes the 32*OBS_DIM floats as
+// consecutive float4 — 512 contiguous bytes per store instruction.
+template <class Env>
+__device__ __forceinline__ void write_obs_float_binary(const uint32_t* __restrict__ scratch, float* __restrict__ obs,
                                                        int64_t warp_env0, int64_t N) {
   const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int w = 0; w < Env::OBS_WORDS; ++w) smem_warp[w * 32 + lane] = bits[w];
+  const uint32_t* __restrict__ sw = scratch + (threadIdx.x & ~31);  // this warp's 32 columns
   __syncwarp();
   constexpr int V = Env::OBS_DIM / 4;  // float4 per env
   const int64_t n_here = (N - warp_env0) < 32 ? (N - warp_env0) : 32;
@@ -45,7 +66,7 @@ __device__ __forceinline__ void write_obs_float_binary(const uint32_t (&bits)[En
     const int env = g / V;
     const int q = g - env * V;
     const int bit = q * 4;
-    const uint32_t nib = (smem_warp[(bit >> 5) * 32 + env] >> (bit & 31)) & 15u;
+    const uint32_t nib = (sw[(bit >> 5) * ENV_BLOCK + env] >> (bit & 31)) & 15u;
     float4 v;
     v.x = (nib & 1u) ? 1.f : 0.f; v.y = (nib & 2u) ? 1.f : 0.f;
     v.z = (nib & 4u) ? 1.f : 0.f; v.w = (nib & 8u) ? 1.f : 0.f;
@@ -54,13 +75,16 @@ __device__ __forceinline__ void write_obs_float_binary(const uint32_t (&bits)[En
   __syncwarp();
 }
 
+// packed row (OBS_WORDS_PAD words, 16-byte multiple) of this thread's env from its scratch column
 template <class Env>
-__device__ __forceinline__ void write_obs_packed(const uint32_t (&bits)[Env::OBS_WORDS_PAD],
-                                                 uint32_t* __restrict__ obs_packed, int64_t i) {
+__device__ __forceinline__ void write_obs_packed(const uint32_t* __restrict__ scratch, uint32_t* __restrict__ obs_packed,
+                                                 int64_t i) {
+  const uint32_t* col = scratch + threadIdx.x;
   uint4* __restrict__ row = reinterpret_cast<uint4*>(obs_packed + i * Env::OBS_WORDS_PAD);
 #pragma unroll
   for (int v = 0; v < Env::OBS_WORDS_PAD / 4; ++v)
-    row[v] = make_uint4(bits[4 * v], bits[4 * v + 1], bits[4 * v + 2], bits[4 * v + 3]);
+    row[v] = make_uint4(col[(4 * v) * ENV_BLOCK], col[(4 * v + 1) * ENV_BLOCK], col[(4 * v + 2) * ENV_BLOCK],
+                        col[(4 * v + 3) * ENV_BLOCK]);
 }
 
 template <class Env>
@@ -80,7 +104,7 @@ __global__ void __launch_bounds__(ENV_BLOCK) env_reset_kernel(const uint32_t* __
                                                               uint32_t* __restrict__ state,
                                                               float* __restrict__ obs, int64_t N, int max_steps,
                                                               int part) {
-  __shared__ uint32_t smem[Env::BINARY_OBS ? (ENV_BLOCK / 32) * 32 * 32 : 1];
+  __shared__ uint32_t smem[ObsScratch<Env>::WORDS];
   const int64_t i = (int64_t)blockIdx.x * ENV_BLOCK + threadIdx.x;
   const bool active = i < N;
   typename Env::State s;
@@ -94,15 +118,9 @@ __global__ void __launch_bounds__(ENV_BLOCK) env_reset_kernel(const uint32_t* __
   }
   if (obs != nullptr) {
     if constexpr (Env::BINARY_OBS) {
-      uint32_t bits[Env::OBS_WORDS_PAD];
-      if (active) Env::obs_bits(s, bits);
-      else {
-#pragma unroll
-        for (int w = 0; w < Env::OBS_WORDS_PAD; ++w) bits[w] = 0u;
-      }
+      obs_to_scratch<Env>(s, active, smem);
       const int64_t warp_env0 = (int64_t)blockIdx.x * ENV_BLOCK + (threadIdx.x & ~31);
-      if (warp_env0 < N)
-        write_obs_float_binary<Env>(bits, smem + (threadIdx.x >> 5) * 32 * 32, obs, warp_env0, N);
+      if (warp_env0 < N) write_obs_float_binary<Env>(smem, obs, warp_env0, N);
     } else {
       if (active) write_obs_float_dense<Env>(s, obs, i);
     }
@@ -116,7 +134,7 @@ __global__ void __launch_bounds__(ENV_BLOCK)
                     uint8_t* __restrict__ done, float* __restrict__ info_discount,
                     float* __restrict__ info_ret, int32_t* __restrict__ info_len,
                     int32_t* __restrict__ info_t, int64_t N, int max_steps, int part) {
-  __shared__ uint32_t smem[Env::BINARY_OBS ? (ENV_BLOCK / 32) * 32 * 32 : 1];
+  __shared__ uint32_t smem[ObsScratch<Env>::WORDS];
   const int64_t i = (int64_t)blockIdx.x * ENV_BLOCK + threadIdx.x;
   const bool active = i < N;
   typename Env::State s;
@@ -139,15 +157,9 @@ __global__ void __launch_bounds__(ENV_BLOCK)
   }
   if (obs != nullptr) {
     if constexpr (Env::BINARY_OBS) {
-      uint32_t bits[Env::OBS_WORDS_PAD];
-      if (active) Env::obs_bits(s, bits);
-      else {
-#pragma unroll
-        for (int w = 0; w < Env::OBS_WORDS_PAD; ++w) bits[w] = 0u;
-      }
+      obs_to_scratch<Env>(s, active, smem);
       const int64_t warp_env0 = (int64_t)blockIdx.x * ENV_BLOCK + (threadIdx.x & ~31);
-      if (warp_env0 < N)
-        write_obs_float_binary<Env>(bits, smem + (threadIdx.x >> 5) * 32 * 32, obs, warp_env0, N);
+      if (warp_env0 < N) write_obs_float_binary<Env>(smem, obs, warp_env0, N);
     } else {
       if (active) write_obs_float_dense<Env>(s, obs, i);
     }
@@ -158,23 +170,17 @@ template <class Env>
 __global__ void __launch_bounds__(ENV_BLOCK)
     env_obs_kernel(const uint32_t* __restrict__ state, float* __restrict__ obs, uint32_t* __restrict__ obs_packed,
                    int64_t N) {
-  __shared__ uint32_t smem[Env::BINARY_OBS ? (ENV_BLOCK / 32) * 32 * 32 : 1];
+  __shared__ uint32_t smem[ObsScratch<Env>::WORDS];
   const int64_t i = (int64_t)blockIdx.x * ENV_BLOCK + threadIdx.x;
   const bool active = i < N;
   typename Env::State s;
   if (active) Env::load(s, state, N, i);
   if constexpr (Env::BINARY_OBS) {
-    uint32_t bits[Env::OBS_WORDS_PAD];
-    if (active) Env::obs_bits(s, bits);
-    else {
-#pragma unroll
-      for (int w = 0; w < Env::OBS_WORDS_PAD; ++w) bits[w] = 0u;
-    }
-    if (obs_packed != nullptr && active) write_obs_packed<Env>(bits, obs_packed, i);
+    obs_to_scratch<Env>(s, active, smem);
+    if (obs_packed != nullptr && active) write_obs_packed<Env>(smem, obs_packed, i);
     if (obs != nullptr) {
       const int64_t warp_env0 = (int64_t)blockIdx.x * ENV_BLOCK + (threadIdx.x & ~31);
-      if (warp_env0 < N)
-        write_obs_float_binary<Env>(bits, smem + (threadIdx.x >> 5) * 32 * 32, obs, warp_env0, N);
+      if (warp_env0 < N) write_obs_float_binary<Env>(smem, obs, warp_env0, N);
     }
   } else {
     if (obs != nullptr && active) write_obs_float_dense<Env>(s, obs, i);
@@ -201,6 +207,7 @@ __global__ void __launch_bounds__(ENV_BLOCK)
                             float* __restrict__ maxq_out, double* __restrict__ info_sums, int E, int max_steps,
                             float rew_scale, int part, int64_t obs_seed_stride, int64_t tr_seed_stride,
                             int info_done_only) {
+  __shared__ uint32_t obs_smem[ObsScratch<Env>::WORDS];
   const int seed = blockIdx.y;
   const int e = blockIdx.x * ENV_BLOCK + threadIdx.x;
   const int64_t N = (int64_t)gridDim.y * E;
@@ -230,9 +237,8 @@ __global__ void __launch_bounds__(ENV_BLOCK)
     done_out[it] = d ? 1 : 0;
     maxq_out[it] = mq;
     if constexpr (Env::BINARY_OBS) {
-      uint32_t bits[Env::OBS_WORDS_PAD];
-      Env::obs_bits(s, bits);
-      write_obs_packed<Env>(bits, reinterpret_cast<uint32_t*>(obs_next), io);
+      obs_to_scratch<Env>(s, true, obs_smem);
+      write_obs_packed<Env>(obs_smem, reinterpret_cast<uint32_t*>(obs_next), io);
     } else {
       write_obs_float_dense<Env>(s, reinterpret_cast<float*>(obs_next), io);
     }
@@ -343,6 +349,8 @@ static void fill_info(pqn_env_info_t* o) {
 #define PQN_ENV_DISPATCH(env_id, ...)                                           \
   switch (env_id) {                                                             \
     case ENV_BREAKOUT: { using EnvT = BreakoutEnv; __VA_ARGS__; } break;        \
+    case ENV_FREEWAY: { using EnvT = FreewayEnv; __VA_ARGS__; } break;          \
+    case ENV_SPACE_INVADERS: { using EnvT = SpaceInvadersEnv; __VA_ARGS__; } break; \
     case ENV_CARTPOLE: { using EnvT = CartPoleEnv; __VA_ARGS__; } break;        \
     case ENV_ACROBOT: { using EnvT = AcrobotEnv; __VA_ARGS__; } break;          \
     default: return set_error(PQN_E_UNSUPPORTED, "env id %d is not built into libpqn_b200", env_id); \

@@ -75,6 +75,36 @@ def state_to_fields(env_name: str, state: torch.Tensor) -> dict:
         bits = (words[p >> 5] >> (p & 31).unsqueeze(1)) & 1                # [100, N]
         f["brick_map"] = bits.t().reshape(n, 10, 10).to(torch.float32)
         core = 6
+    elif env_name == "Freeway-MinAtar":
+        w = st[0]
+        f["pos"] = w & 15
+        f["move_timer"] = (w >> 4) & 3
+        f["terminal"] = ((w >> 6) & 1).bool()
+        f["time"] = st[1]
+        cars = []
+        for c in range(8):
+            v = (st[2 + c // 2] >> (16 * (c % 2))) & 0xFFFF
+            cars.append(torch.stack([v & 15, torch.full_like(v, c + 1), (v >> 4) & 7, ((v >> 7) & 15) - 5], -1))
+        f["cars"] = torch.stack(cars, 1)                                    # [N, 8, 4] = (x, y, timer, speed)
+        core = 6
+    elif env_name == "SpaceInvaders-MinAtar":
+        w = st[0]
+        f["pos"] = w & 15
+        f["alien_dir"] = ((w >> 4) & 1) * 2 - 1
+        f["enemy_move_interval"] = (w >> 5) & 15
+        f["alien_move_timer"] = (w >> 9) & 15
+        f["alien_shot_timer"] = (w >> 13) & 15
+        f["shot_timer"] = (w >> 17) & 7
+        f["terminal"] = ((w >> 20) & 1).bool()
+        f["ramp_index"] = (w >> 21) & 15
+        f["time"] = st[1]
+        n = st.shape[1]
+        p = torch.arange(100, device=st.device)
+        for name, base in (("alien_map", 2), ("f_bullet_map", 6), ("e_bullet_map", 10)):
+            words = st[base:base + 4].to(torch.int64) & 0xFFFFFFFF
+            bits = (words[p >> 5] >> (p & 31).unsqueeze(1)) & 1
+            f[name] = bits.t().reshape(n, 10, 10).to(torch.int32)
+        core = 14
     elif env_name == "CartPole-v1":
         for j, k in enumerate(("x", "x_dot", "theta", "theta_dot")):
             f[k] = _u2f(st[j])
@@ -112,6 +142,29 @@ def fields_to_state(env_name: str, f: dict) -> torch.Tensor:
             v = torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32)
             words.append(v)
         core = [w, i32(f["time"])] + words
+    elif env_name == "Freeway-MinAtar":
+        cars = i32(f["cars"])
+        words = []
+        for k in range(4):
+            v = torch.zeros_like(cars[:, 0, 0])
+            for h in range(2):
+                c = 2 * k + h
+                v = v | ((cars[:, c, 0] | (cars[:, c, 2] << 4) | ((cars[:, c, 3] + 5) << 7)) << (16 * h))
+            words.append(v)
+        core = [i32(f["pos"]) | (i32(f["move_timer"]) << 4) | (i32(f["terminal"]) << 6), i32(f["time"])] + words
+    elif env_name == "SpaceInvaders-MinAtar":
+        w = (i32(f["pos"]) | ((i32(f["alien_dir"]) > 0).to(torch.int32) << 4) | (i32(f["enemy_move_interval"]) << 5)
+             | (i32(f["alien_move_timer"]) << 9) | (i32(f["alien_shot_timer"]) << 13) | (i32(f["shot_timer"]) << 17)
+             | (i32(f["terminal"]) << 20) | (i32(f["ramp_index"]) << 21))
+        n = w.shape[0]
+        core = [w, i32(f["time"])]
+        for name in ("alien_map", "f_bullet_map", "e_bullet_map"):
+            bm = (torch.as_tensor(f[name]).reshape(n, 100) != 0).to(torch.int64)
+            for k in range(4):
+                lo, hi = 32 * k, min(100, 32 * k + 32)
+                sh = torch.arange(hi - lo, device=bm.device)
+                v = (bm[:, lo:hi] << sh).sum(1)
+                core.append(torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32))
     elif env_name == "CartPole-v1":
         core = [_f2u(torch.as_tensor(f[k])) for k in ("x", "x_dot", "theta", "theta_dot")] + [i32(f["time"])]
     elif env_name == "Acrobot-v1":

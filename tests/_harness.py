@@ -29,7 +29,8 @@ def ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-ENV_IDS = {"Breakout-MinAtar": 0, "CartPole-v1": 16, "Acrobot-v1": 17}
+ENV_IDS = {"Breakout-MinAtar": 0, "Asterix-MinAtar": 1, "SpaceInvaders-MinAtar": 2, "Freeway-MinAtar": 3,
+           "CartPole-v1": 16, "Acrobot-v1": 17}
 
 
 class HostEnv:

@@ -32,6 +32,8 @@ def trajectory(name, n, steps, seed, part=False, max_steps=0):
         ks = jr.split(key, 3)
         key, ka, kst = ks[0], ks[1], ks[2]
         act = jr.randint(jr.split(ka, n), (), 0, env.num_actions)
+        if name == "Freeway-MinAtar":          # mostly "up": the chicken reaches the top, cars re-randomise
+            act = np.where(np.arange(n) % 4 != 0, 1, act).astype(np.int32)
         sk = jr.split(kst, n)
         obs, st, r, d, info = env.step(sk, st, act)
         out["step_keys"].append(sk); out["action"].append(act); out["obs"].append(obs)
@@ -44,7 +46,8 @@ def trajectory(name, n, steps, seed, part=False, max_steps=0):
     res["final_time"] = st["time"]
     jr.DEFAULT_PARTITIONABLE = False
     if max_steps:
-        type(env.env.core).max_steps_in_episode = 1000 if name.endswith("MinAtar") else 500
+        type(env.env.core).max_steps_in_episode = {"Breakout-MinAtar": 1000, "Freeway-MinAtar": 2500,
+                                                   "SpaceInvaders-MinAtar": 1000}.get(name, 500)
     return res
 
 
@@ -53,6 +56,10 @@ if __name__ == "__main__":
                         **trajectory("Breakout-MinAtar", 48, 300, 2024))
     np.savez_compressed(os.path.join(HERE, "breakout_traj_partitionable.npz"),
                         **trajectory("Breakout-MinAtar", 48, 120, 7, part=True))
+    np.savez_compressed(os.path.join(HERE, "freeway_traj_original.npz"),
+                        **trajectory("Freeway-MinAtar", 32, 200, 5))
+    np.savez_compressed(os.path.join(HERE, "spaceinvaders_traj_original.npz"),
+                        **trajectory("SpaceInvaders-MinAtar", 32, 400, 6))
     np.savez_compressed(os.path.join(HERE, "cartpole_traj_original.npz"), **trajectory("CartPole-v1", 32, 120, 11))
     np.savez_compressed(os.path.join(HERE, "acrobot_traj_original.npz"), **trajectory("Acrobot-v1", 32, 60, 13))
     print("golden trajectories written")

@@ -9,6 +9,7 @@
 
 #include "../purejaxql_b200/csrc/env_breakout.cuh"
 #include "../purejaxql_b200/csrc/env_classic.cuh"
+#include "../purejaxql_b200/csrc/env_minatar_more.cuh"
 #include "../purejaxql_b200/csrc/rollout_logic.cuh"
 
 using namespace pqn;
@@ -17,7 +18,12 @@ template <class Env>
 static void obs_out(const typename Env::State& s, float* obs, int64_t i) {
   if constexpr (Env::BINARY_OBS) {
     uint32_t bits[Env::OBS_WORDS_PAD];
-    Env::obs_bits(s, bits);
+    if constexpr (Env::OBS_IN_REGS) {
+      Env::obs_bits(s, bits);
+    } else {
+      for (int w = 0; w < Env::OBS_WORDS_PAD; ++w) bits[w] = 0u;
+      Env::obs_bits_mem(s, bits, 1);
+    }
     for (int f = 0; f < Env::OBS_DIM; ++f) obs[i * Env::OBS_DIM + f] = (float)((bits[f >> 5] >> (f & 31)) & 1u);
   } else {
     float o[Env::OBS_DIM];
@@ -62,6 +68,8 @@ extern "C" {
 int h_state_words(int env_id) {
   switch (env_id) {
     case ENV_BREAKOUT: return BreakoutEnv::STATE_WORDS;
+    case ENV_FREEWAY: return FreewayEnv::STATE_WORDS;
+    case ENV_SPACE_INVADERS: return SpaceInvadersEnv::STATE_WORDS;
     case ENV_CARTPOLE: return CartPoleEnv::STATE_WORDS;
     case ENV_ACROBOT: return AcrobotEnv::STATE_WORDS;
   }
@@ -70,6 +78,8 @@ int h_state_words(int env_id) {
 int h_env_reset(int env_id, const uint32_t* keys, uint32_t* state, float* obs, int64_t N, int max_steps, int part) {
   switch (env_id) {
     case ENV_BREAKOUT: reset_t<BreakoutEnv>(keys, state, obs, N, max_steps, part); return 0;
+    case ENV_FREEWAY: reset_t<FreewayEnv>(keys, state, obs, N, max_steps, part); return 0;
+    case ENV_SPACE_INVADERS: reset_t<SpaceInvadersEnv>(keys, state, obs, N, max_steps, part); return 0;
     case ENV_CARTPOLE: reset_t<CartPoleEnv>(keys, state, obs, N, max_steps, part); return 0;
     case ENV_ACROBOT: reset_t<AcrobotEnv>(keys, state, obs, N, max_steps, part); return 0;
   }
@@ -79,6 +89,8 @@ int h_env_step(int env_id, const uint32_t* keys, uint32_t* state, const int32_t*
                uint8_t* done, int64_t N, int max_steps, int part) {
   switch (env_id) {
     case ENV_BREAKOUT: step_t<BreakoutEnv>(keys, state, action, obs, reward, done, N, max_steps, part); return 0;
+    case ENV_FREEWAY: step_t<FreewayEnv>(keys, state, action, obs, reward, done, N, max_steps, part); return 0;
+    case ENV_SPACE_INVADERS: step_t<SpaceInvadersEnv>(keys, state, action, obs, reward, done, N, max_steps, part); return 0;
     case ENV_CARTPOLE: step_t<CartPoleEnv>(keys, state, action, obs, reward, done, N, max_steps, part); return 0;
     case ENV_ACROBOT: step_t<AcrobotEnv>(keys, state, action, obs, reward, done, N, max_steps, part); return 0;
   }

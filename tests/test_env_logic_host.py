@@ -54,6 +54,8 @@ def _rollout_compare(name, steps, n, part, exact, max_steps=0, atol=0.0):
             ks = jr.split(key, 3)
             key, ka, kst = ks[0], ks[1], ks[2]
             act = jr.randint(jr.split(ka, n), (), 0, env.num_actions)
+            if name == "Freeway-MinAtar":      # mostly "up" so that the chicken reaches the top (cars re-randomise)
+                act = np.where(np.arange(n) % 4 != 0, 1, act).astype(np.int32)
             skeys = jr.split(kst, n)
             if not exact:  # teacher-force the oracle state so fp32 drift cannot accumulate
                 h_st = E.fields_to_state(name, {k: torch.from_numpy(np.ascontiguousarray(v))
@@ -73,6 +75,25 @@ def _rollout_compare(name, steps, n, part, exact, max_steps=0, atol=0.0):
     finally:
         jr.DEFAULT_PARTITIONABLE = False
         G.Breakout.max_steps_in_episode = 1000
+        G.Freeway.max_steps_in_episode = 2500
+        G.SpaceInvaders.max_steps_in_episode = 1000
+
+
+def test_space_invaders_logic_bit_exact():
+    _rollout_compare("SpaceInvaders-MinAtar", steps=700, n=96, part=0, exact=True)
+
+
+def test_space_invaders_time_limit():
+    _rollout_compare("SpaceInvaders-MinAtar", steps=40, n=32, part=0, exact=True, max_steps=11)
+
+
+@pytest.mark.parametrize("part", [0, 1])
+def test_freeway_logic_bit_exact(part):
+    _rollout_compare("Freeway-MinAtar", steps=300, n=96, part=part, exact=True)
+
+
+def test_freeway_time_limit():
+    _rollout_compare("Freeway-MinAtar", steps=30, n=32, part=0, exact=True, max_steps=9)
 
 
 @pytest.mark.parametrize("part", [0, 1])

@@ -21,8 +21,10 @@ def _load(name):
 @pytest.mark.parametrize("fname,env_name,part", [
     ("breakout_traj_original.npz", "Breakout-MinAtar", 0),
     ("breakout_traj_partitionable.npz", "Breakout-MinAtar", 1),
+    ("freeway_traj_original.npz", "Freeway-MinAtar", 0),
+    ("spaceinvaders_traj_original.npz", "SpaceInvaders-MinAtar", 0),
 ])
-def test_breakout_golden_oracle_and_device_logic(fname, env_name, part):
+def test_minatar_golden_oracle_and_device_logic(fname, env_name, part):
     g = _load(fname)
     jr.DEFAULT_PARTITIONABLE = bool(part)
     try:
@@ -30,18 +32,22 @@ def test_breakout_golden_oracle_and_device_logic(fname, env_name, part):
         h = _harness.HostEnv(env_name, part=part)
         n = g["reset_keys"].shape[0]
         o_obs, o_st = env.reset(g["reset_keys"])
-        h_obs, h_st = h.reset(g["reset_keys"], 400, 1000)
-        gold0 = np.unpackbits(g["obs0"], axis=-1)[:, :400].astype(np.float32)
+        D = int(np.prod(env.obs_shape))
+        dmax = env.env.core.max_steps_in_episode
+        h_obs, h_st = h.reset(g["reset_keys"], D, dmax)
+        gold0 = np.unpackbits(g["obs0"], axis=-1)[:, :D].astype(np.float32)
         assert np.array_equal(o_obs.reshape(n, -1), gold0) and np.array_equal(h_obs, gold0)
         for t in range(g["action"].shape[0]):
             o_obs, o_st, o_r, o_d, info = env.step(g["step_keys"][t], o_st, g["action"][t])
-            h_obs, h_st, h_r, h_d = h.step(g["step_keys"][t], h_st, g["action"][t], 400, 1000)
-            gold = np.unpackbits(g["obs"][t], axis=-1)[:, :400].astype(np.float32)
+            h_obs, h_st, h_r, h_d = h.step(g["step_keys"][t], h_st, g["action"][t], D, dmax)
+            gold = np.unpackbits(g["obs"][t], axis=-1)[:, :D].astype(np.float32)
             for obs, r, d in ((o_obs.reshape(n, -1), o_r, o_d), (h_obs, h_r, h_d)):
                 assert np.array_equal(obs, gold), t
                 assert np.array_equal(r, g["reward"][t]) and np.array_equal(d, g["done"][t]), t
             assert np.array_equal(info["returned_episode_returns"], g["ret"][t])
-        assert g["done"].sum() > 50 and g["reward"].sum() > 50   # the fixture exercises resets and bricks
+        assert g["reward"].sum() > 20                              # the fixture exercises scoring
+        if env_name != "Freeway-MinAtar":
+            assert g["done"].sum() > 20                            # ... and auto-resets
     finally:
         jr.DEFAULT_PARTITIONABLE = False
 

@@ -69,6 +69,57 @@ def test_breakout_golden_bit_exact(fname, part):
     assert np.array_equal(envs.state_to_fields("Breakout-MinAtar", st)["time"].cpu().numpy(), g["final_time"])
 
 
+@pytest.mark.parametrize("fname,name", [("freeway_traj_original.npz", "Freeway-MinAtar"),
+                                        ("spaceinvaders_traj_original.npz", "SpaceInvaders-MinAtar")])
+def test_other_minatar_golden_bit_exact(fname, name):
+    from purejaxql_b200 import envs
+    g = dict(np.load(os.path.join(GOLD, fname)))
+    env, params = envs.make(name)
+    D = env.obs_dim
+    obs, st = env.reset(tkeys(g["reset_keys"]), params)
+    n = g["reset_keys"].shape[0]
+    assert np.array_equal(obs.cpu().numpy().reshape(n, -1), np.unpackbits(g["obs0"], axis=-1)[:, :D])
+    for t in range(g["action"].shape[0]):
+        obs, st, r, d, info = env.step(tkeys(g["step_keys"][t]), st, torch.from_numpy(g["action"][t]).to(dev()), params)
+        assert np.array_equal(obs.cpu().numpy().reshape(n, -1), np.unpackbits(g["obs"][t], axis=-1)[:, :D]), t
+        assert np.array_equal(r.cpu().numpy(), g["reward"][t]) and np.array_equal(d.cpu().numpy(), g["done"][t]), t
+        assert np.array_equal(info["returned_episode_returns"].cpu().numpy(), g["ret"][t])
+    assert np.array_equal(envs.state_to_fields(name, st)["time"].cpu().numpy(), g["final_time"])
+
+
+@pytest.mark.parametrize("name,steps", [("Freeway-MinAtar", 2600), ("SpaceInvaders-MinAtar", 1200)])
+def test_other_minatar_vs_oracle_long(name, steps):
+    """Ragged N, long enough to hit the time limit; full state compared every 100 steps."""
+    from purejaxql_b200 import envs
+    n = 300 + 13
+    oenv = G.make(name)
+    env, params = envs.make(name)
+    key = jr.PRNGKey(99)
+    ks = jr.split(key, 2); key, kr = ks[0], ks[1]
+    rk = jr.split(kr, n)
+    o_obs, o_st = oenv.reset(rk)
+    obs, st = env.reset(tkeys(rk), params)
+    assert np.array_equal(obs.cpu().numpy(), o_obs)
+    tot_r, tot_d = 0.0, 0
+    for t in range(steps):
+        ks = jr.split(key, 3); key, ka, kst = ks[0], ks[1], ks[2]
+        act = jr.randint(jr.split(ka, n), (), 0, oenv.num_actions)
+        if name == "Freeway-MinAtar":
+            act = np.where(np.arange(n) % 4 != 0, 1, act).astype(np.int32)
+        sk = jr.split(kst, n)
+        o_obs, o_st, o_r, o_d, o_info = oenv.step(sk, o_st, act)
+        obs, st, r, d, info = env.step(tkeys(sk), st, torch.from_numpy(act).to(dev()), params)
+        assert np.array_equal(d.cpu().numpy(), o_d), t
+        assert np.array_equal(r.cpu().numpy(), o_r), t
+        tot_r += float(o_r.sum()); tot_d += int(o_d.sum())
+        if t % 100 == 0 or t == steps - 1:
+            assert np.array_equal(obs.cpu().numpy(), o_obs), t
+            f = envs.state_to_fields(name, st)
+            for k, v in o_st.items():
+                assert np.array_equal(f[k].cpu().numpy().astype(v.dtype), v), (t, k)
+    assert tot_r > 0 and tot_d > 0
+
+
 def test_breakout_vs_oracle_long_ragged_and_truncation():
     """N not a multiple of the warp/block size, 1500 steps (time-limit truncation at
     1000 is reached), full state compared field by field every 50 steps."""

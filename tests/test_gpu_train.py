@@ -172,3 +172,42 @@ def test_minatar_smoke_with_eval_and_save(tmp_path):
     assert tuple(tree["CNN_0"]["Conv_0"]["kernel"].shape) == (3, 3, 4, 16)
     assert tuple(tree["CNN_0"]["Dense_0"]["kernel"].shape) == (1024, 128)
     assert tuple(tree["Dense_0"]["kernel"].shape) == (128, 3) and "BatchNorm_0" in tree
+
+
+@pytest.mark.parametrize("env_name", ["Freeway-MinAtar", "SpaceInvaders-MinAtar"])
+def test_other_minatar_first_update_matches_oracle(env_name):
+    """C=7 / C=6 games through the whole engine: one update with eps=1 reproduces the oracle's parameters."""
+    from purejaxql_b200 import pqn_minatar
+    cfg = _cfg(env_name, NUM_ENVS=64, NUM_STEPS=8, NUM_MINIBATCHES=4)
+    cfg["TOTAL_TIMESTEPS"] = cfg["TOTAL_TIMESTEPS_DECAY"] = float(cfg["NUM_STEPS"] * cfg["NUM_ENVS"])
+    train = pqn_minatar.make_train(cfg)
+    eng = train.engine
+    rngs = jr.split(jr.PRNGKey(2), 1)
+    cap = {}
+    orig = eng.spec.init
+    eng.spec.init = lambda k, d: cap.setdefault("flat", orig(k, d)).clone()
+    out = train(rngs)
+    ts = out["runner_state"][0]
+    tree0 = eng.spec.unflatten(cap["flat"])
+    E = cfg["NUM_ENVS"]
+
+    def leaf(tree, path):
+        d = tree
+        for k in path:
+            d = d[k]
+        return d[0].cpu().numpy()
+    params = {"/".join(p): leaf(tree0, p).astype(np.float32) for p, *_ in eng.spec.entries}
+    K1 = jr.split(rngs[0], 2)[0]
+    K2 = jr.split(K1, 2)[0]
+    k = jr.split(K2, 2); K3, kR = k[0], k[1]
+    env = G.make(env_name)
+    obs, st = env.reset(jr.split(kR, E))
+    rng = jr.split(K3, 2)[1]
+    total = cfg["NUM_UPDATES_DECAY"] * cfg["NUM_MINIBATCHES"] * cfg["NUM_EPOCHS"]
+    lr_fn = lambda i: R.linear_schedule(cfg["LR"], 1e-20, total, i)
+    C = eng.spec.in_c
+    bs = {"mean": np.zeros(C, np.float32), "var": np.ones(C, np.float32)}
+    # the oracle's CNN helpers are written for any channel count
+    p2, *_ = R.update_step(env, "cnn", params, R.opt_init(params), bs, obs, st, rng, dict(cfg), 0, lr_fn)
+    for p, *_ in eng.spec.entries:
+        assert np.abs(leaf(ts.params, p) - p2["/".join(p)]).max() < 1e-5, p
