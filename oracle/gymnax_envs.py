@@ -305,6 +305,121 @@ class SpaceInvaders:
 
 
 # --------------------------------------------------------------------------- #
+# MinAtar Asterix  (gymnax/environments/minatar/asterix.py)
+# --------------------------------------------------------------------------- #
+def _choice_p(key, p):
+    """``jax.random.choice(key, len(p), p=p)`` per row: cumsum, r = total*(1-uniform), searchsorted-left (f32)."""
+    cum = np.cumsum(p.astype(F32), axis=-1, dtype=F32)
+    r = (cum[:, -1] * (F32(1.0) - jr.uniform(key, ()))).astype(F32)
+    with np.errstate(invalid="ignore"):
+        return (cum < r[:, None]).sum(-1).astype(I32)
+
+
+class Asterix:
+    """Restated from MinAtar asterix.py in gymnax 0.0.6's conventions (entities [x, y=slot+1, lr, is_gold,
+    filled]; every step splits its key three ways for direction / treasure / slot draws).  The exact RNG
+    recipe of gymnax's `spawn_entity` could not be checked against a live install (parity unpinned)."""
+    name = "Asterix-MinAtar"
+    obs_shape = (10, 10, 4)
+    num_actions = 5                        # minimal action set [0..4] = noop/left/up/right/down
+    max_steps_in_episode = 1000
+    ramp_interval, init_spawn_speed, init_move_interval = 100, 10, 5
+    state_fields = ("player_x", "player_y", "shot_timer", "spawn_speed", "spawn_timer", "move_speed", "move_timer",
+                    "ramp_timer", "ramp_index", "entities", "time", "terminal")
+
+    def reset_env(self, key):
+        n = key.shape[0]
+        z = lambda v: np.full(n, v, I32)
+        s = dict(player_x=z(5), player_y=z(5), shot_timer=z(0), spawn_speed=z(self.init_spawn_speed),
+                 spawn_timer=z(self.init_spawn_speed), move_speed=z(self.init_move_interval),
+                 move_timer=z(self.init_move_interval), ramp_timer=z(self.ramp_interval), ramp_index=z(0),
+                 entities=np.zeros((n, 8, 5), I32), time=z(0), terminal=np.zeros(n, bool))
+        return self.get_obs(s), s
+
+    def get_obs(self, s):
+        n = s["player_x"].shape[0]
+        idx = np.arange(n)
+        obs = np.zeros((n, 10, 10, 4), bool)
+        obs[idx, s["player_y"], s["player_x"], 0] = True
+        for e in range(8):
+            ent = s["entities"][:, e]
+            on = ent[:, 4] == 1
+            ch = np.where(ent[:, 3] == 1, 3, 1)
+            obs[idx[on], ent[on, 1], ent[on, 0], ch[on]] = True
+            back = np.where(ent[:, 2] == 1, ent[:, 0] - 1, ent[:, 0] + 1)
+            ok = on & (back >= 0) & (back <= 9)
+            obs[idx[ok], ent[ok, 1], back[ok], 2] = True
+        return obs.astype(F32)
+
+    def step_env(self, key, s, action):
+        n = action.shape[0]
+        ent = s["entities"].copy()
+        ks = jr.split(key, 3)
+        lr = (1 - jr.randint(ks[:, 0], (), 0, 2)).astype(I32)                 # choice(key_lr, [1, 0])
+        is_gold = (1 - _choice_p(ks[:, 1], np.tile(np.array([1 / 3, 2 / 3], F32), (n, 1)))).astype(I32)
+        free = (ent[:, :, 4] == 0)
+        nfree = free.sum(1)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            pslot = free.astype(F32) / nfree.astype(F32)[:, None]
+        slot = np.minimum(_choice_p(ks[:, 2], pslot), 7)
+        do_spawn = (s["spawn_timer"] == 0) & (nfree > 0)
+        for i in np.nonzero(do_spawn)[0]:
+            ent[i, slot[i]] = (0 if lr[i] else 9, slot[i] + 1, lr[i], is_gold[i], 1)
+        spawn_timer = np.where(s["spawn_timer"] == 0, s["spawn_speed"], s["spawn_timer"]).astype(I32)
+        # ---- player
+        px, py = s["player_x"].copy(), s["player_y"].copy()
+        px = np.where(action == 1, np.maximum(0, px - 1), np.where(action == 3, np.minimum(9, px + 1), px)).astype(I32)
+        py = np.where(action == 2, np.maximum(1, py - 1), np.where(action == 4, np.minimum(8, py + 1), py)).astype(I32)
+        reward = np.zeros(n, F32)
+        terminal = np.zeros(n, bool)
+
+        def collide():
+            nonlocal reward, terminal
+            for e in range(8):
+                hit = (ent[:, e, 4] == 1) & (ent[:, e, 0] == px) & (ent[:, e, 1] == py)
+                gold = hit & (ent[:, e, 3] == 1)
+                reward = reward + gold.astype(F32)
+                terminal = terminal | (hit & ~gold)
+                ent[gold, e] = 0
+        collide()
+        move = s["move_timer"] == 0
+        move_timer = np.where(move, s["move_speed"], s["move_timer"]).astype(I32)
+        for e in range(8):
+            on = move & (ent[:, e, 4] == 1)
+            nx = ent[:, e, 0] + np.where(ent[:, e, 2] == 1, 1, -1)
+            ent[:, e, 0] = np.where(on, nx, ent[:, e, 0])
+            out = on & ((nx < 0) | (nx > 9))
+            ent[out, e] = 0
+        mv_saved = move
+        if mv_saved.any():
+            r0, t0 = reward.copy(), terminal.copy()
+            ent_before = ent.copy()
+            collide()
+            # the second collision pass only applies where the entities moved
+            reward = np.where(mv_saved, reward, r0)
+            terminal = np.where(mv_saved, terminal, t0)
+            ent = np.where(mv_saved[:, None, None], ent, ent_before)
+        spawn_timer = (spawn_timer - 1).astype(I32)
+        move_timer = (move_timer - 1).astype(I32)
+        # ---- difficulty ramp
+        ss, ms, rt, ri = s["spawn_speed"].copy(), s["move_speed"].copy(), s["ramp_timer"].copy(), s["ramp_index"].copy()
+        active = (ss > 1) | (ms > 1)
+        tick = active & (rt >= 0)
+        fire = active & ~tick
+        ms = np.where(fire & (ms > 1) & (ri % 2 == 1), ms - 1, ms).astype(I32)
+        ss = np.where(fire & (ss > 1), ss - 1, ss).astype(I32)
+        ri = np.where(fire, ri + 1, ri).astype(I32)
+        rt = np.where(tick, rt - 1, np.where(fire, self.ramp_interval, rt)).astype(I32)
+        time = (s["time"] + 1).astype(I32)
+        done = terminal | (time >= self.max_steps_in_episode)
+        ns = dict(player_x=px, player_y=py, shot_timer=s["shot_timer"].copy(), spawn_speed=ss, spawn_timer=spawn_timer,
+                  move_speed=ms, move_timer=move_timer, ramp_timer=rt, ramp_index=ri, entities=ent.astype(I32),
+                  time=time, terminal=done)
+        info = {"discount": np.where(done, F32(0.0), F32(1.0)).astype(F32)}
+        return self.get_obs(ns), ns, reward, done, info
+
+
+# --------------------------------------------------------------------------- #
 # CartPole-v1  (gymnax/environments/classic_control/cartpole.py)
 # --------------------------------------------------------------------------- #
 class CartPole:
@@ -539,7 +654,7 @@ def register(cls):
     return cls
 
 
-for _c in (Breakout, Freeway, SpaceInvaders, CartPole, Acrobot):
+for _c in (Breakout, Asterix, Freeway, SpaceInvaders, CartPole, Acrobot):
     register(_c)
 
 

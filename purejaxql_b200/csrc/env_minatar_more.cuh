@@ -369,4 +369,163 @@ struct SpaceInvadersEnv {
   }
 };
 
+// ---------------------------------------------------------------------------
+// Asterix.  state words: w0 player_x[0:4) player_y[4:8) spawn_speed[8:12) spawn_timer[12:16) move_speed[16:19)
+//   move_timer[19:22) shot_timer[22:25) terminal[25] ; w1 ramp_timer+1 [0:8) ramp_index[8:16) ; w2 time ;
+//   w3,w4 entities, 8 bits each: x[0:4) lr[4] gold[5] filled[6]   (entity e lives in row y = e+1)
+// RNG per step: key_lr, key_gold, key_slot = split(key, 3); lr = choice([1,0]); is_gold = choice([1,0], p=[1/3,2/3]);
+// slot = choice(8, p = free/sum(free))  (jax.random.choice with p: cumsum + searchsorted on total*(1-uniform)).
+// ---------------------------------------------------------------------------
+struct AsterixEnv {
+  static constexpr int ID = ENV_ASTERIX;
+  static constexpr int CORE_WORDS = 5;
+  static constexpr int STATE_WORDS = CORE_WORDS + LOG_WORDS;
+  static constexpr int NUM_ACTIONS = 5;  // noop, left, up, right, down
+  static constexpr int OBS_H = 10, OBS_W = 10, OBS_C = 4;
+  static constexpr int OBS_DIM = 400;
+  static constexpr bool BINARY_OBS = true;
+  static constexpr bool OBS_IN_REGS = false;
+  static constexpr int OBS_WORDS = 13;
+  static constexpr int OBS_WORDS_PAD = 16;
+  static constexpr int DEFAULT_MAX_STEPS = 1000;
+  static constexpr int RAMP_INTERVAL = 100, INIT_SPAWN_SPEED = 10, INIT_MOVE_INTERVAL = 5;
+
+  struct State {
+    int player_x, player_y, shot_timer, spawn_speed, spawn_timer, move_speed, move_timer, ramp_timer, ramp_index, time;
+    bool terminal;
+    int ex[8];
+    bool elr[8], egold[8], efill[8];
+  };
+
+  template <typename W>
+  PQN_HD static void load(State& s, const W* __restrict__ st, int64_t N, int64_t i) {
+    const uint32_t w = st[i], w1 = st[N + i];
+    s.player_x = w & 15u; s.player_y = (w >> 4) & 15u; s.spawn_speed = (w >> 8) & 15u; s.spawn_timer = (w >> 12) & 15u;
+    s.move_speed = (w >> 16) & 7u; s.move_timer = (w >> 19) & 7u; s.shot_timer = (w >> 22) & 7u; s.terminal = (w >> 25) & 1u;
+    s.ramp_timer = (int)(w1 & 255u) - 1; s.ramp_index = (w1 >> 8) & 255u;
+    s.time = (int)st[2 * N + i];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t v = st[(int64_t)(3 + k) * N + i];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const uint32_t e = (v >> (8 * h)) & 255u;
+        s.ex[4 * k + h] = e & 15u; s.elr[4 * k + h] = (e >> 4) & 1u; s.egold[4 * k + h] = (e >> 5) & 1u;
+        s.efill[4 * k + h] = (e >> 6) & 1u;
+      }
+    }
+  }
+  PQN_HD static void store(const State& s, uint32_t* __restrict__ st, int64_t N, int64_t i) {
+    st[i] = (uint32_t)s.player_x | ((uint32_t)s.player_y << 4) | ((uint32_t)s.spawn_speed << 8) |
+            ((uint32_t)s.spawn_timer << 12) | ((uint32_t)s.move_speed << 16) | ((uint32_t)s.move_timer << 19) |
+            ((uint32_t)s.shot_timer << 22) | ((uint32_t)s.terminal << 25);
+    st[N + i] = (uint32_t)(s.ramp_timer + 1) | ((uint32_t)s.ramp_index << 8);
+    st[2 * N + i] = (uint32_t)s.time;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      uint32_t v = 0u;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int e = 4 * k + h;
+        // emptied slots are all-zero (gymnax zeroes the whole entity row)
+        const uint32_t b = s.efill[e] ? ((uint32_t)s.ex[e] | ((uint32_t)s.elr[e] << 4) | ((uint32_t)s.egold[e] << 5) | (1u << 6)) : 0u;
+        v |= b << (8 * h);
+      }
+      st[(int64_t)(3 + k) * N + i] = v;
+    }
+  }
+
+  PQN_HD static void reset_env(Key /*key*/, int /*part*/, int /*max_steps*/, State& s) {
+    s.player_x = 5; s.player_y = 5; s.shot_timer = 0; s.spawn_speed = INIT_SPAWN_SPEED; s.spawn_timer = INIT_SPAWN_SPEED;
+    s.move_speed = INIT_MOVE_INTERVAL; s.move_timer = INIT_MOVE_INTERVAL; s.ramp_timer = RAMP_INTERVAL; s.ramp_index = 0;
+    s.time = 0; s.terminal = false;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s.ex[e] = 0; s.elr[e] = false; s.egold[e] = false; s.efill[e] = false; }
+  }
+
+  PQN_HD static void collide(State& s, int e, float& reward, bool& terminal) {
+    if (s.efill[e] && s.ex[e] == s.player_x && e + 1 == s.player_y) {
+      if (s.egold[e]) { reward += 1.0f; s.efill[e] = false; s.ex[e] = 0; s.elr[e] = false; s.egold[e] = false; }
+      else terminal = true;
+    }
+  }
+
+  PQN_HD static void step_env(Key key, int part, int max_steps, State& s, int action, float& reward, bool& done) {
+    // ---- spawn
+    if (s.spawn_timer == 0) {
+      int nfree = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) nfree += s.efill[e] ? 0 : 1;
+      if (nfree > 0) {
+        Key kl, kg, ks;
+        split3(key, part, kl, kg, ks);
+        const int lr = 1 - randint_scalar(kl, 2u, part);
+        const float c0 = (float)(1.0 / 3.0), c1 = c0 + (float)(2.0 / 3.0);
+        const float rg = c1 * (1.0f - uniform_scalar(kg, part));
+        const int is_gold = 1 - ((c0 < rg ? 1 : 0) + (c1 < rg ? 1 : 0));
+        const float inv = 1.0f / (float)nfree;
+        float cum = 0.f, cums[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { cum = cum + (s.efill[e] ? 0.0f : inv); cums[e] = cum; }
+        const float rs = cum * (1.0f - uniform_scalar(ks, part));
+        int slot = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) slot += cums[e] < rs ? 1 : 0;
+        slot = slot > 7 ? 7 : slot;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (e == slot) { s.ex[e] = lr ? 0 : 9; s.elr[e] = lr != 0; s.egold[e] = is_gold != 0; s.efill[e] = true; }
+      }
+      s.spawn_timer = s.spawn_speed;
+    }
+    // ---- player
+    if (action == 1) s.player_x = s.player_x - 1 < 0 ? 0 : s.player_x - 1;
+    else if (action == 3) s.player_x = s.player_x + 1 > 9 ? 9 : s.player_x + 1;
+    else if (action == 2) s.player_y = s.player_y - 1 < 1 ? 1 : s.player_y - 1;
+    else if (action == 4) s.player_y = s.player_y + 1 > 8 ? 8 : s.player_y + 1;
+    reward = 0.f;
+    bool terminal = false;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) collide(s, e, reward, terminal);
+    if (s.move_timer == 0) {
+      s.move_timer = s.move_speed;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (s.efill[e]) {
+          s.ex[e] += s.elr[e] ? 1 : -1;
+          if (s.ex[e] < 0 || s.ex[e] > 9) { s.efill[e] = false; s.ex[e] = 0; s.elr[e] = false; s.egold[e] = false; }
+        }
+        collide(s, e, reward, terminal);
+      }
+    }
+    s.spawn_timer -= 1;
+    s.move_timer -= 1;
+    // ---- difficulty ramp
+    if (s.spawn_speed > 1 || s.move_speed > 1) {
+      if (s.ramp_timer >= 0) s.ramp_timer -= 1;
+      else {
+        if (s.move_speed > 1 && (s.ramp_index & 1)) s.move_speed -= 1;
+        if (s.spawn_speed > 1) s.spawn_speed -= 1;
+        s.ramp_index += 1;
+        s.ramp_timer = RAMP_INTERVAL;
+      }
+    }
+    s.time += 1;
+    done = terminal || s.time >= max_steps;
+    s.terminal = done;
+  }
+
+  PQN_HD static void obs_bits_mem(const State& s, uint32_t* o, int stride) {
+    obs_set_bit(o, stride, (s.player_y * 10 + s.player_x) * OBS_C + 0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (!s.efill[e]) continue;
+      const int y = e + 1;
+      obs_set_bit(o, stride, (y * 10 + s.ex[e]) * OBS_C + (s.egold[e] ? 3 : 1));
+      const int back = s.elr[e] ? s.ex[e] - 1 : s.ex[e] + 1;
+      if (back >= 0 && back <= 9) obs_set_bit(o, stride, (y * 10 + back) * OBS_C + 2);
+    }
+  }
+};
+
 }  // namespace pqn

@@ -349,6 +349,7 @@ static void fill_info(pqn_env_info_t* o) {
 #define PQN_ENV_DISPATCH(env_id, ...)                                           \
   switch (env_id) {                                                             \
     case ENV_BREAKOUT: { using EnvT = BreakoutEnv; __VA_ARGS__; } break;        \
+    case ENV_ASTERIX: { using EnvT = AsterixEnv; __VA_ARGS__; } break;          \
     case ENV_FREEWAY: { using EnvT = FreewayEnv; __VA_ARGS__; } break;          \
     case ENV_SPACE_INVADERS: { using EnvT = SpaceInvadersEnv; __VA_ARGS__; } break; \
     case ENV_CARTPOLE: { using EnvT = CartPoleEnv; __VA_ARGS__; } break;        \

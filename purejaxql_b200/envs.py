@@ -87,6 +87,26 @@ def state_to_fields(env_name: str, state: torch.Tensor) -> dict:
             cars.append(torch.stack([v & 15, torch.full_like(v, c + 1), (v >> 4) & 7, ((v >> 7) & 15) - 5], -1))
         f["cars"] = torch.stack(cars, 1)                                    # [N, 8, 4] = (x, y, timer, speed)
         core = 6
+    elif env_name == "Asterix-MinAtar":
+        w, w1 = st[0], st[1]
+        f["player_x"] = w & 15
+        f["player_y"] = (w >> 4) & 15
+        f["spawn_speed"] = (w >> 8) & 15
+        f["spawn_timer"] = (w >> 12) & 15
+        f["move_speed"] = (w >> 16) & 7
+        f["move_timer"] = (w >> 19) & 7
+        f["shot_timer"] = (w >> 22) & 7
+        f["terminal"] = ((w >> 25) & 1).bool()
+        f["ramp_timer"] = (w1 & 255) - 1
+        f["ramp_index"] = (w1 >> 8) & 255
+        f["time"] = st[2]
+        ents = []
+        for e in range(8):
+            v = (st[3 + e // 4] >> (8 * (e % 4))) & 255
+            fill = (v >> 6) & 1
+            ents.append(torch.stack([v & 15, fill * (e + 1), (v >> 4) & 1, (v >> 5) & 1, fill], -1))
+        f["entities"] = torch.stack(ents, 1)                                # [N, 8, 5] = (x, y, lr, is_gold, filled)
+        core = 5
     elif env_name == "SpaceInvaders-MinAtar":
         w = st[0]
         f["pos"] = w & 15
@@ -152,6 +172,21 @@ def fields_to_state(env_name: str, f: dict) -> torch.Tensor:
                 v = v | ((cars[:, c, 0] | (cars[:, c, 2] << 4) | ((cars[:, c, 3] + 5) << 7)) << (16 * h))
             words.append(v)
         core = [i32(f["pos"]) | (i32(f["move_timer"]) << 4) | (i32(f["terminal"]) << 6), i32(f["time"])] + words
+    elif env_name == "Asterix-MinAtar":
+        ent = i32(f["entities"])
+        w = (i32(f["player_x"]) | (i32(f["player_y"]) << 4) | (i32(f["spawn_speed"]) << 8) | (i32(f["spawn_timer"]) << 12)
+             | (i32(f["move_speed"]) << 16) | (i32(f["move_timer"]) << 19) | (i32(f["shot_timer"]) << 22)
+             | (i32(f["terminal"]) << 25))
+        w1 = (i32(f["ramp_timer"]) + 1) | (i32(f["ramp_index"]) << 8)
+        words = []
+        for k in range(2):
+            v = torch.zeros_like(w)
+            for h in range(4):
+                e = 4 * k + h
+                b = (ent[:, e, 0] | (ent[:, e, 2] << 4) | (ent[:, e, 3] << 5) | (1 << 6)) * ent[:, e, 4]
+                v = v | (b << (8 * h))
+            words.append(v)
+        core = [w, w1, i32(f["time"])] + words
     elif env_name == "SpaceInvaders-MinAtar":
         w = (i32(f["pos"]) | ((i32(f["alien_dir"]) > 0).to(torch.int32) << 4) | (i32(f["enemy_move_interval"]) << 5)
              | (i32(f["alien_move_timer"]) << 9) | (i32(f["alien_shot_timer"]) << 13) | (i32(f["shot_timer"]) << 17)

@@ -47,7 +47,7 @@ def trajectory(name, n, steps, seed, part=False, max_steps=0):
     jr.DEFAULT_PARTITIONABLE = False
     if max_steps:
         type(env.env.core).max_steps_in_episode = {"Breakout-MinAtar": 1000, "Freeway-MinAtar": 2500,
-                                                   "SpaceInvaders-MinAtar": 1000}.get(name, 500)
+                                                   "SpaceInvaders-MinAtar": 1000, "Asterix-MinAtar": 1000}.get(name, 500)
     return res
 
 
@@ -56,6 +56,8 @@ if __name__ == "__main__":
                         **trajectory("Breakout-MinAtar", 48, 300, 2024))
     np.savez_compressed(os.path.join(HERE, "breakout_traj_partitionable.npz"),
                         **trajectory("Breakout-MinAtar", 48, 120, 7, part=True))
+    np.savez_compressed(os.path.join(HERE, "asterix_traj_original.npz"),
+                        **trajectory("Asterix-MinAtar", 32, 400, 8))
     np.savez_compressed(os.path.join(HERE, "freeway_traj_original.npz"),
                         **trajectory("Freeway-MinAtar", 32, 200, 5))
     np.savez_compressed(os.path.join(HERE, "spaceinvaders_traj_original.npz"),

@@ -69,6 +69,7 @@ int h_state_words(int env_id) {
   switch (env_id) {
     case ENV_BREAKOUT: return BreakoutEnv::STATE_WORDS;
     case ENV_FREEWAY: return FreewayEnv::STATE_WORDS;
+    case ENV_ASTERIX: return AsterixEnv::STATE_WORDS;
     case ENV_SPACE_INVADERS: return SpaceInvadersEnv::STATE_WORDS;
     case ENV_CARTPOLE: return CartPoleEnv::STATE_WORDS;
     case ENV_ACROBOT: return AcrobotEnv::STATE_WORDS;
@@ -79,6 +80,7 @@ int h_env_reset(int env_id, const uint32_t* keys, uint32_t* state, float* obs, i
   switch (env_id) {
     case ENV_BREAKOUT: reset_t<BreakoutEnv>(keys, state, obs, N, max_steps, part); return 0;
     case ENV_FREEWAY: reset_t<FreewayEnv>(keys, state, obs, N, max_steps, part); return 0;
+    case ENV_ASTERIX: reset_t<AsterixEnv>(keys, state, obs, N, max_steps, part); return 0;
     case ENV_SPACE_INVADERS: reset_t<SpaceInvadersEnv>(keys, state, obs, N, max_steps, part); return 0;
     case ENV_CARTPOLE: reset_t<CartPoleEnv>(keys, state, obs, N, max_steps, part); return 0;
     case ENV_ACROBOT: reset_t<AcrobotEnv>(keys, state, obs, N, max_steps, part); return 0;
@@ -90,6 +92,7 @@ int h_env_step(int env_id, const uint32_t* keys, uint32_t* state, const int32_t*
   switch (env_id) {
     case ENV_BREAKOUT: step_t<BreakoutEnv>(keys, state, action, obs, reward, done, N, max_steps, part); return 0;
     case ENV_FREEWAY: step_t<FreewayEnv>(keys, state, action, obs, reward, done, N, max_steps, part); return 0;
+    case ENV_ASTERIX: step_t<AsterixEnv>(keys, state, action, obs, reward, done, N, max_steps, part); return 0;
     case ENV_SPACE_INVADERS: step_t<SpaceInvadersEnv>(keys, state, action, obs, reward, done, N, max_steps, part); return 0;
     case ENV_CARTPOLE: step_t<CartPoleEnv>(keys, state, action, obs, reward, done, N, max_steps, part); return 0;
     case ENV_ACROBOT: step_t<AcrobotEnv>(keys, state, action, obs, reward, done, N, max_steps, part); return 0;

@@ -77,6 +77,12 @@ def _rollout_compare(name, steps, n, part, exact, max_steps=0, atol=0.0):
         G.Breakout.max_steps_in_episode = 1000
         G.Freeway.max_steps_in_episode = 2500
         G.SpaceInvaders.max_steps_in_episode = 1000
+        G.Asterix.max_steps_in_episode = 1000
+
+
+@pytest.mark.parametrize("part", [0, 1])
+def test_asterix_logic_bit_exact(part):
+    _rollout_compare("Asterix-MinAtar", steps=900, n=96, part=part, exact=True)
 
 
 def test_space_invaders_logic_bit_exact():

@@ -21,6 +21,7 @@ def _load(name):
 @pytest.mark.parametrize("fname,env_name,part", [
     ("breakout_traj_original.npz", "Breakout-MinAtar", 0),
     ("breakout_traj_partitionable.npz", "Breakout-MinAtar", 1),
+    ("asterix_traj_original.npz", "Asterix-MinAtar", 0),
     ("freeway_traj_original.npz", "Freeway-MinAtar", 0),
     ("spaceinvaders_traj_original.npz", "SpaceInvaders-MinAtar", 0),
 ])

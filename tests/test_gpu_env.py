@@ -69,7 +69,8 @@ def test_breakout_golden_bit_exact(fname, part):
     assert np.array_equal(envs.state_to_fields("Breakout-MinAtar", st)["time"].cpu().numpy(), g["final_time"])
 
 
-@pytest.mark.parametrize("fname,name", [("freeway_traj_original.npz", "Freeway-MinAtar"),
+@pytest.mark.parametrize("fname,name", [("asterix_traj_original.npz", "Asterix-MinAtar"),
+                                        ("freeway_traj_original.npz", "Freeway-MinAtar"),
                                         ("spaceinvaders_traj_original.npz", "SpaceInvaders-MinAtar")])
 def test_other_minatar_golden_bit_exact(fname, name):
     from purejaxql_b200 import envs
@@ -87,7 +88,8 @@ def test_other_minatar_golden_bit_exact(fname, name):
     assert np.array_equal(envs.state_to_fields(name, st)["time"].cpu().numpy(), g["final_time"])
 
 
-@pytest.mark.parametrize("name,steps", [("Freeway-MinAtar", 2600), ("SpaceInvaders-MinAtar", 1200)])
+@pytest.mark.parametrize("name,steps", [("Asterix-MinAtar", 1200), ("Freeway-MinAtar", 2600),
+                                        ("SpaceInvaders-MinAtar", 1200)])
 def test_other_minatar_vs_oracle_long(name, steps):
     """Ragged N, long enough to hit the time limit; full state compared every 100 steps."""
     from purejaxql_b200 import envs

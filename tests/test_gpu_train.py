@@ -174,7 +174,7 @@ def test_minatar_smoke_with_eval_and_save(tmp_path):
     assert tuple(tree["Dense_0"]["kernel"].shape) == (128, 3) and "BatchNorm_0" in tree
 
 
-@pytest.mark.parametrize("env_name", ["Freeway-MinAtar", "SpaceInvaders-MinAtar"])
+@pytest.mark.parametrize("env_name", ["Asterix-MinAtar", "Freeway-MinAtar", "SpaceInvaders-MinAtar"])
 def test_other_minatar_first_update_matches_oracle(env_name):
     """C=7 / C=6 games through the whole engine: one update with eps=1 reproduces the oracle's parameters."""
     from purejaxql_b200 import pqn_minatar
