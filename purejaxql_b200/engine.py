@@ -177,7 +177,7 @@ class PQNEngine:
         state = torch.empty((self.env.state_words, S * E), dtype=torch.int32, device=dev)
         _lib.check(L.pqn_env_reset(self.env.env_id, _lib.p(reset_keys), _lib.p(state), None, S * E, self.max_steps,
                                    mode, _lib.stream_ptr()), "pqn_env_reset")
-        self._write_obs(state, obs_buf, 0, S)
+        self._write_obs(state, obs_buf, T, S)                        # update_body moves row T to row 0
         rng = jr.split(K3, 2, mode)[:, 1].contiguous()              # :422-423 runner rng
 
         metric_names = ["env_step", "update_steps", "env_frame", "grad_steps", "td_loss", "qvals", *INFO_KEYS]
@@ -193,15 +193,22 @@ class PQNEngine:
         grad_steps = 0
         seed_stride_obs = (T + 1) * E
         seed_stride_tr = T * E
-        perm_view = None
+        # ---- static buffers of the update step (the whole step is CUDA-graph capturable)
+        rng_buf = rng.clone()                                        # runner rng, updated in place
+        kT_buf = torch.zeros((S, 2), dtype=torch.int32, device=dev)  # eval key of this update (:341)
+        upd_idx = torch.zeros(1, dtype=torch.int64, device=dev)      # n_updates on the device
+        m_cur = torch.zeros((S, 7), dtype=torch.float64, device=dev)  # td_loss, qvals, 5 info means
+        ws = self._workspace(S, max(self.mb, E))
+        denom = float(self.epochs * self.nmb)
+        bn_count = float(self.mb * (100 if self.binary else 1))
 
-        on_update_begin = getattr(self, "on_update_begin", None)      # bench/profiling hook
-        for n_updates in range(NU):
-            if on_update_begin is not None:
-                on_update_begin(n_updates)
+        def update_body():
+            """One `_update_step` (pqn_minatar.py:176-350) on the current stream; reads/writes only the static
+            buffers above, so it can be replayed from a CUDA graph."""
             # ================= SAMPLE PHASE (:181-219)
-            eps_dev.copy_(eps_table[n_updates:n_updates + 1])
-            carry = jr.split(rng, 2, mode)[:, 1].contiguous()        # :213  `_rng`
+            eps_dev.copy_(eps_table.index_select(0, upd_idx))
+            obs_buf[:, 0].copy_(obs_buf[:, T])                       # last_obs of this rollout = last next_obs
+            carry = jr.split(rng_buf, 2, mode)[:, 1].contiguous()    # :213  `_rng`
             _lib.check(L.pqn_rollout_keys(_lib.p(carry), _lib.p(step_keys), S, T, mode, sp()), "pqn_rollout_keys")
             info_sums.zero_()
             for t in range(T):
@@ -213,23 +220,21 @@ class PQNEngine:
                     _lib.raw(done_buf[:, t]), _lib.raw(maxq_buf[:, t]),
                     seed_stride_tr, _lib.p(info_sums), 0, S, E, self.max_steps, self.rew_scale, mode, sp()),
                     "pqn_rollout_act_step")
-            rng = carry                                              # scan's final carry (:214)
-            timesteps += T * E                                       # :222-225
+            r = carry                                                # scan's final carry (:214)
             # ================= bootstrap + Q(lambda) (:227-260)
             self.forward(params, obs_buf[:, T], S, E, seed_stride_obs, q_buf)
             _lib.check(L.pqn_qlambda(_lib.p(rew_buf), _lib.p(done_buf), _lib.p(maxq_buf), _lib.p(q_buf),
                                      _lib.p(targets), T, S, E, A, self.gamma, self.lam, sp()), "pqn_qlambda")
             # ================= NETWORKS UPDATE (:263-327)
-            rng = jr.split(rng, 2, mode)[:, 0].contiguous()          # :324
+            r = jr.split(r, 2, mode)[:, 0].contiguous()              # :324
             loss_sum.zero_()
             qsa_sum.zero_()
-            ws = self._workspace(S, max(self.mb, E))
             for _ in range(self.epochs):
-                k = jr.split(rng, 2, mode)                           # :309
-                rng, kperm = k[:, 0].contiguous(), k[:, 1].contiguous()
+                k = jr.split(r, 2, mode)                             # :309
+                r, kperm = k[:, 0].contiguous(), k[:, 1].contiguous()
                 perm = jr.permutation_indices(kperm, T * E, mode)    # :299-315 same perm for every leaf
                 perm_view = perm.view(S, self.nmb, self.mb).transpose(0, 1).contiguous()
-                rng = jr.split(rng, 2, mode)[:, 0].contiguous()      # :317
+                r = jr.split(r, 2, mode)[:, 0].contiguous()          # :317
                 for mbi in range(self.nmb):
                     _lib.check(L.pqn_qnet_loss_grad(
                         spec.desc, _lib.p(params), _lib.p(obs_buf), _lib.p(perm_view[mbi]), seed_stride_obs,
@@ -239,10 +244,50 @@ class PQNEngine:
                                                      _lib.p(sched), _lib.p(step_counter), _lib.p(gnorm), S, P,
                                                      float(c["MAX_GRAD_NORM"]), 0.9, 0.999, 1e-8, sp()),
                                "pqn_radam_clip_step")
-                    count = float(self.mb * (100 if self.binary else 1))
-                    _lib.check(L.pqn_bn_stats_update(_lib.p(batch_stats), _lib.p(bn_sums), S, F, count, 0.99, sp()),
+                    _lib.check(L.pqn_bn_stats_update(_lib.p(batch_stats), _lib.p(bn_sums), S, F, bn_count, 0.99, sp()),
                                "pqn_bn_stats_update")
-                    grad_steps += 1
+            if self.test:                                            # :341  rng, _rng = split(rng)
+                k = jr.split(r, 2, mode)
+                r = k[:, 0].contiguous()
+                kT_buf.copy_(k[:, 1])
+            rng_buf.copy_(r)
+            m_cur[:, 0] = loss_sum.double() / denom
+            m_cur[:, 1] = qsa_sum.double() / denom
+            m_cur[:, 2:7] = info_sums / float(T * E)
+            upd_idx.add_(1)
+
+        # CUDA graph: "auto" captures the update when the run is launch-bound (small S*E); the first update runs
+        # eagerly (warms every code path), later updates replay the captured graph.
+        want_graph = c.get("CUDA_GRAPH", "auto")
+        use_graph = (S * E * T <= (1 << 21)) if want_graph == "auto" else bool(want_graph)
+        use_graph = use_graph and NU > 2 and getattr(self, "on_update_begin", None) is None
+        graph = None
+        self.graph_captured = False
+
+        on_update_begin = getattr(self, "on_update_begin", None)      # bench/profiling hook
+        for n_updates in range(NU):
+            if on_update_begin is not None:
+                on_update_begin(n_updates)
+            if graph is not None:
+                graph.replay()
+            else:
+                update_body()
+                if use_graph and n_updates == 0:
+                    try:
+                        torch.cuda.synchronize(dev)
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            update_body()
+                        graph = g
+                        self.graph_captured = True
+                    except Exception as e:                            # capture is an optimisation only
+                        import warnings
+                        warnings.warn(f"CUDA graph capture of the update step failed ({e!r}); running eagerly")
+                        graph = None
+                        use_graph = False
+                        torch.cuda.synchronize(dev)
+            timesteps += T * E                                       # :222-225
+            grad_steps += self.nmb * self.epochs
             # ================= metrics (:329-338)
             n_done = n_updates + 1
             col = n_updates
@@ -250,21 +295,19 @@ class PQNEngine:
             metrics["update_steps"][:, col] = n_done
             metrics["env_frame"][:, col] = timesteps * obs_channels
             metrics["grad_steps"][:, col] = grad_steps
-            denom = float(self.epochs * self.nmb)
-            metrics["td_loss"][:, col] = loss_sum.double() / denom
-            metrics["qvals"][:, col] = qsa_sum.double() / denom
+            metrics["td_loss"][:, col] = m_cur[:, 0]
+            metrics["qvals"][:, col] = m_cur[:, 1]
             for j, kk in enumerate(INFO_KEYS):
-                metrics[kk][:, col] = info_sums[:, j] / float(T * E)
+                metrics[kk][:, col] = m_cur[:, 2 + j]
             # ================= evaluation (:340-350)
             if self.test:
-                k = jr.split(rng, 2, mode)
-                rng, kT = k[:, 0].contiguous(), k[:, 1].contiguous()
                 if test_every > 0 and n_done % test_every == 0:
-                    test_metrics = self.get_test_metrics(params, kT)
+                    test_metrics = self.get_test_metrics(params, kT_buf.clone())
                 for kk in INFO_KEYS:
                     test_hist[kk][:, col] = test_metrics[kk]
             if c.get("WANDB_MODE", "disabled") != "disabled":
                 self._wandb_log(metrics, test_hist, col, jr.to_numpy_u32(keys)[:, 0])
+        rng = rng_buf
 
         torch.cuda.synchronize(dev)
         out_metrics = {m: v[:, :NU].float() if m in ("td_loss", "qvals", *INFO_KEYS) else v[:, :NU].to(torch.int64)

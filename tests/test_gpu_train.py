@@ -21,14 +21,15 @@ def _cfg(env, **kw):
     return c
 
 
-def _run_one_update_against_oracle(module, env_name, kind, flatten, cfg, S=2):
-    from purejaxql_b200 import jaxrandom
-    nupd = 3
+def _run_updates_against_oracle(module, env_name, kind, flatten, cfg, S=2, nupd=3, graph=False):
+    """eps = 1 for the whole run (every action random => every rollout is integer-exact), so ALL updates of the
+    engine — obs hand-over between updates, key chain, permutations, optimizer — must track the oracle."""
+    cfg["EPS_START"] = cfg["EPS_FINISH"] = 1.0
+    cfg["CUDA_GRAPH"] = graph
     cfg["TOTAL_TIMESTEPS"] = cfg["TOTAL_TIMESTEPS_DECAY"] = float(nupd * cfg["NUM_STEPS"] * cfg["NUM_ENVS"])
     train = module.make_train(cfg)
     eng = train.engine
     rngs = jr.split(jr.PRNGKey(0), S)
-    # deterministic init shared with the oracle: capture the engine's init
     captured = {}
     orig_init = eng.spec.init
 
@@ -38,6 +39,7 @@ def _run_one_update_against_oracle(module, env_name, kind, flatten, cfg, S=2):
         return flat
     eng.spec.init = init
     out = train(rngs)
+    assert eng.graph_captured == bool(graph)
     ts = out["runner_state"][0]
     tree0 = eng.spec.unflatten(captured["flat"])
     T, E = cfg["NUM_STEPS"], cfg["NUM_ENVS"]
@@ -48,9 +50,7 @@ def _run_one_update_against_oracle(module, env_name, kind, flatten, cfg, S=2):
                 d = d[k]
             return d[s].cpu().numpy()
         params = {"/".join(p): leaf(tree0, p).astype(np.float32) for p, *_ in eng.spec.entries}
-        # ---- oracle key chain
-        K = rngs[s]
-        K1 = jr.split(K, 2)[0]
+        K1 = jr.split(rngs[s], 2)[0]                                 # oracle key chain
         K2 = jr.split(K1, 2)[0]
         k = jr.split(K2, 2); K3, kR = k[0], k[1]
         env = G.make(env_name, flatten=flatten)
@@ -59,38 +59,48 @@ def _run_one_update_against_oracle(module, env_name, kind, flatten, cfg, S=2):
         opt = R.opt_init(params)
         F = eng.spec.in_c
         bs = {"mean": np.zeros(F, np.float32), "var": np.ones(F, np.float32)}
-        ocfg = dict(cfg)
         total = cfg["NUM_UPDATES_DECAY"] * cfg["NUM_MINIBATCHES"] * cfg["NUM_EPOCHS"]
         lr_fn = lambda i: R.linear_schedule(cfg["LR"], 1e-20, total, i)
         for u in range(nupd):
-            params, opt, bs, obs, st, rng, m, tr, tg = R.update_step(env, kind, params, opt, bs, obs, st, rng, ocfg,
+            params, opt, bs, obs, st, rng, m, tr, tg = R.update_step(env, kind, params, opt, bs, obs, st, rng, dict(cfg),
                                                                      u, lr_fn)
-            # integer/byte results of the rollout are exact as long as the argmax decisions agree;
-            # eps=1 in update 0 makes every action random => the whole first rollout is bit-exact.
             got = {kk: float(v[s, u]) for kk, v in out["metrics"].items()}
-            if u == 0:
-                for kk in ("returned_episode_returns", "returned_episode_lengths", "timestep", "returned_episode",
-                           "discount"):
-                    assert abs(got[kk] - m[kk]) < 1e-6 * max(1, abs(m[kk])), (kk, got[kk], m[kk])
-                assert abs(got["td_loss"] - m["td_loss"]) < 2e-5 * max(1.0, abs(m["td_loss"])), (got["td_loss"], m["td_loss"])
-                assert abs(got["qvals"] - m["qvals"]) < 2e-5 * max(1.0, abs(m["qvals"]))
-        if u == 0 or True:
-            pass
-        # after update 0 the parameters must agree tightly; later updates can differ only through
-        # argmax flips of near-tied q-values, so compare loosely there.
+            # integer games: exact rollouts; fp32 physics (classic control) may flip a termination once in a while
+            itol, ltol = (1e-6, 1e-4) if kind == "cnn" else (2e-2, 2e-2)
+            for kk in ("returned_episode_returns", "returned_episode_lengths", "timestep", "returned_episode",
+                       "discount"):
+                assert abs(got[kk] - m[kk]) < itol * max(1, abs(m[kk])), (u, kk, got[kk], m[kk])
+            assert abs(got["td_loss"] - m["td_loss"]) < ltol * max(1.0, abs(m["td_loss"])), (u, got["td_loss"], m["td_loss"])
+            assert abs(got["qvals"] - m["qvals"]) < ltol * max(1.0, abs(m["qvals"])), u
+        if kind == "cnn":
+            for p, *_ in eng.spec.entries:                           # parameters after ALL updates
+                assert np.abs(leaf(ts.params, p) - params["/".join(p)]).max() < 5e-5, p
+        assert np.array_equal(out["runner_state"][3][s].cpu().numpy().view(np.uint32), rng)
     return out
 
 
 def test_minatar_update_step_matches_oracle():
     from purejaxql_b200 import pqn_minatar
     cfg = _cfg("Breakout-MinAtar")
-    _run_one_update_against_oracle(pqn_minatar, "Breakout-MinAtar", "cnn", False, cfg)
+    _run_updates_against_oracle(pqn_minatar, "Breakout-MinAtar", "cnn", False, cfg)
+
+
+def test_minatar_update_steps_under_cuda_graph_match_oracle():
+    from purejaxql_b200 import pqn_minatar
+    cfg = _cfg("Breakout-MinAtar")
+    _run_updates_against_oracle(pqn_minatar, "Breakout-MinAtar", "cnn", False, cfg, nupd=4, graph=True)
 
 
 def test_gymnax_update_step_matches_oracle():
     from purejaxql_b200 import pqn_gymnax
     cfg = _cfg("CartPole-v1", HIDDEN_SIZE=128, NUM_LAYERS=2, REW_SCALE=0.1, LAMBDA=0.95, NUM_ENVS=32, NUM_STEPS=16)
-    _run_one_update_against_oracle(pqn_gymnax, "CartPole-v1", "mlp", True, cfg)
+    _run_updates_against_oracle(pqn_gymnax, "CartPole-v1", "mlp", True, cfg)
+
+
+def test_gymnax_update_steps_under_cuda_graph_match_oracle():
+    from purejaxql_b200 import pqn_gymnax
+    cfg = _cfg("CartPole-v1", HIDDEN_SIZE=128, NUM_LAYERS=2, REW_SCALE=0.1, LAMBDA=0.95, NUM_ENVS=32, NUM_STEPS=16)
+    _run_updates_against_oracle(pqn_gymnax, "CartPole-v1", "mlp", True, cfg, nupd=4, graph=True)
 
 
 def test_params_after_first_update_match_oracle():
