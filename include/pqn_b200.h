@@ -168,6 +168,10 @@ int pqn_net_layout(const pqn_net_desc_t* desc_host, pqn_net_layout_t* out_host);
 /* bytes of scratch the forward/backward need for `rows` samples per seed */
 int64_t pqn_net_workspace_bytes(const pqn_net_desc_t* desc_host, int32_t S, int64_t rows);
 
+/* network.init (pqn_minatar.py:156-170) on the device: flax-default initialisers (he_normal / lecun_normal
+ * truncated normals, zero biases, unit norm scales) drawn counter-based from keys[S][2]. */
+int pqn_net_init(const pqn_net_desc_t* desc_host, const uint32_t* keys, float* params, int32_t S, void* stream);
+
 /* q[S][rows][A] = network.apply(params, obs, train=False) — pqn_minatar.py:184-191,227-234.
  *  obs: packed uint32[S][rows_total][packed_words] (CNN) or float32[S][rows_total][D] (MLP);
  *  gather (may be NULL): int32[S][rows] row indices into the seed's obs rows

@@ -61,6 +61,7 @@ _SIGS = {
                             c_float, c_float, c_void_p]),
     "pqn_net_layout": (c_int, [POINTER(NetDesc), POINTER(NetLayout)]),
     "pqn_net_workspace_bytes": (c_int64, [POINTER(NetDesc), c_int32, c_int64]),
+    "pqn_net_init": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_int32, c_void_p]),
     "pqn_qnet_forward": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32,
                                  c_int64, c_void_p, c_void_p]),
     "pqn_qnet_loss_grad": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,

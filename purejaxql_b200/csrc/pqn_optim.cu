@@ -13,10 +13,12 @@
 // The per-step scalars (lr_t, 1-b1^t, 1-b2^t, r_t or 0) come from a device table
 // indexed by a device step counter so that the whole update can live in a CUDA graph.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "../../include/pqn_b200.h"
 #include "api_common.h"
+#include "threefry.cuh"
 
 namespace pqn {
 
@@ -103,6 +105,50 @@ __global__ void bn_update_kernel(float* __restrict__ batch_stats, float* __restr
   sm[F + f] = 0.f;
 }
 
+// Parameter initialisation on the device (network.init, purejaxql/pqn_minatar.py:156-170): flax defaults —
+// Conv/Dense kernels variance_scaling(scale, "fan_in", "truncated_normal") with scale 2 (he_normal) or 1
+// (lecun_normal), i.e. N(0,1) truncated to [-2,2] times sqrt(scale/fan_in)/0.87962566; biases 0; norm scales 1.
+// Draws are counter-based (threefry block (element, attempt) under a per-tensor key derived from the seed key)
+// with Box-Muller + rejection: deterministic in the seed key, same distribution as flax, not the same draws
+// (flax folds module paths into the key).
+struct InitEntry {
+  long long off, n;
+  float std;   // > 0: truncated normal * std ; 0: zeros ; < 0: ones
+};
+constexpr int MAX_INIT = 16;
+struct InitTable {
+  int count;
+  InitEntry e[MAX_INIT];
+};
+
+__global__ void net_init_kernel(const uint32_t* __restrict__ keys, float* __restrict__ params, int64_t P, InitTable tab) {
+  const int seed = blockIdx.y;
+  const Key sk{keys[2 * seed], keys[2 * seed + 1]};
+  for (int t = 0; t < tab.count; ++t) {
+    const InitEntry en = tab.e[t];
+    const Key kt = split_at(sk, (uint32_t)MAX_INIT, (uint32_t)t, 0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < en.n; i += (long long)gridDim.x * blockDim.x) {
+      float v;
+      if (en.std == 0.f) v = 0.f;
+      else if (en.std < 0.f) v = 1.f;
+      else {
+        float z = 0.f;
+        for (uint32_t a = 0; a < 32u; ++a) {
+          uint32_t x0 = (uint32_t)i, x1 = a;
+          threefry2x32(kt.k0, kt.k1, x0, x1);
+          const float u1 = ((float)(x0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
+          const float u2 = ((float)(x1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+          z = sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+          if (fabsf(z) <= 2.0f) break;
+          z = fminf(fmaxf(z, -2.0f), 2.0f);
+        }
+        v = z * en.std;
+      }
+      params[(int64_t)seed * P + en.off + i] = v;
+    }
+  }
+}
+
 }  // namespace pqn
 
 using namespace pqn;
@@ -124,6 +170,43 @@ int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu,
                                             b2, eps); }
   { LaunchScope _ls(K_ADVANCE, st); advance_kernel<<<1, 1, 0, st>>>(step_counter); }
   return check_launch("pqn_radam_clip_step");
+}
+
+int pqn_net_init(const pqn_net_desc_t* d, const uint32_t* keys, float* params, int32_t S, void* stream) {
+  pqn_net_layout_t L;
+  int rc = pqn_net_layout(d, &L);
+  if (rc) return rc;
+  if (!keys || !params || S <= 0 || S > 65535) return set_error(PQN_E_INVALID, "pqn_net_init: bad argument");
+  InitTable tab;
+  tab.count = 0;
+  auto add = [&](int64_t off, int64_t n, float std) {
+    if (off >= 0 && tab.count < MAX_INIT) tab.e[tab.count++] = InitEntry{(long long)off, (long long)n, std};
+  };
+  auto tn = [](double scale, double fan_in) { return (float)(sqrt(scale / fan_in) / 0.87962566103423978); };
+  const int A = d->num_actions;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(params, 0, (size_t)S * L.total * sizeof(float), st) != cudaSuccess) return check_launch("pqn_net_init(memset)");
+  if (d->kind == PQN_NET_MINATAR_CNN) {
+    const int C = d->in_c;
+    add(L.bn_scale, C, -1.f);
+    add(L.conv_w, 9 * C * 16, tn(2.0, 9.0 * C));            // he_normal (pqn_minatar.py:43)
+    add(L.ln0_scale, 16, -1.f);
+    add(L.d0_w, 1024 * 128, tn(2.0, 1024.0));               // he_normal (:48)
+    add(L.ln1_scale, 128, -1.f);
+    add(L.head_w, 128 * A, tn(1.0, 128.0));                 // lecun_normal default (:68)
+  } else {
+    const int D = d->in_c, H = d->hidden;
+    add(L.bn_scale, D, -1.f);
+    add(L.d0_w, (int64_t)D * H, tn(1.0, D));
+    add(L.ln0_scale, H, -1.f);
+    if (d->layers == 2) {
+      add(L.d1_w, (int64_t)H * H, tn(1.0, H));
+      add(L.ln1_scale, H, -1.f);
+    }
+    add(L.head_w, (int64_t)H * A, tn(1.0, H));
+  }
+  { LaunchScope _ls(K_NET_INIT, st); net_init_kernel<<<dim3(64, S), 256, 0, st>>>(keys, params, L.total, tab); }
+  return check_launch("pqn_net_init");
 }
 
 int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F, float count, float momentum,

@@ -144,7 +144,7 @@ class PQNEngine:
         # ---- key chain (pqn_minatar.py:172-173,415-423)
         k = jr.split(keys, 2, mode)
         K1 = k[:, 0].contiguous()                                   # :172 rng (also the init key, :173)
-        params = spec.init(jr.to_numpy_u32(K1), dev)                # :156-170
+        params = spec.init(K1, dev)                                 # :156-170
         mu = torch.zeros_like(params)
         nu = torch.zeros_like(params)
         grads = torch.zeros_like(params)

@@ -101,8 +101,18 @@ class QNetworkSpec:
             flat[:, off:off + n] = v.reshape(S if batched else 1, n)
         return flat.to(device)
 
-    def init(self, keys_u32: np.ndarray, device="cuda") -> torch.Tensor:
-        """flax-default initialisers (he_normal for Conv/Dense_0 of the CNN,
+    def init(self, keys, device="cuda") -> torch.Tensor:
+        """``network.init`` on the device (``pqn_net_init``): flax-default initialisers, deterministic in the
+        per-seed key but not flax's draws (flax folds module paths into the key).
+        ``keys``: int32[S,2] CUDA tensor."""
+        S = keys.shape[0]
+        flat = torch.empty((S, self.total), dtype=torch.float32, device=keys.device)
+        _lib.check(_lib.lib().pqn_net_init(self.desc, _lib.p(keys.contiguous()), _lib.p(flat), S, _lib.stream_ptr()),
+                   "pqn_net_init")
+        return flat
+
+    def init_host(self, keys_u32: np.ndarray, device="cuda") -> torch.Tensor:
+        """Host (torch CPU generator) variant of the same initialisers, kept for tests.  flax-default initialisers (he_normal for Conv/Dense_0 of the CNN,
         lecun_normal elsewhere — truncated normal at +-2 sigma, variance-scaled by
         fan_in; zeros biases; ones LayerNorm/BatchNorm scales).  Deterministic in
         the per-seed key but NOT bit-identical to flax's draws (flax folds module

@@ -217,3 +217,31 @@ def test_radam_clip_matches_oracle():
     assert int(cnt.item()) == steps
     for s in range(S):
         assert np.abs(tp[s].cpu().numpy() - refs[s][0]["w"]).max() < 2e-6
+
+
+def test_device_param_init_distribution_and_determinism():
+    from purejaxql_b200 import jaxrandom
+    from purejaxql_b200.networks import NET_CNN, NET_MLP, QNetworkSpec
+    keys = jaxrandom.split(jaxrandom.PRNGKey(0, dev()), 4)
+    for spec in (QNetworkSpec(NET_CNN, 4, 3), QNetworkSpec(NET_MLP, 6, 3, 256, 2)):
+        a = spec.init(keys, dev())
+        b = spec.init(keys, dev())
+        assert torch.equal(a, b)                                   # deterministic in the keys
+        tree = spec.unflatten(a)
+        assert not torch.equal(a[0], a[1])                         # seeds differ
+        for path, off, shape, kind in spec.entries:
+            d = tree
+            for k in path:
+                d = d[k]
+            w = d.cpu().numpy()
+            if kind == "ones":
+                assert (w == 1).all()
+            elif kind == "zeros":
+                assert (w == 0).all()
+            else:
+                fan_in = int(np.prod(shape[:-1]))
+                target = np.sqrt((2.0 if kind == "he" else 1.0) / fan_in)
+                assert np.abs(w).max() <= 2.0 * target / 0.87962566 + 1e-6       # truncated at 2 sigma
+                if w.size > 4000:
+                    assert abs(w.std() / target - 1.0) < 0.05, (path, w.std(), target)
+                    assert abs(w.mean()) < 0.05 * target
