@@ -308,6 +308,9 @@ def run_gpu(args, rank, world, local_rank):
                 "note": ("fp32-accurate 3xTF32 on tcgen05: each algorithmic FLOP costs 3 tf32 MMAs at half the bf16 "
                          "rate, so the fp32-equivalent tensor peak is peak/6 = %.0f TFLOP/s; the kernel also streams "
                          "its A operand (x and x_lo) from HBM" % (peak / 6.0)) if dom.startswith("tc_") else
+                        ("warp-level tf32 tensor-core MMA (mma.sync m16n8k8, A operand built from the packed observation "
+                         "bits, weights/dz split hi+lo => 2 MMAs per algorithmic one); instruction-issue bound, fraction "
+                         "is against the dense bf16 tcgen05 peak") if dom.startswith("conv_") else
                         "fp32 CUDA-core kernel; fraction is against the dense bf16 tensor peak",
                 "frac_of_3xtf32_peak": round(achieved / (peak / 6.0), 4) if dom.startswith("tc_") else None,
                 "hbm_gbs": round(gbs, 1), "hbm_frac": round(gbs / hbm, 4),
