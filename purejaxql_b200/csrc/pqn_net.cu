@@ -996,7 +996,8 @@ template <int C, bool TRAIN>
 __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
     conv_fwd_mma_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
                         const float* __restrict__ params, int64_t P, pqn_net_layout_t L, float* __restrict__ H1,
-                        float* __restrict__ H1LO, float* __restrict__ bn_sums, int rows) {
+                        float* __restrict__ H1LO, float* __restrict__ XH1, float* __restrict__ RS1,
+                        float* __restrict__ bn_sums, int rows) {
   using Cfg = ConvCfg<C>;
   using M = ConvMma<C>;
   __shared__ float2 wb_hi[M::KS * 2 * 32], wb_lo[M::KS * 2 * 32];
@@ -1029,6 +1030,8 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
     __syncwarp();
     float* __restrict__ hrow = H1 + ((int64_t)seed * rows + row) * FLAT_CNN;
     float* __restrict__ lrow = H1LO ? H1LO + ((int64_t)seed * rows + row) * FLAT_CNN : nullptr;
+    float* __restrict__ xrow = (TRAIN && XH1) ? XH1 + ((int64_t)seed * rows + row) * FLAT_CNN : nullptr;
+    float* __restrict__ rrow = (TRAIN && RS1) ? RS1 + ((int64_t)seed * rows + row) * CONV_PIX : nullptr;
 #pragma unroll 1
     for (int mb = 0; mb < 4; ++mb) {
       float z[2][4];
@@ -1046,6 +1049,13 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
         const int p0 = 16 * mb + g, p1 = p0 + 8;
         *reinterpret_cast<float2*>(hrow + p0 * CONV_O + o) = v0;
         *reinterpret_cast<float2*>(hrow + p1 * CONV_O + o) = v1;
+        if (xrow) {  // saved for the backward pass (no conv recompute there)
+          *reinterpret_cast<float2*>(xrow + p0 * CONV_O + o) =
+              make_float2((z[h][0] - mean0) * rstd0, (z[h][1] - mean0) * rstd0);
+          *reinterpret_cast<float2*>(xrow + p1 * CONV_O + o) =
+              make_float2((z[h][2] - mean1) * rstd1, (z[h][3] - mean1) * rstd1);
+          if (h == 0 && t == 0) { rrow[p0] = rstd0; rrow[p1] = rstd1; }
+        }
         if (lrow) {
           *reinterpret_cast<float2*>(lrow + p0 * CONV_O + o) = make_float2(tc::tf32_lo(v0.x), tc::tf32_lo(v0.y));
           *reinterpret_cast<float2*>(lrow + p1 * CONV_O + o) = make_float2(tc::tf32_lo(v1.x), tc::tf32_lo(v1.y));
@@ -1084,7 +1094,8 @@ template <int C>
 __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
     conv_bwd_mma_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
                         const float* __restrict__ params, int64_t P, pqn_net_layout_t L, const float* __restrict__ DY1,
-                        float* __restrict__ grads, int rows) {
+                        const float* __restrict__ XH1, const float* __restrict__ RS1, float* __restrict__ grads,
+                        int rows) {
   using Cfg = ConvCfg<C>;
   using M = ConvMma<C>;
   __shared__ float2 wb_hi[M::KS * 2 * 32], wb_lo[M::KS * 2 * 32];
@@ -1145,9 +1156,26 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
         dyv[h][1] = __ldg(reinterpret_cast<const float2*>(dyrow + p1 * CONV_O + 8 * h + 2 * t));
       }
       float z[2][4];
-      conv_mma_block<C>(my_so, wb_hi, wb_lo, cb, mb, lane, off0, off1, z);
-      float mean0, rstd0, mean1, rstd1;
-      ln16_quad(z, mean0, rstd0, mean1, rstd1);
+      float mean0 = 0.f, rstd0, mean1 = 0.f, rstd1;
+      if (XH1 != nullptr) {
+        // xhat / rstd saved by the training forward: no conv recompute
+        const float* __restrict__ xrow = XH1 + ((int64_t)seed * rows + row) * FLAT_CNN;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 a0 = __ldg(reinterpret_cast<const float2*>(xrow + p0 * CONV_O + 8 * h + 2 * t));
+          const float2 a1 = __ldg(reinterpret_cast<const float2*>(xrow + p1 * CONV_O + 8 * h + 2 * t));
+          z[h][0] = a0.x; z[h][1] = a0.y; z[h][2] = a1.x; z[h][3] = a1.y;
+        }
+        rstd0 = __ldg(RS1 + ((int64_t)seed * rows + row) * CONV_PIX + p0);
+        rstd1 = __ldg(RS1 + ((int64_t)seed * rows + row) * CONV_PIX + p1);
+      } else {
+        conv_mma_block<C>(my_so, wb_hi, wb_lo, cb, mb, lane, off0, off1, z);
+        ln16_quad(z, mean0, rstd0, mean1, rstd1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) z[h][j] = (z[h][j] - (j < 2 ? mean0 : mean1)) * (j < 2 ? rstd0 : rstd1);
+      }
       float dxh[2][4];
       float m1a = 0.f, m2a = 0.f, m1b = 0.f, m2b = 0.f;
 #pragma unroll
@@ -1156,9 +1184,7 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
         const float dy4[4] = {dyv[h][0].x, dyv[h][0].y, dyv[h][1].x, dyv[h][1].y};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float mean = j < 2 ? mean0 : mean1, rstd = j < 2 ? rstd0 : rstd1;
-          z[h][j] = (z[h][j] - mean) * rstd;  // xhat
-          const int col = 2 * h + (j & 1);    // index into the lane's 4 columns
+          const int col = 2 * h + (j & 1);    // index into the lane's 4 columns; z[h][j] holds xhat
           a_dsc[col] = fmaf(dy4[j], z[h][j], a_dsc[col]);
           a_dbi[col] += dy4[j];
           dxh[h][j] = dy4[j] * sc[o + (j & 1)];
@@ -1290,6 +1316,7 @@ struct Workspace {
   // CNN
   float *h1, *h2, *xhat2, *rstd2, *dz2;
   float *h1_lo, *dz2_lo, *w1_lo;  // 3xTF32 "lo" operands of the tcgen05 path
+  float *cxhat, *crstd;           // conv LayerNorm xhat / rstd saved by the training forward (MMA conv path)
   // MLP
   float *xg, *h0, *xhat0, *rstd0, *hh1, *xhat1, *rstd1, *dzl, *dh0;
 };
@@ -1313,6 +1340,8 @@ static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* bas
     ww->h1_lo = take(R * FLAT_CNN);
     ww->dz2_lo = take(R * HID_CNN);
     ww->w1_lo = take((int64_t)S * FLAT_CNN * HID_CNN);
+    ww->cxhat = take(R * FLAT_CNN);
+    ww->crstd = take(R * CONV_PIX);
   } else {
     const int H = d->hidden;
     ww->xg = take(R * d->in_c);
@@ -1351,15 +1380,15 @@ static unsigned conv_mma_ctas(int S, int rows) {
 template <bool TRAIN>
 static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
                            const float* params, int64_t P, const pqn_net_layout_t& L, float* h1, float* h1lo, float* bn,
-                           int rows) {
+                           int rows, float* xh1 = nullptr, float* rs1 = nullptr) {
   if (g_conv_mma) {
     const dim3 mg(conv_mma_ctas((int)grid.y, rows), grid.y);
     LaunchScope _ls(K_CONV_FWD, st);
     switch (C) {
-      case 4: conv_fwd_mma_kernel<4, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); break;
-      case 6: conv_fwd_mma_kernel<6, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); break;
-      case 7: conv_fwd_mma_kernel<7, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); break;
-      case 10: conv_fwd_mma_kernel<10, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); break;
+      case 4: conv_fwd_mma_kernel<4, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows); break;
+      case 6: conv_fwd_mma_kernel<6, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows); break;
+      case 7: conv_fwd_mma_kernel<7, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows); break;
+      case 10: conv_fwd_mma_kernel<10, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows); break;
       default: return -1;
     }
     return 0;
@@ -1561,7 +1590,8 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
     const uint32_t* ob = (const uint32_t*)obs;
     const bool use_tc = g_use_tc && A <= PQN_TC_MAX_A;
     launch_conv_fwd<true>(d->in_c, dim3(cdiv(rows, 4), S), st, ob, obs_rows_per_seed, gather, params, P, L, w.h1,
-                          use_tc ? w.h1_lo : nullptr, bn_sums, R);
+                          use_tc ? w.h1_lo : nullptr, bn_sums, R, g_conv_mma ? w.cxhat : nullptr,
+                          g_conv_mma ? w.crstd : nullptr);
     if (use_tc) {
       launch_split_w1(params, P, L.d0_w, w.w1_lo, S, st);
       if ((rc = tc_dense_fwd(tc::EPI_LN_TRAIN, params, P, L, w, A, nullptr, S, R, st))) return rc;
@@ -1590,10 +1620,10 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
       const dim3 mg(conv_mma_ctas(S, R), S);
       LaunchScope _ls(K_CONV_BWD, st);
       switch (d->in_c) {
-        case 4: conv_bwd_mma_kernel<4><<<mg, ConvMma<4>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
-        case 6: conv_bwd_mma_kernel<6><<<mg, ConvMma<6>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
-        case 7: conv_bwd_mma_kernel<7><<<mg, ConvMma<7>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
-        case 10: conv_bwd_mma_kernel<10><<<mg, ConvMma<10>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); break;
+        case 4: conv_bwd_mma_kernel<4><<<mg, ConvMma<4>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
+        case 6: conv_bwd_mma_kernel<6><<<mg, ConvMma<6>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
+        case 7: conv_bwd_mma_kernel<7><<<mg, ConvMma<7>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
+        case 10: conv_bwd_mma_kernel<10><<<mg, ConvMma<10>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
       }
     } else
     switch (d->in_c) {
