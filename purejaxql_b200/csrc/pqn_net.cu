@@ -31,7 +31,7 @@ constexpr int FLAT_CNN = CONV_PIX * CONV_O;  // 1024
 // tcgen05 path for the CNN dense layer (pqn_set_tensor_core_path); default on
 static int g_use_tc = 1;
 // warp-level tensor-core (mma.sync tf32) conv kernels (pqn_set_conv_mma_path); default on
-static int g_conv_mma = 1;
+static int g_conv_mma = 1;   // 0: fp32 CUDA cores, 1: mma.sync tf32, 2: tcgen05 forward (+ mma.sync backward)
 
 static inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
 
@@ -1292,6 +1292,254 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
   }
 }
 
+// ---------------------------------------------------------------------------
+// conv forward on tcgen05: per tile of 2 samples (128 output pixels) the 128 producer threads (thread = pixel)
+// write their im2col row ({0,1} floats, taps padded to a multiple of 32) straight into shared memory in the
+// K-major SWIZZLE_128B operand layout, one elected thread issues tcgen05.mma M=128 x N=16 x K=8 per 8 taps
+// against the (hi, lo)-split weights/255 held in shared memory, and the same 128 threads read their pixel's 16
+// channels back from TMEM for LayerNorm + ReLU and the stores.  A tiles and TMEM accumulators are double
+// buffered: tile i+1 is produced while tile i's MMAs run.
+// ---------------------------------------------------------------------------
+template <int C>
+struct ConvTc {
+  static constexpr int TAPS = 9 * C;
+  static constexpr int KB = (TAPS + 31) / 32;           // k-blocks of 32 taps (one 128-byte swizzle row each)
+  static constexpr int KS = (TAPS + 7) / 8;             // MMA k-steps
+  static constexpr int A_TILE = 128 * 128;              // bytes per k-block tile (128 rows x 128 B)
+  static constexpr int A_BUF = KB * A_TILE;
+  static constexpr int B_TILE = 16 * 128;               // 16 output channels x 128 B
+  static constexpr int OFF_A = 0;                       // 2 buffers
+  static constexpr int OFF_BHI = 2 * A_BUF;
+  static constexpr int OFF_BLO = OFF_BHI + KB * B_TILE;
+  static constexpr int OFF_MISC = OFF_BLO + KB * B_TILE;  // barriers, tmem slot, obs words, consts
+  static constexpr int SMEM = OFF_MISC + 1024 + 1024 /*align slack*/;
+};
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int C, bool TRAIN>
+__global__ void __launch_bounds__(160)
+    conv_fwd_tc_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
+                       const float* __restrict__ params, int64_t P, pqn_net_layout_t L, float* __restrict__ H1,
+                       float* __restrict__ H1LO, float* __restrict__ XH1, float* __restrict__ RS1,
+                       float* __restrict__ bn_sums, int rows, int tiles_per_seed, int ctas_per_seed) {
+  using Cfg = ConvCfg<C>;
+  using T = ConvTc<C>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (sbase - tc::smem_u32(smem_raw));
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sm + T::OFF_MISC);  // [2]
+  uint64_t* d_full = a_full + 2;                                      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 2);
+  float* cb = reinterpret_cast<float*>(sm + T::OFF_MISC + 64);       // [16] conv bias, LN scale, LN bias
+  float* sc = cb + CONV_O;
+  float* bi = sc + CONV_O;
+  float* s_cnt = bi + CONV_O;                                         // [C]
+  uint32_t* sobs = reinterpret_cast<uint32_t*>(sm + T::OFF_MISC + 320);  // [2 buf][2 samples][SW]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int seed = blockIdx.y;
+  const float* __restrict__ prm = params + (int64_t)seed * P;
+
+  // ---- one-time setup: weights (hi, lo) as K-major SW128 B tiles, constants, barriers, TMEM
+  {
+    const float inv255 = 1.0f / 255.0f;
+    for (int i = tid; i < T::KB * 16 * 32; i += blockDim.x) {
+      const int kb = i / (16 * 32), n = (i / 32) % 16, kk = i % 32;
+      const int tap = kb * 32 + kk;
+      const float w = tap < T::TAPS ? __ldg(prm + L.conv_w + tap * CONV_O + n) * inv255 : 0.f;
+      const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+      const int off = kb * T::B_TILE + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
+      *reinterpret_cast<float*>(sm + T::OFF_BHI + off) = hi;
+      *reinterpret_cast<float*>(sm + T::OFF_BLO + off) = w - hi;
+    }
+    if (tid < CONV_O) {
+      cb[tid] = __ldg(prm + L.conv_b + tid);
+      sc[tid] = __ldg(prm + L.ln0_scale + tid);
+      bi[tid] = __ldg(prm + L.ln0_bias + tid);
+    }
+    if (tid < C) s_cnt[tid] = 0.f;
+    if (tid == 128) {
+      for (int b = 0; b < 2; ++b) { tc::mbar_init(&a_full[b], 128); tc::mbar_init(&d_full[b], 1); }
+      tc::fence_barrier_init();
+    }
+    if (warp == 4) { tc::tmem_alloc(tmem_slot, 32); tc::tmem_relinquish(); }
+    fence_proxy_async_smem();
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+  }
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_iters = (tiles_per_seed - (int)blockIdx.x + ctas_per_seed - 1) / ctas_per_seed;  // tiles of this CTA
+
+  if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_tf32(128, 16, 0, 0);
+      for (int it = 0; it < n_iters; ++it) {
+        const int b = it & 1;
+        tc::mbar_wait(&a_full[b], (it >> 1) & 1);
+        tc::tcgen05_fence_after();
+        const uint32_t d = tmem_base + b * 16;
+        const uint32_t abase = sbase + T::OFF_A + b * T::A_BUF;
+#pragma unroll
+        for (int ks = 0; ks < T::KS; ++ks) {
+          const int kb = ks >> 2, kq = ks & 3;
+          const uint64_t da = tc::make_sdesc<0>(abase + kb * T::A_TILE, kq);
+          const uint64_t dlo = tc::make_sdesc<0>(sbase + T::OFF_BLO + kb * T::B_TILE, kq);
+          const uint64_t dhi = tc::make_sdesc<0>(sbase + T::OFF_BHI + kb * T::B_TILE, kq);
+          tc::umma_tf32(d, da, dlo, idesc, ks > 0 ? 1u : 0u);
+          tc::umma_tf32(d, da, dhi, idesc, 1u);
+        }
+        tc::umma_commit(&d_full[b]);
+      }
+    }
+  } else {
+    // ===================== producers / epilogue: thread = output pixel of the 2-sample tile =====================
+    const int sl = tid >> 6, pix = tid & 63, y = pix >> 3, x = pix & 7;
+    int cnt[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) cnt[c] = 0;
+
+    auto produce = [&](int it) {
+      const int b = it & 1;
+      const int tile = blockIdx.x + it * ctas_per_seed;
+      const int row = tile * 2 + sl;
+      uint32_t* so = sobs + (b * 2 + sl) * Cfg::SW;
+      if (pix < Cfg::SW) {
+        uint32_t w = 0u;
+        if (row < rows && pix < Cfg::PW) {
+          const int64_t src = gather ? gather[(int64_t)seed * rows + row] : row;
+          w = __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + pix);
+        }
+        so[pix] = w;
+      }
+      bar_sync_named(1, 128);
+      // im2col row of this pixel: taps (di,dj,c) -> {0,1}
+      float f[T::KB * 32];
+#pragma unroll
+      for (int k = 0; k < T::KB * 32; ++k) f[k] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const uint32_t nib = pixel_bits<C>(so, (y + r / 3) * 10 + x + r % 3);
+#pragma unroll
+        for (int c = 0; c < C; ++c) f[r * C + c] = ((nib >> c) & 1u) ? 1.0f : 0.0f;
+      }
+      uint8_t* arow = sm + T::OFF_A + b * T::A_BUF + tid * 128;
+#pragma unroll
+      for (int kb = 0; kb < T::KB; ++kb)
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16)
+          *reinterpret_cast<float4*>(arow + kb * T::A_TILE + ((c16 ^ (tid & 7)) << 4)) =
+              make_float4(f[kb * 32 + 4 * c16], f[kb * 32 + 4 * c16 + 1], f[kb * 32 + 4 * c16 + 2], f[kb * 32 + 4 * c16 + 3]);
+      if (TRAIN && bn_sums != nullptr && row < rows) {
+        const uint32_t b0 = pixel_bits<C>(so, pix);
+        const uint32_t b1 = (pix + 64 < 100) ? pixel_bits<C>(so, pix + 64) : 0u;
+#pragma unroll
+        for (int c = 0; c < C; ++c) cnt[c] += (int)((b0 >> c) & 1u) + (int)((b1 >> c) & 1u);
+      }
+      fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc::mbar_arrive(&a_full[b]);
+    };
+
+    auto epilogue = [&](int it) {
+      const int b = it & 1;
+      const int tile = blockIdx.x + it * ctas_per_seed;
+      const int row = tile * 2 + sl;
+      tc::mbar_wait(&d_full[b], (it >> 1) & 1);
+      tc::tcgen05_fence_after();
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_base + b * 16 + ((uint32_t)(warp * 32) << 16), v);
+      tc::tmem_ld_wait();
+      tc::tcgen05_fence_before();
+      float z[CONV_O];
+#pragma unroll
+      for (int o = 0; o < CONV_O; ++o) z[o] = __uint_as_float(v[o]) + cb[o];
+      float mean, rstd;
+      ln16(z, mean, rstd);
+      if (row < rows) {
+        const int64_t base = ((int64_t)seed * rows + row) * FLAT_CNN + pix * CONV_O;
+#pragma unroll
+        for (int o4 = 0; o4 < CONV_O / 4; ++o4) {
+          float xh[4], hv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            xh[j] = (z[4 * o4 + j] - mean) * rstd;
+            hv[j] = fmaxf(xh[j] * sc[4 * o4 + j] + bi[4 * o4 + j], 0.f);
+          }
+          *reinterpret_cast<float4*>(H1 + base + 4 * o4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          if (H1LO)
+            *reinterpret_cast<float4*>(H1LO + base + 4 * o4) =
+                make_float4(tc::tf32_lo(hv[0]), tc::tf32_lo(hv[1]), tc::tf32_lo(hv[2]), tc::tf32_lo(hv[3]));
+          if (TRAIN && XH1) *reinterpret_cast<float4*>(XH1 + base + 4 * o4) = make_float4(xh[0], xh[1], xh[2], xh[3]);
+        }
+        if (TRAIN && RS1) RS1[((int64_t)seed * rows + row) * CONV_PIX + pix] = rstd;
+      }
+    };
+
+    if (n_iters > 0) produce(0);
+    for (int it = 1; it < n_iters; ++it) {
+      produce(it);
+      epilogue(it - 1);
+    }
+    if (n_iters > 0) epilogue(n_iters - 1);
+
+    if (TRAIN && bn_sums != nullptr) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        int vsum = cnt[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+        if (lane == 0 && vsum) atomicAdd(&s_cnt[c], (float)vsum);
+      }
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (TRAIN && bn_sums != nullptr && tid < C && s_cnt[tid] != 0.f) {
+    atomicAdd(bn_sums + (int64_t)seed * 2 * C + tid, s_cnt[tid]);
+    atomicAdd(bn_sums + (int64_t)seed * 2 * C + C + tid, s_cnt[tid]);
+  }
+  if (warp == 4) {
+    tc::tcgen05_fence_after();
+    tc::tmem_dealloc(tmem_base, 32);
+  }
+}
+
+template <int C, bool TRAIN>
+static int launch_conv_fwd_tc_t(int S, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
+                                const float* params, int64_t P, const pqn_net_layout_t& L, float* h1, float* h1lo,
+                                float* xh1, float* rs1, float* bn, int rows) {
+  auto kfn = conv_fwd_tc_kernel<C, TRAIN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTc<C>::SMEM) != cudaSuccess)
+      return check_launch("conv_fwd_tc(cudaFuncSetAttribute)");
+    attr_set = true;
+  }
+  const int tiles = (rows + 1) / 2;
+  int per_seed = (148 * 3 + S - 1) / S;  // ~3 resident CTAs per SM over all seeds
+  if (per_seed > tiles) per_seed = tiles;
+  if (per_seed < 1) per_seed = 1;
+  {
+    LaunchScope _ls(K_CONV_FWD, st);
+    kfn<<<dim3(per_seed, S), 160, ConvTc<C>::SMEM, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows,
+                                                         tiles, per_seed);
+  }
+  return 0;
+}
+
 // MLP input gather (minibatch rows of float obs) + dummy BatchNorm sums.
 __global__ void gather_rows_kernel(const float* __restrict__ obs, int64_t obs_rows_per_seed,
                                    const int32_t* __restrict__ gather, float* __restrict__ out,
@@ -1381,6 +1629,16 @@ template <bool TRAIN>
 static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
                            const float* params, int64_t P, const pqn_net_layout_t& L, float* h1, float* h1lo, float* bn,
                            int rows, float* xh1 = nullptr, float* rs1 = nullptr) {
+  if (g_conv_mma == 2) {
+    const int S = (int)grid.y;
+    switch (C) {
+      case 4: return launch_conv_fwd_tc_t<4, TRAIN>(S, st, obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows);
+      case 6: return launch_conv_fwd_tc_t<6, TRAIN>(S, st, obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows);
+      case 7: return launch_conv_fwd_tc_t<7, TRAIN>(S, st, obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows);
+      case 10: return launch_conv_fwd_tc_t<10, TRAIN>(S, st, obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows);
+      default: return -1;
+    }
+  }
   if (g_conv_mma) {
     const dim3 mg(conv_mma_ctas((int)grid.y, rows), grid.y);
     LaunchScope _ls(K_CONV_FWD, st);
@@ -1496,7 +1754,7 @@ using namespace pqn;
 extern "C" {
 
 int pqn_set_conv_mma_path(int on) {
-  g_conv_mma = on ? 1 : 0;
+  g_conv_mma = on < 0 ? 0 : (on > 2 ? 2 : on);
   return PQN_OK;
 }
 

@@ -52,7 +52,8 @@ def _ws(spec, S, rows):
     return torch.empty(n, dtype=torch.uint8, device=dev())
 
 
-@pytest.fixture(params=[(1, 1), (0, 0), (1, 0)], ids=["tcgen05+mma_conv", "ffma", "tcgen05+cuda_conv"])
+@pytest.fixture(params=[(1, 1), (0, 0), (1, 0), (1, 2)],
+                ids=["tcgen05+mma_conv", "ffma", "tcgen05+cuda_conv", "tcgen05+tcgen05_conv"])
 def dense_path(request):
     """Runs the CNN tests on the implementation variants: dense layer on tcgen05 3xTF32 or fp32 FFMA,
     conv on warp-level tf32 MMA or fp32 CUDA cores."""
