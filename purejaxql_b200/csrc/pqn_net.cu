@@ -1412,19 +1412,24 @@ __global__ void __launch_bounds__(160)
 #pragma unroll
     for (int c = 0; c < C; ++c) cnt[c] = 0;
 
+    // observation word of this thread for tile `it` (issued one iteration ahead to hide the HBM latency)
+    auto fetch_word = [&](int it) -> uint32_t {
+      const int row = (blockIdx.x + it * ctas_per_seed) * 2 + sl;
+      if (it < n_iters && row < rows && pix < Cfg::PW) {
+        const int64_t src = gather ? gather[(int64_t)seed * rows + row] : row;
+        return __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + pix);
+      }
+      return 0u;
+    };
+    uint32_t w_next = fetch_word(0);
+
     auto produce = [&](int it) {
       const int b = it & 1;
       const int tile = blockIdx.x + it * ctas_per_seed;
       const int row = tile * 2 + sl;
       uint32_t* so = sobs + (b * 2 + sl) * Cfg::SW;
-      if (pix < Cfg::SW) {
-        uint32_t w = 0u;
-        if (row < rows && pix < Cfg::PW) {
-          const int64_t src = gather ? gather[(int64_t)seed * rows + row] : row;
-          w = __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + pix);
-        }
-        so[pix] = w;
-      }
+      if (pix < Cfg::SW) so[pix] = w_next;
+      w_next = fetch_word(it + 1);
       bar_sync_named(1, 128);
       // im2col row of this pixel: taps (di,dj,c) -> {0,1}
       float f[T::KB * 32];
@@ -1529,7 +1534,8 @@ static int launch_conv_fwd_tc_t(int S, cudaStream_t st, const uint32_t* obs, int
     attr_set = true;
   }
   const int tiles = (rows + 1) / 2;
-  int per_seed = (148 * 3 + S - 1) / S;  // ~3 resident CTAs per SM over all seeds
+  // all CTAs co-resident (3 per SM by shared memory): a second partial wave would double the time
+  int per_seed = (148 * 3) / S;
   if (per_seed > tiles) per_seed = tiles;
   if (per_seed < 1) per_seed = 1;
   {
