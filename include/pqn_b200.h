@@ -211,7 +211,8 @@ int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F
 int pqn_set_tensor_core_path(int on);
 /* The CNN's 3x3 conv (forward, recompute and weight gradient) runs on warp-level tf32 tensor-core MMA built
  * straight from the packed observation bits by default (1); 0 selects the fp32 CUDA-core kernels; 2 runs the
- * forward conv on tcgen05 (im2col rows written by the producer threads directly in the UMMA smem layout). */
+ * forward conv on tcgen05 (im2col rows written by the producer threads directly in the UMMA smem layout;
+ * correct, but measured slower than 1 because the per-pixel LayerNorm/store epilogue dominates: DESIGN.md). */
 int pqn_set_conv_mma_path(int on);
 
 /* ---- tcgen05 (5th-gen tensor core) path of the dense contractions ----------

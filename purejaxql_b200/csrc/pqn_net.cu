@@ -31,7 +31,7 @@ constexpr int FLAT_CNN = CONV_PIX * CONV_O;  // 1024
 // tcgen05 path for the CNN dense layer (pqn_set_tensor_core_path); default on
 static int g_use_tc = 1;
 // warp-level tensor-core (mma.sync tf32) conv kernels (pqn_set_conv_mma_path); default on
-static int g_conv_mma = 2;   // 0: fp32 CUDA cores, 1: mma.sync tf32, 2: tcgen05 forward (+ mma.sync backward)
+static int g_conv_mma = 1;   // 0: fp32 CUDA cores, 1: mma.sync tf32, 2: tcgen05 forward (+ mma.sync backward)
 
 static inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
 

@@ -62,7 +62,7 @@ def dense_path(request):
     _lib.lib().pqn_set_conv_mma_path(request.param[1])
     yield request.param
     _lib.lib().pqn_set_tensor_core_path(1)
-    _lib.lib().pqn_set_conv_mma_path(2)
+    _lib.lib().pqn_set_conv_mma_path(1)
 
 
 @pytest.mark.parametrize("rows", [1, 130, 515])
