@@ -93,9 +93,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """Start of the timed region: samples taken before this index belong to the warm-up."""
+        self.start_idx = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)                      # let the last 200 ms sample of the timed region land
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -103,7 +108,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[getattr(self, "start_idx", 0):]
+        window = "timed region"
+        if not rows:                          # timed region shorter than one sampling period: use the loaded
+            rows = self.rows[-3:]             # warm-up samples right before it
+            window = "last warm-up samples (timed region < 200 ms)"
+        self.window = window
+        for r in rows:
             if len(r) < 8:
                 continue
             try:
@@ -114,7 +125,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------- #
@@ -238,9 +249,10 @@ def run_gpu(args, rank, world, local_rank):
             L.pqn_profile_read((_lib.c_double * L.pqn_num_kernels())(), (_lib.c_longlong * L.pqn_num_kernels())(), 1)
             L.pqn_profile_enable(1)
             state["launch0"] = L.pqn_launch_count()
-            sampler.start()
+            sampler.mark()
             ev["start"].record(torch.cuda.current_stream(dev))
     eng.on_update_begin = on_update
+    sampler.start()                           # runs through the warm-up; mark() at the start of the timed region
     out = train(rngs_host)
     ev["end"].record(torch.cuda.current_stream(dev))
     barrier()
