@@ -114,3 +114,18 @@ def test_config_composition_matches_hydra_semantics():
     assert flat["TOTAL_TIMESTEPS"] // flat["NUM_STEPS"] // flat["NUM_ENVS"] == 76
     c2 = C.compose(["+alg=pqn_cartpole", "alg.ENV_NAME=Acrobot-v1"])
     assert c2["alg"]["ENV_NAME"] == "Acrobot-v1" and c2["alg"]["REW_SCALE"] == 0.1
+
+
+def test_library_sass_has_blackwell_tensor_and_tma_ops():
+    """The built .so must contain the sm_100a-native paths: tcgen05.mma (UTC*MMA), TMEM loads (LDTM),
+    TMA tensor loads (UTMALDG) and the warp-level tf32 MMA of the conv kernels."""
+    import shutil
+    import subprocess
+    from purejaxql_b200 import build
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    so = build.build()
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR", "HMMA"):
+        assert mnemonic in sass, f"{mnemonic} missing from the SASS of {so}"
