@@ -293,6 +293,16 @@ def run_gpu(args, rank, world, local_rank):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # dram__bytes_read+write per launch from the committed `ncu --set full` capture of the same workload
+    # (profiles/r1h_ncu_launch_table.md); keys = bench kernel ids
+    traffic_map = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1h_traffic.json")))
+        traffic_map = {"conv_bwd": tj.get("void conv_bwd_mma_kernel<4>"), "conv_fwd": tj.get("void conv_fwd_mma_kernel<4, 1>"),
+                       "tc_dense_fwd": tj.get("void tc_gemm_kernel<0, 1, 1>"), "tc_wgrad": tj.get("void tc_gemm_kernel<1, 1, 0>"),
+                       "tc_dgrad": tj.get("void tc_gemm_kernel<0, 0, 3>"), "row_bwd": tj.get("void row_bwd_kernel<128, 1>")}
+    except Exception:
+        pass
     total_k_ms = sum(v[0] for v in prof.values()) or 1.0
     breakdown = {k: {"ms": round(v[0], 3), "launches": v[1], "share": round(v[0] / total_k_ms, 4)}
                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
@@ -315,7 +325,9 @@ def run_gpu(args, rank, world, local_rank):
         hbm = peaks.get("hbm_gbs", 6650.0)
         gbs = ALG_BYTES.get(dom, 0) * samples / (d_ms / 1e3) / 1e9
         roof = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
-                "frac": round(achieved / peak, 4), "traffic": None,
+                "frac": round(achieved / peak, 4),
+                "traffic": traffic_map.get(dom) if (S == 128 and args.envs == NUM_ENVS) else None,
+                "traffic_source": "profiles/r1h_ncu_launch_table.md (ncu --set full, same workload, training-step launch)",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PF sustained (of fallback)",
                 "note": ("fp32-accurate 3xTF32 on tcgen05: each algorithmic FLOP costs 3 tf32 MMAs at half the bf16 "
                          "rate, so the fp32-equivalent tensor peak is peak/6 = %.0f TFLOP/s; the kernel also streams "
