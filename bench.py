@@ -308,7 +308,24 @@ def run_gpu(args, rank, world, local_rank):
                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
     roof = None
-    if dom in ALG_FLOPS:
+    if dom == "conv_fwd":
+        # the conv forward is a store-bound kernel: 64 B of packed obs in, h1 + h1_lo (+ xhat, rstd when training) out
+        d_ms, d_n = prof[dom]
+        mb = NUM_STEPS * args.envs // 32
+        n_roll = (NUM_STEPS + 1) * args.steps
+        n_mb = d_n - n_roll
+        nbytes = S * (n_roll * args.envs * (64 + 2 * 4096) + n_mb * mb * (64 + 3 * 4096 + 256))
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        gbs = nbytes / (d_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s",
+                "frac": round(gbs / hbm, 4),
+                "traffic": traffic_map.get(dom) if (S == 128 and args.envs == NUM_ENVS) else None,
+                "traffic_source": "profiles/r1h_ncu_launch_table.md (ncu --set full, training-variant launch: 6.52 GB written)",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
+                "note": "conv3x3+LayerNorm+ReLU on warp-level tf32 MMA from bit-packed obs; algorithmic bytes = 64 B in + "
+                        "8 KB out (rollout) or 12.5 KB out (training: + xhat, rstd) per sample",
+                "avg_launch_ms": round(d_ms / d_n, 4), "launches": d_n}
+    elif dom in ALG_FLOPS:
         per_launch_samples = {"dense_fwd": None}.get(dom)
         # samples per launch: minibatch launches process S*4096 samples (T*E/32), rollout forwards S*E
         d_ms, d_n = prof[dom]
