@@ -221,3 +221,22 @@ def test_other_minatar_first_update_matches_oracle(env_name):
     p2, *_ = R.update_step(env, "cnn", params, R.opt_init(params), bs, obs, st, rng, dict(cfg), 0, lr_fn)
     for p, *_ in eng.spec.entries:
         assert np.abs(leaf(ts.params, p) - p2["/".join(p)]).max() < 1e-5, p
+
+
+def test_wandb_offline_logging_path(tmp_path, monkeypatch):
+    """WANDB_MODE != disabled takes the per-update logging branch (pqn_minatar.py:353-365), incl. per-seed keys."""
+    pytest.importorskip("wandb")
+    import wandb
+    from purejaxql_b200 import config_loader, pqn_gymnax
+    monkeypatch.setenv("WANDB_DIR", str(tmp_path))
+    monkeypatch.setenv("WANDB_SILENT", "true")
+    c = config_loader.compose(["+alg=pqn_cartpole", "NUM_SEEDS=2", "SAVE_PATH=null", "WANDB_MODE=offline",
+                               "alg.TOTAL_TIMESTEPS=8192", "alg.TOTAL_TIMESTEPS_DECAY=8192", "alg.NUM_ENVS=16",
+                               "alg.TEST_NUM_ENVS=8", "alg.TEST_NUM_STEPS=20", "alg.WANDB_LOG_ALL_SEEDS=True",
+                               "PROJECT=pqn_b200_test"])
+    try:
+        out = pqn_gymnax.single_run(c)
+    finally:
+        wandb.finish()
+    assert out["metrics"]["td_loss"].shape == (2, 8)
+    assert any(p.name.startswith("offline-run") for p in (tmp_path / "wandb").iterdir())
