@@ -997,7 +997,7 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
     conv_fwd_mma_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
                         const float* __restrict__ params, int64_t P, pqn_net_layout_t L, float* __restrict__ H1,
                         float* __restrict__ H1LO, float* __restrict__ XH1, float* __restrict__ RS1,
-                        float* __restrict__ bn_sums, int rows) {
+                        uint32_t* __restrict__ RB, float* __restrict__ bn_sums, int rows) {
   using Cfg = ConvCfg<C>;
   using M = ConvMma<C>;
   __shared__ float2 wb_hi[M::KS * 2 * 32], wb_lo[M::KS * 2 * 32];
@@ -1032,12 +1032,16 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
     float* __restrict__ lrow = H1LO ? H1LO + ((int64_t)seed * rows + row) * FLAT_CNN : nullptr;
     float* __restrict__ xrow = (TRAIN && XH1) ? XH1 + ((int64_t)seed * rows + row) * FLAT_CNN : nullptr;
     float* __restrict__ rrow = (TRAIN && RS1) ? RS1 + ((int64_t)seed * rows + row) * CONV_PIX : nullptr;
+    // packed ReLU mask for the dense dgrad epilogue: bit (pixel * 16 + channel) = (h1 > 0), 16 bits per pixel
+    uint16_t* __restrict__ brow =
+        (TRAIN && RB) ? reinterpret_cast<uint16_t*>(RB + ((int64_t)seed * rows + row) * (FLAT_CNN / 32)) : nullptr;
 #pragma unroll 1
     for (int mb = 0; mb < 4; ++mb) {
       float z[2][4];
       conv_mma_block<C>(my_so, wb_hi, wb_lo, cb, mb, lane, off0, off1, z);
       float mean0, rstd0, mean1, rstd1;
       ln16_quad(z, mean0, rstd0, mean1, rstd1);
+      uint32_t rb0 = 0u, rb1 = 0u;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int o = 8 * h + 2 * t;
@@ -1049,6 +1053,10 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
         const int p0 = 16 * mb + g, p1 = p0 + 8;
         *reinterpret_cast<float2*>(hrow + p0 * CONV_O + o) = v0;
         *reinterpret_cast<float2*>(hrow + p1 * CONV_O + o) = v1;
+        if (TRAIN) {
+          rb0 |= ((v0.x > 0.f ? 1u : 0u) | (v0.y > 0.f ? 2u : 0u)) << o;
+          rb1 |= ((v1.x > 0.f ? 1u : 0u) | (v1.y > 0.f ? 2u : 0u)) << o;
+        }
         if (xrow) {  // saved for the backward pass (no conv recompute there)
           *reinterpret_cast<float2*>(xrow + p0 * CONV_O + o) =
               make_float2((z[h][0] - mean0) * rstd0, (z[h][1] - mean0) * rstd0);
@@ -1060,6 +1068,11 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
           *reinterpret_cast<float2*>(lrow + p0 * CONV_O + o) = make_float2(tc::tf32_lo(v0.x), tc::tf32_lo(v0.y));
           *reinterpret_cast<float2*>(lrow + p1 * CONV_O + o) = make_float2(tc::tf32_lo(v1.x), tc::tf32_lo(v1.y));
         }
+      }
+      if (TRAIN && brow) {
+        rb0 |= __shfl_xor_sync(0xffffffffu, rb0, 1); rb1 |= __shfl_xor_sync(0xffffffffu, rb1, 1);
+        rb0 |= __shfl_xor_sync(0xffffffffu, rb0, 2); rb1 |= __shfl_xor_sync(0xffffffffu, rb1, 2);
+        if (t == 0) { brow[16 * mb + g] = (uint16_t)rb0; brow[16 * mb + g + 8] = (uint16_t)rb1; }
       }
     }
     if (TRAIN && bn_sums != nullptr) {
@@ -1571,6 +1584,7 @@ struct Workspace {
   float *h1, *h2, *xhat2, *rstd2, *dz2;
   float *h1_lo, *dz2_lo, *w1_lo;  // 3xTF32 "lo" operands of the tcgen05 path
   float *cxhat, *crstd;           // conv LayerNorm xhat / rstd saved by the training forward (MMA conv path)
+  uint32_t* relu_bits;            // packed (h1 > 0) mask, 1024 bits per row (MMA conv path -> tcgen05 dgrad epilogue)
   // MLP
   float *xg, *h0, *xhat0, *rstd0, *hh1, *xhat1, *rstd1, *dzl, *dh0;
 };
@@ -1596,6 +1610,7 @@ static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* bas
     ww->w1_lo = take((int64_t)S * FLAT_CNN * HID_CNN);
     ww->cxhat = take(R * FLAT_CNN);
     ww->crstd = take(R * CONV_PIX);
+    ww->relu_bits = reinterpret_cast<uint32_t*>(take(R * (FLAT_CNN / 32)));
   } else {
     const int H = d->hidden;
     ww->xg = take(R * d->in_c);
@@ -1634,7 +1649,7 @@ static unsigned conv_mma_ctas(int S, int rows) {
 template <bool TRAIN>
 static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
                            const float* params, int64_t P, const pqn_net_layout_t& L, float* h1, float* h1lo, float* bn,
-                           int rows, float* xh1 = nullptr, float* rs1 = nullptr) {
+                           int rows, float* xh1 = nullptr, float* rs1 = nullptr, uint32_t* rb = nullptr) {
   if (g_conv_mma == 2) {
     const int S = (int)grid.y;
     switch (C) {
@@ -1649,10 +1664,10 @@ static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* ob
     const dim3 mg(conv_mma_ctas((int)grid.y, rows), grid.y);
     LaunchScope _ls(K_CONV_FWD, st);
     switch (C) {
-      case 4: conv_fwd_mma_kernel<4, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows); break;
-      case 6: conv_fwd_mma_kernel<6, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows); break;
-      case 7: conv_fwd_mma_kernel<7, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows); break;
-      case 10: conv_fwd_mma_kernel<10, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows); break;
+      case 4: conv_fwd_mma_kernel<4, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
+      case 6: conv_fwd_mma_kernel<6, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
+      case 7: conv_fwd_mma_kernel<7, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
+      case 10: conv_fwd_mma_kernel<10, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
       default: return -1;
     }
     return 0;
@@ -1738,7 +1753,7 @@ static int tc_wgrad(float* grads, int64_t P, const pqn_net_layout_t& L, const Wo
 
 // dY1 = relu_mask(H1) * (dZ2 . W1^T), written in place over H1
 static int tc_dgrad(const float* params, int64_t P, const pqn_net_layout_t& L, const Workspace& w, int S, int rows,
-                    cudaStream_t st) {
+                    bool have_bits, cudaStream_t st) {
   CUtensorMap t[4];
   int rc;
   if ((rc = tc::make_tmap(&t[0], w.dz2, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 128, 0))) return rc;
@@ -1750,7 +1765,9 @@ static int tc_dgrad(const float* params, int64_t P, const pqn_net_layout_t& L, c
   gs.split3 = 1;
   tc::EpiParams ep = {};
   ep.out = w.h1; ep.mask = w.h1; ep.ld_out = FLAT_CNN; ep.out_seed_stride = (int64_t)rows * FLAT_CNN;
-  return tc::launch_gemm(0, 0, tc::EPI_RELU_MASK, t, gs, ep, st, K_TC_DGRAD);
+  ep.relu_bits = w.relu_bits; ep.rows = rows;
+  // the packed mask (16 B per row and tile) replaces re-reading the 2 GB of activations it was derived from
+  return tc::launch_gemm(0, 0, have_bits ? tc::EPI_RELU_BITS : tc::EPI_RELU_MASK, t, gs, ep, st, K_TC_DGRAD);
 }
 
 }  // namespace pqn
@@ -1855,7 +1872,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
     const bool use_tc = g_use_tc && A <= PQN_TC_MAX_A;
     launch_conv_fwd<true>(d->in_c, dim3(cdiv(rows, 4), S), st, ob, obs_rows_per_seed, gather, params, P, L, w.h1,
                           use_tc ? w.h1_lo : nullptr, bn_sums, R, g_conv_mma ? w.cxhat : nullptr,
-                          g_conv_mma ? w.crstd : nullptr);
+                          g_conv_mma ? w.crstd : nullptr, g_conv_mma == 1 ? w.relu_bits : nullptr);
     if (use_tc) {
       launch_split_w1(params, P, L.d0_w, w.w1_lo, S, st);
       if ((rc = tc_dense_fwd(tc::EPI_LN_TRAIN, params, P, L, w, A, nullptr, S, R, st))) return rc;
@@ -1869,7 +1886,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
         L.head_w, L.head_b, A, gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, R); }
     if (use_tc) {
       if ((rc = tc_wgrad(grads, P, L, w, S, R, st))) return rc;
-      if ((rc = tc_dgrad(params, P, L, w, S, R, st))) return rc;
+      if ((rc = tc_dgrad(params, P, L, w, S, R, g_conv_mma == 1, st))) return rc;
     } else {
       const int splits = wgrad_splits(FLAT_CNN / 128, S, R);
       { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(FLAT_CNN / 128, 1, S * splits), GT, 0, st>>>(w.h1, rows * FLAT_CNN, FLAT_CNN, w.dz2,

@@ -93,14 +93,18 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[1
                                              int m_base, int n0, int M, const uint32_t (&mask_bits)[4]) {
   const int m = m_base + lane;
   const bool row_ok = m < M;
-  if constexpr (EPI == EPI_STORE || EPI == EPI_RELU_MASK) {
+  if constexpr (EPI == EPI_STORE || EPI == EPI_RELU_MASK || EPI == EPI_RELU_BITS) {
     // no __restrict__: dgrad runs in place (out == mask)
     float* out = ep.out + (int64_t)seed * ep.out_seed_stride + (int64_t)m_base * ep.ld_out + n0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
+      for (int j = 0; j < 32; ++j) {
+        v[j] = acc[c * 32 + j];
+        // EPI_RELU_BITS: mask_bits = this lane's own row, one word per 32-column chunk
+        if (EPI == EPI_RELU_BITS) v[j] = ((mask_bits[c] >> j) & 1u) ? v[j] : 0.f;
+      }
       store_chunk_coalesced<EPI == EPI_RELU_MASK>(stage, v, lane, out + c * 32, mask_bits[c], ep.ld_out, m_base, M);
     }
   } else {
@@ -325,6 +329,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int m0 = (rem / gs.n_tiles) * 128, n0 = (rem % gs.n_tiles) * 128;
       uint32_t mask_bits[4] = {0u, 0u, 0u, 0u};
       if constexpr (EPI == EPI_RELU_MASK) prefetch_mask_bits(ep, seed, m0 + quad * 32, n0, lane, gs.M, mask_bits);
+      if constexpr (EPI == EPI_RELU_BITS) {
+        // packed ReLU mask written by the conv forward: 16 bytes per (row, 128-column tile)
+        const int m = m0 + quad * 32 + lane;
+        if (m < gs.M) {
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(
+              ep.relu_bits + ((int64_t)seed * ep.rows + m) * (ep.ld_out >> 5) + (n0 >> 5)));
+          mask_bits[0] = b.x; mask_bits[1] = b.y; mask_bits[2] = b.z; mask_bits[3] = b.w;
+        }
+      }
       float acc[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) acc[j] = 0.f;
@@ -433,6 +446,7 @@ int launch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap* t, const GemmSha
   PQN_TC_CASE(1, 1, EPI_STORE)
   PQN_TC_CASE(0, 0, EPI_STORE)
   PQN_TC_CASE(0, 0, EPI_RELU_MASK)
+  PQN_TC_CASE(0, 0, EPI_RELU_BITS)
 #undef PQN_TC_CASE
   return set_error(PQN_E_UNSUPPORTED, "tc_gemm: combination a_mn=%d b_mn=%d epi=%d not instantiated", a_mn, b_mn, epi);
 }

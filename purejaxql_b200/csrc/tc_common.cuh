@@ -17,7 +17,7 @@ constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ 
                               4 * 32 * 36 * 4 /*epilogue store staging, 4 warps x [32][36] floats*/;
 #define PQN_TC_MAX_A 8
 
-enum Epilogue : int { EPI_STORE = 0, EPI_LN_TRAIN = 1, EPI_LN_HEAD = 2, EPI_RELU_MASK = 3 };
+enum Epilogue : int { EPI_STORE = 0, EPI_LN_TRAIN = 1, EPI_LN_HEAD = 2, EPI_RELU_MASK = 3, EPI_RELU_BITS = 4 };
 
 struct GemmShape {
   int S;         // batch (seeds)
@@ -30,6 +30,7 @@ struct EpiParams {
   // EPI_STORE / EPI_RELU_MASK
   float* out;
   const float* mask;
+  const uint32_t* relu_bits;  // EPI_RELU_BITS: [S][rows][ld_out / 32] words, bit c of a row = (activation c > 0)
   int64_t ld_out, out_seed_stride;
   // EPI_LN_*
   const float* params;
