@@ -206,8 +206,9 @@ int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu,
 int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F, float count, float momentum,
                         void* stream);
 
-/* The CNN's dense layer (forward, wgrad, dgrad) runs on the tcgen05 3xTF32 path by default; 0 selects the
- * fp32 FFMA kernels instead (kept as the A/B reference for parity tests). */
+/* The CNN's dense layer (forward, wgrad, dgrad) runs on the tcgen05 3xTF32 path: 2 (default) derives the "lo"
+ * half of the activation operand inside the GEMM kernel, 1 reads it from a tensor the conv forward wrote,
+ * 0 selects the fp32 FFMA kernels instead (kept as the A/B reference for parity tests). */
 int pqn_set_tensor_core_path(int on);
 /* The CNN's 3x3 conv (forward, recompute and weight gradient) runs on warp-level tf32 tensor-core MMA built
  * straight from the packed observation bits by default (1); 0 selects the fp32 CUDA-core kernels; 2 runs the

@@ -29,7 +29,7 @@ constexpr int HID_CNN = 128;
 constexpr int FLAT_CNN = CONV_PIX * CONV_O;  // 1024
 
 // tcgen05 path for the CNN dense layer (pqn_set_tensor_core_path); default on
-static int g_use_tc = 1;
+static int g_use_tc = 2;  // 0 FFMA, 1 tcgen05 with A_lo tensors in memory, 2 tcgen05 with in-kernel A_lo (default)
 // warp-level tensor-core (mma.sync tf32) conv kernels (pqn_set_conv_mma_path); default on
 static int g_conv_mma = 1;   // 0: fp32 CUDA cores, 1: mma.sync tf32, 2: tcgen05 forward (+ mma.sync backward)
 
@@ -1725,8 +1725,9 @@ static int tc_dense_fwd(int epi, const float* params, int64_t P, const pqn_net_l
   if ((rc = tc::make_tmap(&t[1], w.h1_lo, FLAT_CNN, rows, S, FLAT_CNN, (uint64_t)rows * FLAT_CNN, 128, 0))) return rc;
   if ((rc = tc::make_tmap(&t[2], params + L.d0_w, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)P, 32, 1))) return rc;
   if ((rc = tc::make_tmap(&t[3], w.w1_lo, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)FLAT_CNN * HID_CNN, 32, 1))) return rc;
-  tc::GemmShape gs;
+  tc::GemmShape gs = {};
   gs.S = S; gs.M = rows; gs.m_tiles = (rows + 127) / 128; gs.n_tiles = 1; gs.k_blocks = FLAT_CNN / tc::TC_BK; gs.split3 = 1;
+  gs.a_lo_inline = g_use_tc == 2;
   tc::EpiParams ep = {};
   ep.params = params; ep.P = P; ep.off_b = L.d0_b; ep.off_scale = L.ln1_scale; ep.off_bias = L.ln1_bias;
   ep.off_hw = L.head_w; ep.off_hb = L.head_b; ep.A = A; ep.rows = rows;
@@ -1743,9 +1744,10 @@ static int tc_wgrad(float* grads, int64_t P, const pqn_net_layout_t& L, const Wo
   if ((rc = tc::make_tmap(&t[1], w.h1_lo, FLAT_CNN, rows, S, FLAT_CNN, (uint64_t)rows * FLAT_CNN, 32, 1))) return rc;
   if ((rc = tc::make_tmap(&t[2], w.dz2, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 32, 1))) return rc;
   if ((rc = tc::make_tmap(&t[3], w.dz2_lo, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 32, 1))) return rc;
-  tc::GemmShape gs;
+  tc::GemmShape gs = {};
   gs.S = S; gs.M = FLAT_CNN; gs.m_tiles = FLAT_CNN / 128; gs.n_tiles = 1; gs.k_blocks = (rows + tc::TC_BK - 1) / tc::TC_BK;
   gs.split3 = 1;
+  gs.a_lo_inline = g_use_tc == 2;
   tc::EpiParams ep = {};
   ep.out = grads + L.d0_w; ep.ld_out = HID_CNN; ep.out_seed_stride = P;
   return tc::launch_gemm(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD);
@@ -1760,7 +1762,7 @@ static int tc_dgrad(const float* params, int64_t P, const pqn_net_layout_t& L, c
   if ((rc = tc::make_tmap(&t[1], w.dz2_lo, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 128, 0))) return rc;
   if ((rc = tc::make_tmap(&t[2], params + L.d0_w, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)P, 128, 0))) return rc;
   if ((rc = tc::make_tmap(&t[3], w.w1_lo, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)FLAT_CNN * HID_CNN, 128, 0))) return rc;
-  tc::GemmShape gs;
+  tc::GemmShape gs = {};
   gs.S = S; gs.M = rows; gs.m_tiles = (rows + 127) / 128; gs.n_tiles = FLAT_CNN / 128; gs.k_blocks = HID_CNN / tc::TC_BK;
   gs.split3 = 1;
   tc::EpiParams ep = {};
@@ -1782,7 +1784,7 @@ int pqn_set_conv_mma_path(int on) {
 }
 
 int pqn_set_tensor_core_path(int on) {
-  g_use_tc = on ? 1 : 0;
+  g_use_tc = on < 0 ? 0 : (on > 2 ? 2 : on);
   return PQN_OK;
 }
 
@@ -1814,7 +1816,7 @@ int pqn_qnet_forward(const pqn_net_desc_t* d, const float* params, const void* o
   if (d->kind == PQN_NET_MINATAR_CNN) {
     const bool use_tc = g_use_tc && A <= PQN_TC_MAX_A;
     launch_conv_fwd<false>(d->in_c, dim3(cdiv(rows, 4), S), st, (const uint32_t*)obs, obs_rows_per_seed, gather, params,
-                           L.total, L, w.h1, use_tc ? w.h1_lo : nullptr, nullptr, (int)rows);
+                           L.total, L, w.h1, (use_tc && g_use_tc == 1) ? w.h1_lo : nullptr, nullptr, (int)rows);
     if (use_tc) {
       launch_split_w1(params, L.total, L.d0_w, w.w1_lo, S, st);
       if ((rc = tc_dense_fwd(tc::EPI_LN_HEAD, params, L.total, L, w, A, q, S, (int)rows, st))) return rc;
@@ -1871,7 +1873,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
     const uint32_t* ob = (const uint32_t*)obs;
     const bool use_tc = g_use_tc && A <= PQN_TC_MAX_A;
     launch_conv_fwd<true>(d->in_c, dim3(cdiv(rows, 4), S), st, ob, obs_rows_per_seed, gather, params, P, L, w.h1,
-                          use_tc ? w.h1_lo : nullptr, bn_sums, R, g_conv_mma ? w.cxhat : nullptr,
+                          (use_tc && g_use_tc == 1) ? w.h1_lo : nullptr, bn_sums, R, g_conv_mma ? w.cxhat : nullptr,
                           g_conv_mma ? w.crstd : nullptr, g_conv_mma == 1 ? w.relu_bits : nullptr);
     if (use_tc) {
       launch_split_w1(params, P, L.d0_w, w.w1_lo, S, st);

@@ -14,7 +14,10 @@
 //   warp 0   TMA producer   cp.async.bulk.tensor (SWIZZLE_128B boxes) -> smem ring
 //   warp 1   MMA issuer     tcgen05.mma.cta_group::1.kind::tf32 (one thread), TMEM accumulators
 //   warps 2-5 epilogue      tcgen05.ld 32x32b -> registers -> fused epilogue -> global
-// Barriers: full[stage]/empty[stage] (TMA <-> MMA), tmem_full/tmem_empty[2] (MMA <-> epilogue).
+//   warps 6-7 converters    (a_lo_inline) A_lo tile = A tile - trunc_tf32(A tile), smem -> smem, so that the
+//                           big activation operand is read from HBM once instead of as a (hi, lo) pair
+// Barriers: full[stage]/empty[stage] (TMA <-> MMA), lo_full[stage] (converters -> MMA),
+//           main_full/main_empty[2], corr_full/corr_empty[2] (MMA <-> epilogue).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -197,17 +200,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint64_t* main_empty = main_full + 2;         // [2]           epilogue -> MMA
   uint64_t* corr_full = main_empty + 2;         // [2]
   uint64_t* corr_empty = corr_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_empty + 2);
+  uint64_t* lo_full = corr_empty + 2;           // [TC_STAGES]   converters -> MMA (A_lo tile written)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + TC_STAGES);
   float* stage_all = reinterpret_cast<float*>(smem_al + TC_STAGES * TC_STAGE_BYTES + 256);  // 4 x [32][STG_LD]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_b_hi);
-    if (gs.split3) { prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_b_lo); }
+    if (gs.split3) { if (!gs.a_lo_inline) prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_b_lo); }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&lo_full[i], TC_CONV_THREADS);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&main_full[i], 1); mbar_init(&main_empty[i], 4);
       mbar_init(&corr_full[i], 1); mbar_init(&corr_empty[i], 4);
@@ -226,6 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int tiles_per_seed = gs.m_tiles * gs.n_tiles;
   const int num_tiles = tiles_per_seed * gs.S;
 
+  const bool a_lo_tma = gs.split3 && !gs.a_lo_inline;
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -238,17 +245,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int kb = 0; kb < gs.k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
-          mbar_expect_tx(&full[stage], gs.split3 ? TC_STAGE_BYTES : TC_STAGE_BYTES / 2);
+          mbar_expect_tx(&full[stage], gs.split3 ? (a_lo_tma ? TC_STAGE_BYTES : 3 * TC_TILE_BYTES) : TC_STAGE_BYTES / 2);
           const int k0 = kb * TC_BK;
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               tma_load_3d(sb + TC_A_HI + j * 4096, &tm_a_hi, &full[stage], m0 + 32 * j, k0, seed);
-              if (gs.split3) tma_load_3d(sb + TC_A_LO + j * 4096, &tm_a_lo, &full[stage], m0 + 32 * j, k0, seed);
+              if (a_lo_tma) tma_load_3d(sb + TC_A_LO + j * 4096, &tm_a_lo, &full[stage], m0 + 32 * j, k0, seed);
             }
           } else {
             tma_load_3d(sb + TC_A_HI, &tm_a_hi, &full[stage], k0, m0, seed);
-            if (gs.split3) tma_load_3d(sb + TC_A_LO, &tm_a_lo, &full[stage], k0, m0, seed);
+            if (a_lo_tma) tma_load_3d(sb + TC_A_LO, &tm_a_lo, &full[stage], k0, m0, seed);
           }
           if (B_MN) {
 #pragma unroll
@@ -287,6 +294,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           const uint32_t d_main = tmem_base + mb * 128;
           mbar_wait(&full[stage], phase);
+          if (gs.a_lo_inline) mbar_wait(&lo_full[stage], phase);
           tcgen05_fence_after();
           const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
 #pragma unroll
@@ -313,6 +321,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (gs.split3) {
           umma_commit(&corr_full[cb]);
           if (++cb == 2) { cb = 0; cb_phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== converter warps (6..7) =====================
+    // The split is elementwise, so it is independent of the (swizzled) tile layout: byte i of the A_hi tile maps
+    // to byte i of the A_lo tile.  TMA zero-fills out-of-range rows, whose lo is 0 as well.
+    if (gs.split3 && gs.a_lo_inline) {
+      const int ct = threadIdx.x - 6 * 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < gs.k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          const float4* src = reinterpret_cast<const float4*>(smem_al + stage * TC_STAGE_BYTES + TC_A_HI);
+          float4* dst = reinterpret_cast<float4*>(smem_al + stage * TC_STAGE_BYTES + TC_A_LO);
+          constexpr int PER = TC_TILE_BYTES / 16 / TC_CONV_THREADS;  // 16 float4 per thread
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float4 v[PER / 2];
+#pragma unroll
+            for (int i = 0; i < PER / 2; ++i) v[i] = src[(half * (PER / 2) + i) * TC_CONV_THREADS + ct];
+#pragma unroll
+            for (int i = 0; i < PER / 2; ++i)
+              dst[(half * (PER / 2) + i) * TC_CONV_THREADS + ct] =
+                  make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&lo_full[stage]);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -577,15 +615,16 @@ int pqn_tc_debug(const float* a, const float* b, float* dump_a, float* dump_b, f
 // Test hook: D[s] = A[s] . B[s] on the tcgen05 path (fp32 in, fp32 out).
 //   a_mn = 0: A is [S][M][K] (K contiguous)   a_mn = 1: A is [S][K][M] (M contiguous)
 //   b_mn = 0: B is [S][N][K] (K contiguous)   b_mn = 1: B is [S][K][N] (N contiguous)
-//   split3 != 0: 3xTF32 (a_lo / b_lo must hold x - trunc_tf32(x)); else single-pass TF32.
+//   split3 = 1: 3xTF32 (a_lo / b_lo must hold x - trunc_tf32(x)); 2: same, but A_lo is derived in the kernel
+//   (a_lo unused); 0: single-pass TF32.
 // M, N multiples of 128 are not required for M (rows are guarded); N % 128 == 0, K % 32 == 0 or zero-filled.
 int pqn_tc_gemm_test(const float* a, const float* a_lo, const float* b, const float* b_lo, float* d, int32_t S,
                      int32_t M, int32_t N, int32_t K, int a_mn, int b_mn, int split3, void* stream) {
-  if (!a || !b || !d || S <= 0 || M <= 0 || N <= 0 || K <= 0 || (N % 128) || (split3 && (!a_lo || !b_lo)))
+  if (!a || !b || !d || S <= 0 || M <= 0 || N <= 0 || K <= 0 || (N % 128) || (split3 && !b_lo) || (split3 == 1 && !a_lo))
     return set_error(PQN_E_INVALID, "pqn_tc_gemm_test: bad argument");
   CUtensorMap t[4];
   int rc;
-  const float* al = split3 ? a_lo : a;
+  const float* al = split3 == 1 ? a_lo : a;
   const float* bl = split3 ? b_lo : b;
   if (a_mn) {
     if ((rc = make_tmap(&t[0], a, M, K, S, M, (uint64_t)M * K, 32, 1))) return rc;
@@ -601,9 +640,10 @@ int pqn_tc_gemm_test(const float* a, const float* a_lo, const float* b, const fl
     if ((rc = make_tmap(&t[2], b, K, N, S, K, (uint64_t)N * K, 128, 0))) return rc;
     if ((rc = make_tmap(&t[3], bl, K, N, S, K, (uint64_t)N * K, 128, 0))) return rc;
   }
-  GemmShape gs;
+  GemmShape gs = {};
   gs.S = S; gs.M = M; gs.m_tiles = (M + 127) / 128; gs.n_tiles = N / 128; gs.k_blocks = (K + TC_BK - 1) / TC_BK;
   gs.split3 = split3 ? 1 : 0;
+  gs.a_lo_inline = split3 == 2;
   EpiParams ep = {};
   ep.out = d; ep.ld_out = N; ep.out_seed_stride = (int64_t)M * N;
   return launch_gemm(a_mn, b_mn, EPI_STORE, t, gs, ep, (cudaStream_t)stream);

@@ -6,7 +6,9 @@
 namespace pqn {
 namespace tc {
 
-constexpr int TC_THREADS = 192;          // warp0 TMA, warp1 MMA, warps 2-5 epilogue (warp2 also owns TMEM alloc)
+constexpr int TC_THREADS = 256;          // warp0 TMA, warp1 MMA, warps 2-5 epilogue (warp2 also owns TMEM alloc),
+                                         // warps 6-7 operand converters (in-kernel A_lo, see GemmShape::a_lo_inline)
+constexpr int TC_CONV_THREADS = 64;
 constexpr int TC_BK = 32;                // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int TC_STAGES = 3;
 constexpr int TC_PROMOTE = 4;             // k-blocks (of 32) per in-TMEM main chain before promotion to registers
@@ -24,6 +26,8 @@ struct GemmShape {
   int M;         // rows of D that exist (rows >= M are not stored)
   int m_tiles, n_tiles, k_blocks;
   int split3;    // 1: 3xTF32, 0: single TF32 pass
+  int a_lo_inline;  // split3 only: 1 = no A_lo tensor in memory; the converter warps derive A_lo = A - trunc_tf32(A)
+                    // from the A tile TMA staged in shared memory (halves the HBM traffic of the A operand)
 };
 
 struct EpiParams {
@@ -70,6 +74,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads, TMA)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {

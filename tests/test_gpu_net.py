@@ -52,8 +52,9 @@ def _ws(spec, S, rows):
     return torch.empty(n, dtype=torch.uint8, device=dev())
 
 
-@pytest.fixture(params=[(1, 1), (0, 0), (1, 0), (1, 2)],
-                ids=["tcgen05+mma_conv", "ffma", "tcgen05+cuda_conv", "tcgen05+tcgen05_conv"])
+@pytest.fixture(params=[(2, 1), (1, 1), (0, 0), (1, 0), (2, 2)],
+                ids=["tcgen05_inline_lo+mma_conv", "tcgen05+mma_conv", "ffma", "tcgen05+cuda_conv",
+                     "tcgen05_inline_lo+tcgen05_conv"])
 def dense_path(request):
     """Runs the CNN tests on the implementation variants: dense layer on tcgen05 3xTF32 or fp32 FFMA,
     conv on warp-level tf32 MMA or fp32 CUDA cores."""
@@ -61,7 +62,7 @@ def dense_path(request):
     _lib.lib().pqn_set_tensor_core_path(request.param[0])
     _lib.lib().pqn_set_conv_mma_path(request.param[1])
     yield request.param
-    _lib.lib().pqn_set_tensor_core_path(1)
+    _lib.lib().pqn_set_tensor_core_path(2)
     _lib.lib().pqn_set_conv_mma_path(1)
 
 

@@ -43,6 +43,18 @@ def test_tc_gemm_single_pass_tf32(a_mn, b_mn):
 
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 1), (1, 1), (0, 0)])
 @pytest.mark.parametrize("S,M,N,K", [(1, 128, 128, 32), (3, 200, 128, 1024), (2, 1024, 256, 4096)])
+def test_tc_gemm_inline_a_lo_is_bitwise_the_same(a_mn, b_mn, S, M, N, K):
+    """split3=2 derives A_lo inside the kernel (converter warps, smem -> smem) instead of reading it from memory:
+    same operands, same MMA order, so the result must be identical to the precomputed-lo run."""
+    d1, ref, *_ = _run(S, M, N, K, a_mn, b_mn, 1, seed=K)
+    d2, *_ = _run(S, M, N, K, a_mn, b_mn, 2, seed=K)
+    assert np.isfinite(d2).all()
+    assert np.array_equal(d1, d2)
+    assert np.abs(d2 - ref).max() < 4e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 1), (1, 1), (0, 0)])
+@pytest.mark.parametrize("S,M,N,K", [(1, 128, 128, 32), (3, 200, 128, 1024), (2, 1024, 256, 4096)])
 def test_tc_gemm_3xtf32_fp32_accuracy(a_mn, b_mn, S, M, N, K):
     d, ref, A, B, alo = _run(S, M, N, K, a_mn, b_mn, 1, seed=K)
     assert np.isfinite(d).all()
