@@ -915,6 +915,44 @@ __device__ __forceinline__ uint32_t obs_bit_f32(const uint32_t* __restrict__ so,
   return (valid && bit) ? 0x3F800000u : 0u;  // 1.0f / 0.0f as tf32 bit patterns
 }
 
+// im2col "patch" of one output pixel as bits: bit k = tap k = (di*3+dj)*C + c, i.e. obs bit
+// ((y+di)*10 + x+dj)*C + c.  9C <= 90 bits -> PatchCfg::WORDS words; bits beyond 9C are zero.  Built once per
+// sample into shared memory (patch[pixel][word]); the MMA fragment builders then test bits with a shift instead of
+// re-deriving the observation bit address for every (pixel, tap) pair.
+template <int C>
+struct PatchCfg {
+  static constexpr int WORDS = (9 * C + 31) / 32;
+};
+
+template <int C>
+__device__ __forceinline__ void build_patch(const uint32_t* __restrict__ so, int pix, uint32_t* __restrict__ out) {
+  constexpr int W = PatchCfg<C>::WORDS;
+  uint32_t w[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) w[k] = 0u;
+  const int y = pix >> 3, x = pix & 7;
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const uint32_t nib = pixel_bits<C>(so, (y + r / 3) * 10 + x + r % 3);
+    const int o = r * C;  // compile-time after unrolling
+    w[o >> 5] |= nib << (o & 31);
+    if ((o & 31) + C > 32) w[min((o >> 5) + 1, W - 1)] |= nib >> (32 - (o & 31));
+  }
+#pragma unroll
+  for (int k = 0; k < W; ++k) out[k] = w[k];
+}
+
+// both output pixels of a lane (pix = lane, lane + 32) -> patch[64][WORDS]
+template <int C>
+__device__ __forceinline__ void build_patches(const uint32_t* __restrict__ so, uint32_t* __restrict__ patch, int lane) {
+  build_patch<C>(so, lane, patch + lane * PatchCfg<C>::WORDS);
+  build_patch<C>(so, lane + 32, patch + (lane + 32) * PatchCfg<C>::WORDS);
+}
+
+__device__ __forceinline__ uint32_t bit_f32(uint32_t word, int shift) {
+  return ((word >> shift) & 1u) ? 0x3F800000u : 0u;
+}
+
 // B fragments of the conv weights (scaled by 1/255), hi and lo, laid out [ks][half][lane] as float2 (b0, b1)
 template <int C>
 __device__ __forceinline__ void conv_mma_load_weights(const float* __restrict__ prm, const pqn_net_layout_t& L,
@@ -940,8 +978,10 @@ __device__ __forceinline__ void conv_mma_load_weights(const float* __restrict__ 
 
 // conv pre-activation of the 16 pixels of m-block `mb` (pixel = 16*mb + g [+8]); z[h][0..3] in C-fragment layout:
 // z[h][0],z[h][1] -> pixel g, channels 8h+2t, 8h+2t+1 ; z[h][2],z[h][3] -> pixel g+8, same channels.
+// (forward kernel: fragment bits straight from the packed observation; the patch staging only pays off in the
+// backward kernel, which reuses every patch for the weight-gradient fragments as well)
 template <int C>
-__device__ __forceinline__ void conv_mma_block(const uint32_t* __restrict__ so, const float2* __restrict__ wb_hi,
+__device__ __forceinline__ void conv_mma_block_direct(const uint32_t* __restrict__ so, const float2* __restrict__ wb_hi,
                                                const float2* __restrict__ wb_lo, const float* __restrict__ cb, int mb,
                                                int lane, const int (&off0)[ConvMma<C>::KS],
                                                const int (&off1)[ConvMma<C>::KS], float (&z)[2][4]) {
@@ -962,6 +1002,40 @@ __device__ __forceinline__ void conv_mma_block(const uint32_t* __restrict__ so, 
     a[1] = obs_bit_f32(so, base1 + off0[ks], v0);
     a[2] = obs_bit_f32(so, base0 + off1[ks], v1);
     a[3] = obs_bit_f32(so, base1 + off1[ks], v1);
+    if (__ballot_sync(0xffffffffu, (a[0] | a[1] | a[2] | a[3]) != 0u) == 0u) continue;  // empty patch slice
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float2 bl = wb_lo[(ks * 2 + h) * 32 + lane];
+      mma_tf32_16n8k8(z[h], a, __float_as_uint(bl.x), __float_as_uint(bl.y));
+      const float2 bh = wb_hi[(ks * 2 + h) * 32 + lane];
+      mma_tf32_16n8k8(z[h], a, __float_as_uint(bh.x), __float_as_uint(bh.y));
+    }
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void conv_mma_block(const uint32_t* __restrict__ patch, const float2* __restrict__ wb_hi,
+                                               const float2* __restrict__ wb_lo, const float* __restrict__ cb, int mb,
+                                               int lane, float (&z)[2][4]) {
+  using M = ConvMma<C>;
+  constexpr int PW = PatchCfg<C>::WORDS;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    z[h][0] = z[h][2] = cb[8 * h + 2 * t];
+    z[h][1] = z[h][3] = cb[8 * h + 2 * t + 1];
+  }
+  const int p0 = 16 * mb + g, p1 = p0 + 8;
+  uint32_t q0[PW], q1[PW];
+#pragma unroll
+  for (int k = 0; k < PW; ++k) { q0[k] = patch[p0 * PW + k]; q1[k] = patch[p1 * PW + k]; }
+#pragma unroll
+  for (int ks = 0; ks < M::KS; ++ks) {
+    // taps 8ks .. 8ks+7 live in one patch word (32 % 8 == 0); bits beyond 9C are zero
+    const uint32_t w0 = q0[(8 * ks) >> 5], w1 = q1[(8 * ks) >> 5];
+    const int sh = ((8 * ks) & 31) + t;
+    uint32_t a[4];
+    a[0] = bit_f32(w0, sh); a[1] = bit_f32(w1, sh); a[2] = bit_f32(w0, sh + 4); a[3] = bit_f32(w1, sh + 4);
     if (__ballot_sync(0xffffffffu, (a[0] | a[1] | a[2] | a[3]) != 0u) == 0u) continue;  // empty patch slice
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -1038,7 +1112,7 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
 #pragma unroll 1
     for (int mb = 0; mb < 4; ++mb) {
       float z[2][4];
-      conv_mma_block<C>(my_so, wb_hi, wb_lo, cb, mb, lane, off0, off1, z);
+      conv_mma_block_direct<C>(my_so, wb_hi, wb_lo, cb, mb, lane, off0, off1, z);
       float mean0, rstd0, mean1, rstd1;
       ln16_quad(z, mean0, rstd0, mean1, rstd1);
       uint32_t rb0 = 0u, rb1 = 0u;
@@ -1113,29 +1187,17 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
   using M = ConvMma<C>;
   __shared__ float2 wb_hi[M::KS * 2 * 32], wb_lo[M::KS * 2 * 32];
   __shared__ float cb[CONV_O], sc[CONV_O], bi[CONV_O];
-  __shared__ uint32_t so[M::BWD_WARPS][Cfg::SW];
+  __shared__ uint32_t spatch[M::BWD_WARPS][CONV_PIX * PatchCfg<C>::WORDS];
   __shared__ float sdz[M::BWD_WARPS][CONV_PIX * CDZ_LD];
-  __shared__ float s_w[M::MT * 16 * CONV_O];
   __shared__ float s_red[3 * CONV_O];
+  static_assert(Cfg::SW <= CONV_PIX * CDZ_LD, "obs staging aliases the dz stage");
+  static_assert(M::MT * 16 * CONV_O <= M::BWD_WARPS * CONV_PIX * CDZ_LD, "dW reduction buffer aliases the dz stage");
+  float* s_w = &sdz[0][0];  // block-level dW reduction buffer; only used after the row loop
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int seed = blockIdx.y;
   conv_mma_load_weights<C>(params + (int64_t)seed * P, L, wb_hi, wb_lo, cb, sc, bi);
-  for (int i = tid; i < M::MT * 16 * CONV_O; i += blockDim.x) s_w[i] = 0.f;
   if (tid < 3 * CONV_O) s_red[tid] = 0.f;
-  int off0[M::KS], off1[M::KS];
-#pragma unroll
-  for (int ks = 0; ks < M::KS; ++ks) {
-    off0[ks] = tap_bit_offset<C>(min(ks * 8 + t, M::TAPS - 1));
-    off1[ks] = tap_bit_offset<C>(min(ks * 8 + t + 4, M::TAPS - 1));
-  }
-  // weight-gradient A fragments: rows = taps 16*mt + g (+8)
-  int woff0[M::MT], woff1[M::MT];
-#pragma unroll
-  for (int mt = 0; mt < M::MT; ++mt) {
-    woff0[mt] = tap_bit_offset<C>(min(16 * mt + g, M::TAPS - 1));
-    woff1[mt] = tap_bit_offset<C>(min(16 * mt + g + 8, M::TAPS - 1));
-  }
   __syncthreads();
   // lane-private accumulators: columns {2t, 2t+1, 8+2t, 8+2t+1}
   float a_dsc[4] = {0.f, 0.f, 0.f, 0.f}, a_dbi[4] = {0.f, 0.f, 0.f, 0.f}, a_dcb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1147,8 +1209,9 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
 #pragma unroll
       for (int j = 0; j < 4; ++j) wrun[mt][h][j] = 0.f;
 
-  uint32_t* __restrict__ my_so = so[warp];
-  float* __restrict__ my_dz = sdz[warp];
+  // the packed observation is only needed until the patches are built: stage it in the (not yet written) dz buffer
+  float* my_dz = sdz[warp];
+  uint32_t* my_so = reinterpret_cast<uint32_t*>(sdz[warp]);
   for (int row = blockIdx.x * M::BWD_WARPS + warp; row < rows; row += gridDim.x * M::BWD_WARPS) {
     __syncwarp();
     {
@@ -1156,6 +1219,8 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
       const uint32_t* __restrict__ orow = obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW;
       for (int wi = lane; wi < Cfg::SW; wi += 32) my_so[wi] = wi < Cfg::PW ? __ldg(orow + wi) : 0u;
     }
+    __syncwarp();
+    build_patches<C>(my_so, spatch[warp], lane);
     __syncwarp();
     const float* __restrict__ dyrow = DY1 + ((int64_t)seed * rows + row) * FLAT_CNN;
     // ---- phase A: recompute conv + LN, LN backward, stage dz
@@ -1182,7 +1247,7 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
         rstd0 = __ldg(RS1 + ((int64_t)seed * rows + row) * CONV_PIX + p0);
         rstd1 = __ldg(RS1 + ((int64_t)seed * rows + row) * CONV_PIX + p1);
       } else {
-        conv_mma_block<C>(my_so, wb_hi, wb_lo, cb, mb, lane, off0, off1, z);
+        conv_mma_block<C>(spatch[warp], wb_hi, wb_lo, cb, mb, lane, z);
         ln16_quad(z, mean0, rstd0, mean1, rstd1);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -1243,16 +1308,18 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
         bl[h][0] = __float_as_uint(v0 - __uint_as_float(bh[h][0])); bl[h][1] = __float_as_uint(v1 - __uint_as_float(bh[h][1]));
       }
       // A fragments: x[tap, pixel]: a0 = (tap g, pixel 8kk+t), a1 = (tap g+8, same), a2 = (tap g, pixel+4), a3
+      constexpr int PWD = PatchCfg<C>::WORDS;
       const int pa = 8 * kk + t, pb = pa + 4;
-      const int basea = ((pa >> 3) * 10 + (pa & 7)) * C, baseb = ((pb >> 3) * 10 + (pb & 7)) * C;
+      uint32_t qa[PWD], qb[PWD];
+#pragma unroll
+      for (int k = 0; k < PWD; ++k) { qa[k] = spatch[warp][pa * PWD + k]; qb[k] = spatch[warp][pb * PWD + k]; }
 #pragma unroll
       for (int mt = 0; mt < M::MT; ++mt) {
-        const bool v0 = 16 * mt + g < M::TAPS, v1 = 16 * mt + g + 8 < M::TAPS;
+        // taps 16mt .. 16mt+15 live in one patch word (32 % 16 == 0, 16 mt < 9C <= 32 PWD); bits beyond 9C are zero
+        const uint32_t wa = qa[(16 * mt) >> 5], wb = qb[(16 * mt) >> 5];
+        const int sh = ((16 * mt) & 31) + g;
         uint32_t a[4];
-        a[0] = obs_bit_f32(my_so, basea + woff0[mt], v0);
-        a[1] = obs_bit_f32(my_so, basea + woff1[mt], v1);
-        a[2] = obs_bit_f32(my_so, baseb + woff0[mt], v0);
-        a[3] = obs_bit_f32(my_so, baseb + woff1[mt], v1);
+        a[0] = bit_f32(wa, sh); a[1] = bit_f32(wa, sh + 8); a[2] = bit_f32(wb, sh); a[3] = bit_f32(wb, sh + 8);
         if (__ballot_sync(0xffffffffu, (a[0] | a[1] | a[2] | a[3]) != 0u) == 0u) continue;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -1269,6 +1336,9 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
         for (int j = 0; j < 4; ++j) wrun[mt][h][j] += wacc[mt][h][j];
   }
   // ---- reduce and publish: wrun[mt][h][j] is dW[tap = 16mt + g (+8 for j>=2)][o = 8h + 2t + (j&1)]
+  __syncthreads();  // all warps are done with the dz stage
+  for (int i = tid; i < M::MT * 16 * CONV_O; i += blockDim.x) s_w[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int mt = 0; mt < M::MT; ++mt)
 #pragma unroll
