@@ -900,7 +900,6 @@ struct ConvMma {
   static constexpr int TAPS = 9 * C;
   static constexpr int KS = (TAPS + 7) / 8;    // k-steps of the forward GEMM (taps)
   static constexpr int MT = (TAPS + 15) / 16;  // m-blocks of the weight-gradient GEMM (taps)
-  static constexpr int BWD_WARPS = C >= 7 ? 4 : 8;
 };
 
 // bit offset of tap (di,dj,c) relative to the first channel bit of the output pixel's top-left input pixel
@@ -953,8 +952,10 @@ __device__ __forceinline__ uint32_t bit_f32(uint32_t word, int shift) {
   return ((word >> shift) & 1u) ? 0x3F800000u : 0u;
 }
 
-// B fragments of the conv weights (scaled by 1/255), hi and lo, laid out [ks][half][lane] as float2 (b0, b1)
-template <int C>
+// B fragments of the conv weights (scaled by 1/255), hi and lo, laid out [ks][half][lane] as float2 (b0, b1).
+// EXPC: the A operand is "exponent coded" (see ExpPatch): the activation of tap k is the power of two
+// 2^(2^(k%8) - 127) instead of 1, so row k of B carries the inverse factor 2^(127 - 2^(k%8)) (exact scaling).
+template <int C, bool EXPC = false>
 __device__ __forceinline__ void conv_mma_load_weights(const float* __restrict__ prm, const pqn_net_layout_t& L,
                                                       float2* wb_hi, float2* wb_lo, float* cb, float* sc, float* bi) {
   using M = ConvMma<C>;
@@ -963,8 +964,12 @@ __device__ __forceinline__ void conv_mma_load_weights(const float* __restrict__ 
     const int ln = i & 31, h = (i >> 5) & 1, ks = i >> 6;
     const int o = h * 8 + (ln >> 2);
     const int t0 = ks * 8 + (ln & 3), t1 = t0 + 4;
-    const float w0 = t0 < M::TAPS ? __ldg(prm + L.conv_w + t0 * CONV_O + o) * inv255 : 0.f;
-    const float w1 = t1 < M::TAPS ? __ldg(prm + L.conv_w + t1 * CONV_O + o) * inv255 : 0.f;
+    float w0 = t0 < M::TAPS ? __ldg(prm + L.conv_w + t0 * CONV_O + o) * inv255 : 0.f;
+    float w1 = t1 < M::TAPS ? __ldg(prm + L.conv_w + t1 * CONV_O + o) * inv255 : 0.f;
+    if (EXPC) {
+      w0 *= __uint_as_float((254u - (1u << (t0 & 7))) << 23);
+      w1 *= __uint_as_float((254u - (1u << (t1 & 7))) << 23);
+    }
     const float h0 = __uint_as_float(__float_as_uint(w0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(w1) & 0xFFFFE000u);
     wb_hi[i] = make_float2(h0, h1);
     wb_lo[i] = make_float2(w0 - h0, w1 - h1);
@@ -1047,6 +1052,81 @@ __device__ __forceinline__ void conv_mma_block(const uint32_t* __restrict__ patc
   }
 }
 
+// ---- exponent-coded im2col fragments (forward kernel) --------------------------------------------------------
+// A tf32 MMA operand only has to be *some* exactly known value when the input bit is set, not 1.0: a word whose
+// bits 23..30 (the fp32 exponent field) hold eight tap bits turns into an A element with ONE instruction,
+//     a = word & (1 << (23 + j))      ->  0  or  2^(2^j - 127)        (a normal power of two, mantissa 0)
+// and the matching row of B is pre-multiplied by 2^(127 - 2^j) (conv_mma_load_weights<C, true>), so every product
+// is bit-for-bit the product of the plain 0/1 formulation.  Per output pixel the patch is stored as KS words,
+// word ks = taps 8ks .. 8ks+7 at bits 23..30; lane (g, t) of the m16n8k8 fragment needs taps t and t+4.
+template <int C>
+struct ExpPatch {
+  static constexpr int KS = ConvMma<C>::KS;
+  static constexpr int LD = KS | 1;  // odd row stride: conflict-free for the 8 pixel rows a fragment load touches
+};
+
+template <int C>
+__device__ __forceinline__ void build_exp_patch(const uint32_t* __restrict__ so, int pix, uint32_t* __restrict__ out) {
+  constexpr int W = PatchCfg<C>::WORDS;
+  uint32_t w[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) w[k] = 0u;
+  const int y = pix >> 3, x = pix & 7;
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const uint32_t nib = pixel_bits<C>(so, (y + r / 3) * 10 + x + r % 3);
+    const int o = r * C;
+    w[o >> 5] |= nib << (o & 31);
+    if ((o & 31) + C > 32) w[min((o >> 5) + 1, W - 1)] |= nib >> (32 - (o & 31));
+  }
+#pragma unroll
+  for (int ks = 0; ks < ExpPatch<C>::KS; ++ks)  // 8 | 32: a k-step never straddles two words; bits >= 9C are zero
+    out[ks] = ((w[(8 * ks) >> 5] >> ((8 * ks) & 31)) & 0xFFu) << 23;
+}
+
+// conv pre-activation of the 32 pixels of m-blocks 2*mbp and 2*mbp+1 (two blocks share every B fragment load);
+// z[i][h][0..3] is the C fragment of block 2*mbp+i as in conv_mma_block.
+template <int C>
+__device__ __forceinline__ void conv_mma_block2_exp(const uint32_t* __restrict__ xp, const float2* __restrict__ wb_hi,
+                                                    const float2* __restrict__ wb_lo, const float* __restrict__ cb,
+                                                    int mbp, int lane, float (&z)[2][2][4]) {
+  using E = ExpPatch<C>;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t m_lo = 1u << (23 + t), m_hi = 1u << (27 + t);
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      z[i][h][0] = z[i][h][2] = cb[8 * h + 2 * t];
+      z[i][h][1] = z[i][h][3] = cb[8 * h + 2 * t + 1];
+    }
+  const uint32_t* r00 = xp + (32 * mbp + g) * E::LD;  // pixel rows g, g+8 of block 2mbp; +16, +24 of block 2mbp+1
+#pragma unroll
+  for (int ks = 0; ks < E::KS; ++ks) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t w0 = r00[(16 * i) * E::LD + ks], w1 = r00[(16 * i + 8) * E::LD + ks];
+      a[i][0] = w0 & m_lo; a[i][1] = w1 & m_lo; a[i][2] = w0 & m_hi; a[i][3] = w1 & m_hi;
+    }
+    float2 bl[2], bh[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      bl[h] = wb_lo[(ks * 2 + h) * 32 + lane];
+      bh[h] = wb_hi[(ks * 2 + h) * 32 + lane];
+    }
+    // four independent accumulators between the lo and the hi pass of the same one (no back-to-back dependency)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) mma_tf32_16n8k8(z[i][h], a[i], __float_as_uint(bl[h].x), __float_as_uint(bl[h].y));
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) mma_tf32_16n8k8(z[i][h], a[i], __float_as_uint(bh[h].x), __float_as_uint(bh[h].y));
+  }
+}
+
 // LayerNorm statistics over the 16 channels of pixel rows g (z[.][0..1]) and g+8 (z[.][2..3]); quad reduction
 __device__ __forceinline__ void ln16_quad(const float (&z)[2][4], float& mean0, float& rstd0, float& mean1,
                                           float& rstd1) {
@@ -1060,14 +1140,15 @@ __device__ __forceinline__ void ln16_quad(const float (&z)[2][4], float& mean0, 
     s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
   }
   mean0 = s0 * (1.0f / CONV_O); mean1 = s1 * (1.0f / CONV_O);
-  rstd0 = 1.0f / sqrtf(fmaxf(q0 * (1.0f / CONV_O) - mean0 * mean0, 0.f) + LN_EPS);
-  rstd1 = 1.0f / sqrtf(fmaxf(q1 * (1.0f / CONV_O) - mean1 * mean1, 0.f) + LN_EPS);
+  // MUFU.RSQ (2 ulp) instead of the IEEE 1/sqrt sequence, whose slow-path branches cost more than the conv MMAs
+  rstd0 = rsqrtf(fmaxf(q0 * (1.0f / CONV_O) - mean0 * mean0, 0.f) + LN_EPS);
+  rstd1 = rsqrtf(fmaxf(q1 * (1.0f / CONV_O) - mean1 * mean1, 0.f) + LN_EPS);
 }
 
 constexpr int CONV_MMA_WARPS = 8;
 
 template <int C, bool TRAIN>
-__global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
+__global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
     conv_fwd_mma_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
                         const float* __restrict__ params, int64_t P, pqn_net_layout_t L, float* __restrict__ H1,
                         float* __restrict__ H1LO, float* __restrict__ XH1, float* __restrict__ RS1,
@@ -1077,30 +1158,35 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
   __shared__ float2 wb_hi[M::KS * 2 * 32], wb_lo[M::KS * 2 * 32];
   __shared__ float cb[CONV_O], sc[CONV_O], bi[CONV_O];
   __shared__ uint32_t so[CONV_MMA_WARPS][Cfg::SW];
+  __shared__ uint32_t sxp[CONV_MMA_WARPS][CONV_PIX * ExpPatch<C>::LD];
   __shared__ float s_cnt[C];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int seed = blockIdx.y;
-  conv_mma_load_weights<C>(params + (int64_t)seed * P, L, wb_hi, wb_lo, cb, sc, bi);
+  conv_mma_load_weights<C, true>(params + (int64_t)seed * P, L, wb_hi, wb_lo, cb, sc, bi);
   if (TRAIN && tid < C) s_cnt[tid] = 0.f;
-  int off0[M::KS], off1[M::KS];
-#pragma unroll
-  for (int ks = 0; ks < M::KS; ++ks) {
-    off0[ks] = tap_bit_offset<C>(min(ks * 8 + t, M::TAPS - 1));
-    off1[ks] = tap_bit_offset<C>(min(ks * 8 + t + 4, M::TAPS - 1));
-  }
   __syncthreads();
   int cnt[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) cnt[c] = 0;
   uint32_t* __restrict__ my_so = so[warp];
-  for (int row = blockIdx.x * CONV_MMA_WARPS + warp; row < rows; row += gridDim.x * CONV_MMA_WARPS) {
+  static_assert(Cfg::PW <= 32, "one packed observation word per lane");
+  if (lane == 0) my_so[Cfg::PW] = 0u;  // pad word read by the funnel shift of the last pixel
+  // software pipeline: the next sample's packed observation is fetched while the current one is processed
+  const int row_stride = gridDim.x * CONV_MMA_WARPS;
+  auto fetch = [&](int r) -> uint32_t {
+    if (r >= rows || lane >= Cfg::PW) return 0u;
+    const int64_t src = gather ? gather[(int64_t)seed * rows + r] : r;
+    return __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + lane);
+  };
+  uint32_t pre = fetch(blockIdx.x * CONV_MMA_WARPS + warp);
+  for (int row = blockIdx.x * CONV_MMA_WARPS + warp; row < rows; row += row_stride) {
     __syncwarp();
-    {
-      const int64_t src = gather ? gather[(int64_t)seed * rows + row] : row;
-      const uint32_t* __restrict__ orow = obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW;
-      for (int wi = lane; wi < Cfg::SW; wi += 32) my_so[wi] = wi < Cfg::PW ? __ldg(orow + wi) : 0u;
-    }
+    if (lane < Cfg::PW) my_so[lane] = pre;
+    __syncwarp();
+    pre = fetch(row + row_stride);
+    build_exp_patch<C>(my_so, lane, sxp[warp] + lane * ExpPatch<C>::LD);
+    build_exp_patch<C>(my_so, lane + 32, sxp[warp] + (lane + 32) * ExpPatch<C>::LD);
     __syncwarp();
     float* __restrict__ hrow = H1 + ((int64_t)seed * rows + row) * FLAT_CNN;
     float* __restrict__ lrow = H1LO ? H1LO + ((int64_t)seed * rows + row) * FLAT_CNN : nullptr;
@@ -1110,9 +1196,13 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
     uint16_t* __restrict__ brow =
         (TRAIN && RB) ? reinterpret_cast<uint16_t*>(RB + ((int64_t)seed * rows + row) * (FLAT_CNN / 32)) : nullptr;
 #pragma unroll 1
-    for (int mb = 0; mb < 4; ++mb) {
-      float z[2][4];
-      conv_mma_block_direct<C>(my_so, wb_hi, wb_lo, cb, mb, lane, off0, off1, z);
+    for (int mbp = 0; mbp < 2; ++mbp) {
+     float z2[2][2][4];
+     conv_mma_block2_exp<C>(sxp[warp], wb_hi, wb_lo, cb, mbp, lane, z2);
+#pragma unroll
+     for (int mi = 0; mi < 2; ++mi) {
+      const int mb = 2 * mbp + mi;
+      float (&z)[2][4] = z2[mi];
       float mean0, rstd0, mean1, rstd1;
       ln16_quad(z, mean0, rstd0, mean1, rstd1);
       uint32_t rb0 = 0u, rb1 = 0u;
@@ -1148,6 +1238,7 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
         rb0 |= __shfl_xor_sync(0xffffffffu, rb0, 2); rb1 |= __shfl_xor_sync(0xffffffffu, rb1, 2);
         if (t == 0) { brow[16 * mb + g] = (uint16_t)rb0; brow[16 * mb + g + 8] = (uint16_t)rb1; }
       }
+     }
     }
     if (TRAIN && bn_sums != nullptr) {
       // dummy input BatchNorm statistics: per-channel popcount of the 100 input pixels (x in {0,1})
@@ -1176,27 +1267,60 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32)
 
 constexpr int CDZ_LD = 17;  // staged dz row stride (floats): conflict-free B-fragment reads
 
-// (4 warps per CTA for the wide-channel games keep the static shared memory under 48 KB)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// per-warp shared-memory slice of the conv backward kernel (floats)
 template <int C>
-__global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
+struct ConvBwdSmem {
+  static constexpr int DY = 0;                                  // [64][16] upstream gradient of the sample
+  static constexpr int XH = DY + FLAT_CNN;                      // [64][16] saved LayerNorm xhat
+  static constexpr int RS = XH + FLAT_CNN;                      // [64]     saved rstd
+  static constexpr int DZ = RS + CONV_PIX;                      // [64][CDZ_LD] dz stage (aliases the packed obs row)
+  static constexpr int PATCH = DZ + CONV_PIX * CDZ_LD;          // [64][PatchCfg::WORDS] im2col bit patches
+  static constexpr int WARP_FLOATS = (PATCH + CONV_PIX * PatchCfg<C>::WORDS + 3) / 4 * 4;
+  static constexpr int WARPS = 8;
+  static constexpr int BYTES = (WARPS * WARP_FLOATS + 4 * CONV_O) * 4;  // + sc[16] + s_red[48]
+};
+
+// Backward of conv3x3 + LayerNorm(16) + ReLU for one sample per warp, from the xhat / rstd the training forward
+// saved (ReLU' is already folded into DY1 by the dense dgrad epilogue):
+//   phase A  LayerNorm backward per pixel -> dz[pixel][16] (staged in shared memory), d(scale), d(bias), d(conv bias)
+//   phase B  dW[tap][o] += sum_pixels x[pixel, tap] dz[pixel][o] on mma.sync (A = im2col bits, B = dz as hi + lo)
+// The sample's DY1 / xhat / rstd rows (8.25 KB) are fetched with cp.async while phase B of the previous sample
+// runs, so the HBM latency is off the dependent path (it was 42% of all stall samples before).
+template <int C>
+__global__ void __launch_bounds__(ConvBwdSmem<C>::WARPS * 32, 2)
     conv_bwd_mma_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
                         const float* __restrict__ params, int64_t P, pqn_net_layout_t L, const float* __restrict__ DY1,
                         const float* __restrict__ XH1, const float* __restrict__ RS1, float* __restrict__ grads,
                         int rows) {
   using Cfg = ConvCfg<C>;
   using M = ConvMma<C>;
-  __shared__ float2 wb_hi[M::KS * 2 * 32], wb_lo[M::KS * 2 * 32];
-  __shared__ float cb[CONV_O], sc[CONV_O], bi[CONV_O];
-  __shared__ uint32_t spatch[M::BWD_WARPS][CONV_PIX * PatchCfg<C>::WORDS];
-  __shared__ float sdz[M::BWD_WARPS][CONV_PIX * CDZ_LD];
-  __shared__ float s_red[3 * CONV_O];
-  static_assert(Cfg::SW <= CONV_PIX * CDZ_LD, "obs staging aliases the dz stage");
-  static_assert(M::MT * 16 * CONV_O <= M::BWD_WARPS * CONV_PIX * CDZ_LD, "dW reduction buffer aliases the dz stage");
-  float* s_w = &sdz[0][0];  // block-level dW reduction buffer; only used after the row loop
+  using SM = ConvBwdSmem<C>;
+  constexpr int PWD = PatchCfg<C>::WORDS;
+  extern __shared__ __align__(16) float smem_bwd[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int seed = blockIdx.y;
-  conv_mma_load_weights<C>(params + (int64_t)seed * P, L, wb_hi, wb_lo, cb, sc, bi);
+  float* my = smem_bwd + warp * SM::WARP_FLOATS;
+  float* my_dy = my + SM::DY;
+  float* my_xh = my + SM::XH;
+  float* my_rs = my + SM::RS;
+  float* my_dz = my + SM::DZ;
+  uint32_t* my_so = reinterpret_cast<uint32_t*>(my + SM::DZ);  // only needed until the patches are built
+  uint32_t* my_patch = reinterpret_cast<uint32_t*>(my + SM::PATCH);
+  float* sc = smem_bwd + SM::WARPS * SM::WARP_FLOATS;
+  float* s_red = sc + CONV_O;
+  float* s_w = smem_bwd;  // block-level dW reduction buffer, aliases warp 0's slice; only used after the row loop
+  static_assert(Cfg::SW <= CONV_PIX * CDZ_LD, "obs staging aliases the dz stage");
+  static_assert(M::MT * 16 * CONV_O <= SM::WARP_FLOATS * SM::WARPS, "dW reduction buffer aliases the warp slices");
+  static_assert(Cfg::PW <= 32, "one packed observation word per lane");
+  if (tid < CONV_O) sc[tid] = __ldg(params + (int64_t)seed * P + L.ln0_scale + tid);
   if (tid < 3 * CONV_O) s_red[tid] = 0.f;
   __syncthreads();
   // lane-private accumulators: columns {2t, 2t+1, 8+2t, 8+2t+1}
@@ -1209,51 +1333,53 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
 #pragma unroll
       for (int j = 0; j < 4; ++j) wrun[mt][h][j] = 0.f;
 
-  // the packed observation is only needed until the patches are built: stage it in the (not yet written) dz buffer
-  float* my_dz = sdz[warp];
-  uint32_t* my_so = reinterpret_cast<uint32_t*>(sdz[warp]);
-  for (int row = blockIdx.x * M::BWD_WARPS + warp; row < rows; row += gridDim.x * M::BWD_WARPS) {
-    __syncwarp();
-    {
-      const int64_t src = gather ? gather[(int64_t)seed * rows + row] : row;
-      const uint32_t* __restrict__ orow = obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW;
-      for (int wi = lane; wi < Cfg::SW; wi += 32) my_so[wi] = wi < Cfg::PW ? __ldg(orow + wi) : 0u;
+  const int row_stride = gridDim.x * SM::WARPS;
+  auto fetch_obs = [&](int r) -> uint32_t {
+    if (r >= rows || lane >= Cfg::PW) return 0u;
+    const int64_t src = gather ? gather[(int64_t)seed * rows + r] : r;
+    return __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + lane);
+  };
+  auto fetch_rows = [&](int r) {  // async copy of the sample's dy / xhat / rstd rows into this warp's slice
+    if (r < rows) {
+      const int64_t gr = (int64_t)seed * rows + r;
+      const float* dsrc = DY1 + gr * FLAT_CNN;
+      const float* xsrc = XH1 + gr * FLAT_CNN;
+#pragma unroll
+      for (int i = 0; i < FLAT_CNN / 4 / 32; ++i) {
+        cp_async16(my_dy + (i * 32 + lane) * 4, dsrc + (i * 32 + lane) * 4);
+        cp_async16(my_xh + (i * 32 + lane) * 4, xsrc + (i * 32 + lane) * 4);
+      }
+      if (lane < CONV_PIX / 4) cp_async16(my_rs + lane * 4, RS1 + gr * CONV_PIX + lane * 4);
     }
+    cp_async_commit();
+  };
+  int row = blockIdx.x * SM::WARPS + warp;
+  uint32_t pre = fetch_obs(row);
+  fetch_rows(row);
+  for (; row < rows; row += row_stride) {
     __syncwarp();
-    build_patches<C>(my_so, spatch[warp], lane);
+    if (lane < Cfg::PW) my_so[lane] = pre;
+    if (lane == 0) my_so[Cfg::PW] = 0u;  // pad word read by the funnel shift of the last pixel
     __syncwarp();
-    const float* __restrict__ dyrow = DY1 + ((int64_t)seed * rows + row) * FLAT_CNN;
-    // ---- phase A: recompute conv + LN, LN backward, stage dz
+    pre = fetch_obs(row + row_stride);
+    build_patches<C>(my_so, my_patch, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    // ---- phase A: LayerNorm backward, stage dz
 #pragma unroll 1
     for (int mb = 0; mb < 4; ++mb) {
       const int p0 = 16 * mb + g, p1 = p0 + 8;
+      float z[2][4];  // xhat in C-fragment layout
       float2 dyv[2][2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        dyv[h][0] = __ldg(reinterpret_cast<const float2*>(dyrow + p0 * CONV_O + 8 * h + 2 * t));
-        dyv[h][1] = __ldg(reinterpret_cast<const float2*>(dyrow + p1 * CONV_O + 8 * h + 2 * t));
+        dyv[h][0] = *reinterpret_cast<const float2*>(my_dy + p0 * CONV_O + 8 * h + 2 * t);
+        dyv[h][1] = *reinterpret_cast<const float2*>(my_dy + p1 * CONV_O + 8 * h + 2 * t);
+        const float2 a0 = *reinterpret_cast<const float2*>(my_xh + p0 * CONV_O + 8 * h + 2 * t);
+        const float2 a1 = *reinterpret_cast<const float2*>(my_xh + p1 * CONV_O + 8 * h + 2 * t);
+        z[h][0] = a0.x; z[h][1] = a0.y; z[h][2] = a1.x; z[h][3] = a1.y;
       }
-      float z[2][4];
-      float mean0 = 0.f, rstd0, mean1 = 0.f, rstd1;
-      if (XH1 != nullptr) {
-        // xhat / rstd saved by the training forward: no conv recompute
-        const float* __restrict__ xrow = XH1 + ((int64_t)seed * rows + row) * FLAT_CNN;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float2 a0 = __ldg(reinterpret_cast<const float2*>(xrow + p0 * CONV_O + 8 * h + 2 * t));
-          const float2 a1 = __ldg(reinterpret_cast<const float2*>(xrow + p1 * CONV_O + 8 * h + 2 * t));
-          z[h][0] = a0.x; z[h][1] = a0.y; z[h][2] = a1.x; z[h][3] = a1.y;
-        }
-        rstd0 = __ldg(RS1 + ((int64_t)seed * rows + row) * CONV_PIX + p0);
-        rstd1 = __ldg(RS1 + ((int64_t)seed * rows + row) * CONV_PIX + p1);
-      } else {
-        conv_mma_block<C>(spatch[warp], wb_hi, wb_lo, cb, mb, lane, z);
-        ln16_quad(z, mean0, rstd0, mean1, rstd1);
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) z[h][j] = (z[h][j] - (j < 2 ? mean0 : mean1)) * (j < 2 ? rstd0 : rstd1);
-      }
+      const float rstd0 = my_rs[p0], rstd1 = my_rs[p1];
       float dxh[2][4];
       float m1a = 0.f, m2a = 0.f, m1b = 0.f, m2b = 0.f;
 #pragma unroll
@@ -1289,6 +1415,7 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
       }
     }
     __syncwarp();
+    fetch_rows(row + row_stride);  // overlaps phase B
     // ---- phase B: dW[tap][o] += sum_pixels x[pixel, tap] * dz[pixel][o]   (fresh accumulators per sample)
     float wacc[M::MT][2][4];
 #pragma unroll
@@ -1308,11 +1435,10 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
         bl[h][0] = __float_as_uint(v0 - __uint_as_float(bh[h][0])); bl[h][1] = __float_as_uint(v1 - __uint_as_float(bh[h][1]));
       }
       // A fragments: x[tap, pixel]: a0 = (tap g, pixel 8kk+t), a1 = (tap g+8, same), a2 = (tap g, pixel+4), a3
-      constexpr int PWD = PatchCfg<C>::WORDS;
       const int pa = 8 * kk + t, pb = pa + 4;
       uint32_t qa[PWD], qb[PWD];
 #pragma unroll
-      for (int k = 0; k < PWD; ++k) { qa[k] = spatch[warp][pa * PWD + k]; qb[k] = spatch[warp][pb * PWD + k]; }
+      for (int k = 0; k < PWD; ++k) { qa[k] = my_patch[pa * PWD + k]; qb[k] = my_patch[pb * PWD + k]; }
 #pragma unroll
       for (int mt = 0; mt < M::MT; ++mt) {
         // taps 16mt .. 16mt+15 live in one patch word (32 % 16 == 0, 16 mt < 9C <= 32 PWD); bits beyond 9C are zero
@@ -1335,8 +1461,9 @@ __global__ void __launch_bounds__(ConvMma<C>::BWD_WARPS * 32, 2)
 #pragma unroll
         for (int j = 0; j < 4; ++j) wrun[mt][h][j] += wacc[mt][h][j];
   }
+  cp_async_wait_all();
   // ---- reduce and publish: wrun[mt][h][j] is dW[tap = 16mt + g (+8 for j>=2)][o = 8h + 2t + (j&1)]
-  __syncthreads();  // all warps are done with the dz stage
+  __syncthreads();  // all warps are done with their slices
   for (int i = tid; i < M::MT * 16 * CONV_O; i += blockDim.x) s_w[i] = 0.f;
   __syncthreads();
 #pragma unroll
@@ -1708,6 +1835,22 @@ static void launch_dense(int BN, dim3 grid, cudaStream_t st, const float* X, int
 
 static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
+template <int C>
+static int launch_conv_bwd_mma(dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
+                               const float* params, int64_t P, const pqn_net_layout_t& L, const float* dy1,
+                               const float* xh1, const float* rs1, float* grads, int rows) {
+  auto kfn = conv_bwd_mma_kernel<C>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvBwdSmem<C>::BYTES) != cudaSuccess)
+      return check_launch("conv_bwd_mma(cudaFuncSetAttribute)");
+    attr_set = true;
+  }
+  kfn<<<grid, ConvBwdSmem<C>::WARPS * 32, ConvBwdSmem<C>::BYTES, st>>>(obs, orps, gather, params, P, L, dy1, xh1, rs1,
+                                                                       grads, rows);
+  return 0;
+}
+
 static unsigned conv_mma_ctas(int S, int rows) {
   int per_seed = (148 * 2 * 4 + S - 1) / S;
   const int maxc = (rows + CONV_MMA_WARPS - 1) / CONV_MMA_WARPS;
@@ -1973,11 +2116,12 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
       const dim3 mg(conv_mma_ctas(S, R), S);
       LaunchScope _ls(K_CONV_BWD, st);
       switch (d->in_c) {
-        case 4: conv_bwd_mma_kernel<4><<<mg, ConvMma<4>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
-        case 6: conv_bwd_mma_kernel<6><<<mg, ConvMma<6>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
-        case 7: conv_bwd_mma_kernel<7><<<mg, ConvMma<7>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
-        case 10: conv_bwd_mma_kernel<10><<<mg, ConvMma<10>::BWD_WARPS * 32, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
+        case 4: rc = launch_conv_bwd_mma<4>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
+        case 6: rc = launch_conv_bwd_mma<6>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
+        case 7: rc = launch_conv_bwd_mma<7>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
+        case 10: rc = launch_conv_bwd_mma<10>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
       }
+      if (rc) return rc;
     } else
     switch (d->in_c) {
       case 4: { LaunchScope _ls(K_CONV_BWD, st); conv_bwd_kernel<4><<<cg, 256, 0, st>>>(ob, obs_rows_per_seed, gather, params, P, L, w.h1, grads, R); } break;
