@@ -1167,8 +1167,18 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
   if (TRAIN && tid < C) s_cnt[tid] = 0.f;
   __syncthreads();
   int cnt[C];
+  uint32_t cmask[C];  // bits of this lane's observation word (word index = lane) that belong to channel c
 #pragma unroll
-  for (int c = 0; c < C; ++c) cnt[c] = 0;
+  for (int c = 0; c < C; ++c) {
+    cnt[c] = 0;
+    cmask[c] = 0u;
+    if (TRAIN) {
+      for (int b = 0; b < 32; ++b) {
+        const int f = lane * 32 + b;
+        if (f < Cfg::OBS_BITS && f % C == c) cmask[c] |= 1u << b;
+      }
+    }
+  }
   uint32_t* __restrict__ my_so = so[warp];
   static_assert(Cfg::PW <= 32, "one packed observation word per lane");
   if (lane == 0) my_so[Cfg::PW] = 0u;  // pad word read by the funnel shift of the last pixel
@@ -1183,6 +1193,11 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
   for (int row = blockIdx.x * CONV_MMA_WARPS + warp; row < rows; row += row_stride) {
     __syncwarp();
     if (lane < Cfg::PW) my_so[lane] = pre;
+    if (TRAIN && bn_sums != nullptr) {
+      // dummy input BatchNorm statistics: per-channel popcount of the 100 input pixels (x in {0,1})
+#pragma unroll
+      for (int c = 0; c < C; ++c) cnt[c] += __popc(pre & cmask[c]);
+    }
     __syncwarp();
     pre = fetch(row + row_stride);
     build_exp_patch<C>(my_so, lane, sxp[warp] + lane * ExpPatch<C>::LD);
@@ -1239,14 +1254,6 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
         if (t == 0) { brow[16 * mb + g] = (uint16_t)rb0; brow[16 * mb + g + 8] = (uint16_t)rb1; }
       }
      }
-    }
-    if (TRAIN && bn_sums != nullptr) {
-      // dummy input BatchNorm statistics: per-channel popcount of the 100 input pixels (x in {0,1})
-      for (int p = lane; p < 100; p += 32) {
-        const uint32_t b = pixel_bits<C>(my_so, p);
-#pragma unroll
-        for (int c = 0; c < C; ++c) cnt[c] += (int)((b >> c) & 1u);
-      }
     }
   }
   if (TRAIN && bn_sums != nullptr) {
@@ -1447,11 +1454,11 @@ __global__ void __launch_bounds__(ConvBwdSmem<C>::WARPS * 32, 2)
         uint32_t a[4];
         a[0] = bit_f32(wa, sh); a[1] = bit_f32(wa, sh + 8); a[2] = bit_f32(wb, sh); a[3] = bit_f32(wb, sh + 8);
         if (__ballot_sync(0xffffffffu, (a[0] | a[1] | a[2] | a[3]) != 0u) == 0u) continue;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mma_tf32_16n8k8(wacc[mt][h], a, bl[h][0], bl[h][1]);
-          mma_tf32_16n8k8(wacc[mt][h], a, bh[h][0], bh[h][1]);
-        }
+        // lo pass of both column halves, then the hi pass: no back-to-back MMAs on one accumulator
+        mma_tf32_16n8k8(wacc[mt][0], a, bl[0][0], bl[0][1]);
+        mma_tf32_16n8k8(wacc[mt][1], a, bl[1][0], bl[1][1]);
+        mma_tf32_16n8k8(wacc[mt][0], a, bh[0][0], bh[0][1]);
+        mma_tf32_16n8k8(wacc[mt][1], a, bh[1][0], bh[1][1]);
       }
     }
 #pragma unroll
