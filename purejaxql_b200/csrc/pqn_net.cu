@@ -1858,12 +1858,29 @@ static int launch_conv_bwd_mma(dim3 grid, cudaStream_t st, const uint32_t* obs, 
   return 0;
 }
 
-static unsigned conv_mma_ctas(int S, int rows) {
-  int per_seed = (148 * 2 * 4 + S - 1) / S;
+// CTAs per seed for the warp-per-sample conv kernels (grid = per_seed x S).  `resident` = CTAs the GPU holds at once
+// (SMs x CTAs/SM): the grid is sized to fill whole waves of that many CTAs -- 1280 CTAs on 296 slots would run a
+// fifth, 32%-full wave -- while staying near 4 waves so that per-CTA setup (weight fragments) stays amortised.
+static unsigned conv_mma_ctas(int S, int rows, int ctas_per_sm) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  const int resident = sms * ctas_per_sm;
   const int maxc = (rows + CONV_MMA_WARPS - 1) / CONV_MMA_WARPS;
-  if (per_seed > maxc) per_seed = maxc;
-  if (per_seed < 1) per_seed = 1;
-  return (unsigned)per_seed;
+  int best = 1;
+  double best_eff = 0.0;
+  const int lim = (6 * resident + S - 1) / S;
+  for (int per_seed = 1; per_seed <= lim && per_seed <= maxc; ++per_seed) {
+    const int total = per_seed * S;
+    const int waves = (total + resident - 1) / resident;
+    if (waves > 6) break;
+    const double eff = (double)total / ((double)waves * resident);
+    if (eff > best_eff + 0.01 || (eff > best_eff - 0.01 && waves <= 4)) { best_eff = eff > best_eff ? eff : best_eff; best = per_seed; }
+  }
+  return (unsigned)best;
 }
 
 template <bool TRAIN>
@@ -1881,7 +1898,7 @@ static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* ob
     }
   }
   if (g_conv_mma) {
-    const dim3 mg(conv_mma_ctas((int)grid.y, rows), grid.y);
+    const dim3 mg(conv_mma_ctas((int)grid.y, rows, 3), grid.y);
     LaunchScope _ls(K_CONV_FWD, st);
     switch (C) {
       case 4: conv_fwd_mma_kernel<4, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
@@ -2120,7 +2137,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
     }
     dim3 cg(conv_bwd_ctas(S, R), S);
     if (g_conv_mma) {
-      const dim3 mg(conv_mma_ctas(S, R), S);
+      const dim3 mg(conv_mma_ctas(S, R, 2), S);
       LaunchScope _ls(K_CONV_BWD, st);
       switch (d->in_c) {
         case 4: rc = launch_conv_bwd_mma<4>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;

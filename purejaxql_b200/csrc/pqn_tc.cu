@@ -91,9 +91,34 @@ __device__ __forceinline__ void prefetch_mask_bits(const EpiParams& ep, int seed
 }
 
 // `m_base` = first row of this warp's 32-row block; the lane's own row is m_base + lane.
+// Shared-memory copy of the per-seed epilogue parameters (LN epilogues), staged once per tile by the 128 epilogue
+// threads: every thread needs all of them, and 128-bit broadcast reads cost a quarter of the per-element loads.
+constexpr int SP_B = 0, SP_SC = 128, SP_BI = 256, SP_HW = 384 /* [PQN_TC_MAX_A][128] */,
+              SP_HB = SP_HW + PQN_TC_MAX_A * 128, SP_FLOATS = SP_HB + PQN_TC_MAX_A;
+static_assert(SP_FLOATS == 384 + 8 * 128 + 8, "matches the TC_SMEM_BYTES budget in tc_common.cuh");
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[128], float* stage, int lane, int seed,
-                                             int m_base, int n0, int M, const uint32_t (&mask_bits)[4]) {
+__device__ __forceinline__ void stage_epi_params(const EpiParams& ep, float* sp, int seed, int et /*0..127*/) {
+  if constexpr (EPI == EPI_LN_TRAIN || EPI == EPI_LN_HEAD) {
+    const float* __restrict__ prm = ep.params + (int64_t)seed * ep.P;
+    epi_bar_sync();  // everyone is done with the previous tile's parameters
+    sp[SP_B + et] = __ldg(prm + ep.off_b + et);
+    sp[SP_SC + et] = __ldg(prm + ep.off_scale + et);
+    sp[SP_BI + et] = __ldg(prm + ep.off_bias + et);
+    if constexpr (EPI == EPI_LN_HEAD) {
+      for (int a = 0; a < ep.A; ++a) sp[SP_HW + a * 128 + et] = __ldg(prm + ep.off_hw + (int64_t)et * ep.A + a);
+      if (et < ep.A) sp[SP_HB + et] = __ldg(prm + ep.off_hb + et);
+    }
+    epi_bar_sync();
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[128], float* stage, const float* sp,
+                                             int lane, int seed, int m_base, int n0, int M,
+                                             const uint32_t (&mask_bits)[4]) {
   const int m = m_base + lane;
   const bool row_ok = m < M;
   if constexpr (EPI == EPI_STORE || EPI == EPI_RELU_MASK || EPI == EPI_RELU_BITS) {
@@ -112,13 +137,18 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[1
     }
   } else {
     // bias + LayerNorm(128) + ReLU, then either (h, xhat, rstd) or the fused Q-head
-    const float* __restrict__ prm = ep.params + (int64_t)seed * ep.P;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 128; ++j) {
-      acc[j] += __ldg(prm + ep.off_b + j);
-      s1 += acc[j];
-      s2 = fmaf(acc[j], acc[j], s2);
+    for (int j4 = 0; j4 < 32; ++j4) {
+      const float4 b = *reinterpret_cast<const float4*>(sp + SP_B + 4 * j4);
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * j4 + e;
+        acc[j] += bb[e];
+        s1 += acc[j];
+        s2 = fmaf(acc[j], acc[j], s2);
+      }
     }
     const float mean = s1 * (1.0f / 128.f);
     const float var = fmaxf(s2 * (1.0f / 128.f) - mean * mean, 0.f);
@@ -131,10 +161,16 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[1
       for (int c = 0; c < 4; ++c) {
         float xh[32], h[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = c * 32 + j;
-          xh[j] = (acc[col] - mean) * rstd;
-          h[j] = fmaxf(xh[j] * __ldg(prm + ep.off_scale + col) + __ldg(prm + ep.off_bias + col), 0.f);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sp + SP_SC + c * 32 + 4 * j4);
+          const float4 b4 = *reinterpret_cast<const float4*>(sp + SP_BI + c * 32 + 4 * j4);
+          const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * j4 + e;
+            xh[j] = (acc[c * 32 + j] - mean) * rstd;
+            h[j] = fmaxf(xh[j] * ss[e] + bb[e], 0.f);
+          }
         }
         store_chunk_coalesced<false>(stage, h, lane, hbase + c * 32, 0u, 128, m_base, M);
         store_chunk_coalesced<false>(stage, xh, lane, xbase + c * 32, 0u, 128, m_base, M);
@@ -145,16 +181,26 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[1
 #pragma unroll
       for (int a = 0; a < PQN_TC_MAX_A; ++a) q[a] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 128; ++j) {
-        const float h = fmaxf((acc[j] - mean) * rstd * __ldg(prm + ep.off_scale + j) + __ldg(prm + ep.off_bias + j), 0.f);
+      for (int j4 = 0; j4 < 32; ++j4) {
+        const float4 s4 = *reinterpret_cast<const float4*>(sp + SP_SC + 4 * j4);
+        const float4 b4 = *reinterpret_cast<const float4*>(sp + SP_BI + 4 * j4);
+        float h[4];
+        h[0] = fmaxf((acc[4 * j4 + 0] - mean) * rstd * s4.x + b4.x, 0.f);
+        h[1] = fmaxf((acc[4 * j4 + 1] - mean) * rstd * s4.y + b4.y, 0.f);
+        h[2] = fmaxf((acc[4 * j4 + 2] - mean) * rstd * s4.z + b4.z, 0.f);
+        h[3] = fmaxf((acc[4 * j4 + 3] - mean) * rstd * s4.w + b4.w, 0.f);
 #pragma unroll
         for (int a = 0; a < PQN_TC_MAX_A; ++a)
-          if (a < ep.A) q[a] = fmaf(h, __ldg(prm + ep.off_hw + (int64_t)j * ep.A + a), q[a]);
+          if (a < ep.A) {
+            const float4 w4 = *reinterpret_cast<const float4*>(sp + SP_HW + a * 128 + 4 * j4);
+            q[a] = fmaf(h[0], w4.x, q[a]); q[a] = fmaf(h[1], w4.y, q[a]);
+            q[a] = fmaf(h[2], w4.z, q[a]); q[a] = fmaf(h[3], w4.w, q[a]);
+          }
       }
       if (row_ok) {
 #pragma unroll
         for (int a = 0; a < PQN_TC_MAX_A; ++a)
-          if (a < ep.A) ep.Q[grow * ep.A + a] = q[a] + __ldg(prm + ep.off_hb + a);
+          if (a < ep.A) ep.Q[grow * ep.A + a] = q[a] + sp[SP_HB + a];
       }
     }
   }
@@ -203,6 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint64_t* lo_full = corr_empty + 2;           // [TC_STAGES]   converters -> MMA (A_lo tile written)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + TC_STAGES);
   float* stage_all = reinterpret_cast<float*>(smem_al + TC_STAGES * TC_STAGE_BYTES + 256);  // 4 x [32][STG_LD]
+  float* sp_all = stage_all + 4 * 32 * STG_LD;                                              // [SP_FLOATS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -376,6 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           mask_bits[0] = b.x; mask_bits[1] = b.y; mask_bits[2] = b.z; mask_bits[3] = b.w;
         }
       }
+      stage_epi_params<EPI>(ep, sp_all, seed, threadIdx.x - 64);
       float acc[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) acc[j] = 0.f;
@@ -397,7 +445,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) mbar_arrive(&corr_empty[cb]);
         if (++cb == 2) { cb = 0; cb_phase ^= 1u; }
       }
-      epilogue_row<EPI>(ep, acc, stage_all + (warp - 2) * 32 * STG_LD, lane, seed, m0 + quad * 32, n0, gs.M, mask_bits);
+      epilogue_row<EPI>(ep, acc, stage_all + (warp - 2) * 32 * STG_LD, sp_all, lane, seed, m0 + quad * 32, n0, gs.M,
+                        mask_bits);
     }
   }
   tcgen05_fence_before();

@@ -16,7 +16,8 @@ constexpr int TC_TILE_BYTES = 128 * TC_BK * 4;   // 16 KB
 constexpr int TC_A_HI = 0, TC_A_LO = TC_TILE_BYTES, TC_B_HI = 2 * TC_TILE_BYTES, TC_B_LO = 3 * TC_TILE_BYTES;
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;  // 64 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                              4 * 32 * 36 * 4 /*epilogue store staging, 4 warps x [32][36] floats*/;
+                              4 * 32 * 36 * 4 /*epilogue store staging, 4 warps x [32][36] floats*/ +
+                              (384 + 8 * 128 + 8) * 4 /*per-seed epilogue parameters (LN scale/bias, Q-head)*/;
 #define PQN_TC_MAX_A 8
 
 enum Epilogue : int { EPI_STORE = 0, EPI_LN_TRAIN = 1, EPI_LN_HEAD = 2, EPI_RELU_MASK = 3, EPI_RELU_BITS = 4 };
