@@ -206,15 +206,36 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[1
   }
 }
 
-// acc[0..128) += the 128 fp32 columns of this thread's TMEM lane at `row_addr`
+// acc[0..128) (+)= the 128 fp32 columns of this thread's TMEM lane at `row_addr`.  The loads are issued back to
+// back and awaited once (FIRST: all four 32-column loads straight into acc; otherwise two at a time, 64 staging
+// registers) -- the per-load round trip to TMEM was the longest part of the epilogue's dependent chain.
+template <bool FIRST>
 __device__ __forceinline__ void tmem_accumulate_row(uint32_t row_addr, float (&acc)[128]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(row_addr + c * 32, v);
+  if constexpr (FIRST) {
+    uint32_t v0[32], v1[32], v2[32], v3[32];
+    tmem_ld_32x32b_x32(row_addr, v0);
+    tmem_ld_32x32b_x32(row_addr + 32, v1);
+    tmem_ld_32x32b_x32(row_addr + 64, v2);
+    tmem_ld_32x32b_x32(row_addr + 96, v3);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+    for (int j = 0; j < 32; ++j) {
+      acc[j] = __uint_as_float(v0[j]); acc[32 + j] = __uint_as_float(v1[j]);
+      acc[64 + j] = __uint_as_float(v2[j]); acc[96 + j] = __uint_as_float(v3[j]);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32b_x32(row_addr + c * 64, v0);
+      tmem_ld_32x32b_x32(row_addr + c * 64 + 32, v1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        acc[c * 64 + j] += __uint_as_float(v0[j]);
+        acc[c * 64 + 32 + j] += __uint_as_float(v1[j]);
+      }
+    }
   }
 }
 
@@ -326,6 +347,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       uint32_t phase = 0;
       int mb = 0, cb = 0;
       uint32_t mb_phase = 0, cb_phase = 0;
+      // Short-K mode (k_blocks <= TC_PROMOTE, e.g. dgrad with K = 128): the whole tile is one promotion chunk, so the
+      // correction terms share the main accumulator (a chain of <= 48 MMAs keeps the truncation drift ~1e-6) and the
+      // four 128-column TMEM regions form one ring of accumulators: the epilogue reads each tile once.
+      const bool single_acc = gs.split3 && gs.k_blocks <= TC_PROMOTE;
+      if (single_acc) {
+        int ab = 0;
+        uint32_t ab_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          uint64_t* e_bar = ab < 2 ? &main_empty[ab] : &corr_empty[ab - 2];
+          uint64_t* f_bar = ab < 2 ? &main_full[ab] : &corr_full[ab - 2];
+          mbar_wait(e_bar, ab_phase ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t d_acc = tmem_base + ab * 128;
+          bool first = true;
+          for (int kb = 0; kb < gs.k_blocks; ++kb) {
+            mbar_wait(&full[stage], phase);
+            if (gs.a_lo_inline) mbar_wait(&lo_full[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+              const uint64_t a_hi = make_sdesc<A_MN>(sb + TC_A_HI, ks), a_lo = make_sdesc<A_MN>(sb + TC_A_LO, ks);
+              const uint64_t b_hi = make_sdesc<B_MN>(sb + TC_B_HI, ks), b_lo = make_sdesc<B_MN>(sb + TC_B_LO, ks);
+              umma_tf32(d_acc, a_lo, b_hi, idesc, first ? 0u : 1u);
+              umma_tf32(d_acc, a_hi, b_lo, idesc, 1u);
+              umma_tf32(d_acc, a_hi, b_hi, idesc, 1u);
+              first = false;
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(f_bar);
+          if (++ab == 4) { ab = 0; ab_phase ^= 1u; }
+        }
+      } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const uint32_t d_corr = tmem_base + 256 + cb * 128;
         if (gs.split3) {
@@ -405,9 +461,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // ===================== epilogue warps (2..5) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access (warp id % 4)
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    int mb = 0, cb = 0;
-    uint32_t mb_phase = 0, cb_phase = 0;
+    int mb = 0, cb = 0, ab = 0;
+    uint32_t mb_phase = 0, cb_phase = 0, ab_phase = 0;
     const int partials = (gs.k_blocks + TC_PROMOTE - 1) / TC_PROMOTE;
+    const bool single_acc = gs.split3 && gs.k_blocks <= TC_PROMOTE;  // see the MMA issuer
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int seed = tile / tiles_per_seed;
       const int rem = tile - seed * tiles_per_seed;
@@ -425,12 +482,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       stage_epi_params<EPI>(ep, sp_all, seed, threadIdx.x - 64);
       float acc[128];
-#pragma unroll
-      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      if (single_acc) {
+        uint64_t* e_bar = ab < 2 ? &main_empty[ab] : &corr_empty[ab - 2];
+        uint64_t* f_bar = ab < 2 ? &main_full[ab] : &corr_full[ab - 2];
+        mbar_wait(f_bar, ab_phase);
+        tcgen05_fence_after();
+        tmem_accumulate_row<true>(tmem_base + ab * 128 + lane_off, acc);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(e_bar);
+        if (++ab == 4) { ab = 0; ab_phase ^= 1u; }
+      } else {
       for (int pi = 0; pi < partials; ++pi) {
         mbar_wait(&main_full[mb], mb_phase);
         tcgen05_fence_after();
-        tmem_accumulate_row(tmem_base + mb * 128 + lane_off, acc);
+        if (pi == 0) tmem_accumulate_row<true>(tmem_base + mb * 128 + lane_off, acc);
+        else tmem_accumulate_row<false>(tmem_base + mb * 128 + lane_off, acc);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&main_empty[mb]);
@@ -439,11 +506,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (gs.split3) {
         mbar_wait(&corr_full[cb], cb_phase);
         tcgen05_fence_after();
-        tmem_accumulate_row(tmem_base + 256 + cb * 128 + lane_off, acc);
+        tmem_accumulate_row<false>(tmem_base + 256 + cb * 128 + lane_off, acc);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&corr_empty[cb]);
         if (++cb == 2) { cb = 0; cb_phase ^= 1u; }
+      }
       }
       epilogue_row<EPI>(ep, acc, stage_all + (warp - 2) * 32 * STG_LD, sp_all, lane, seed, m0 + quad * 32, n0, gs.M,
                         mask_bits);
