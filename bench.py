@@ -51,10 +51,14 @@ ALG_FLOPS = {  # per launch-unit sample, by kernel
     "tc_dense_fwd": 2 * 1024 * 128, "tc_wgrad": 2 * 1024 * 128, "tc_dgrad": 2 * 1024 * 128,
     "conv_fwd": 2 * 64 * 36 * 16, "conv_bwd": 2 * 2 * 64 * 36 * 16,
 }
-ALG_BYTES = {  # HBM bytes per sample per launch the kernel must move (h1 + its tf32-lo operand etc.)
-    "tc_dense_fwd": 2 * 4096 + 2 * 512, "tc_wgrad": 2 * 4096 + 2 * 512, "tc_dgrad": 2 * 512 + 2 * 4096,
-    "conv_fwd": 64 + 2 * 4096, "conv_bwd": 64 + 4096,
+ALG_BYTES = {  # HBM bytes per sample per launch the kernel must move
+    "tc_dense_fwd": 4096 + 2 * 512 + 4,          # h1 in; h2 + xhat2 + rstd out (training epilogue)
+    "tc_wgrad": 4096 + 2 * 512,                  # h1 in; dz2 + its tf32-lo in
+    "tc_dgrad": 2 * 512 + 128 + 4096,            # dz2 (+lo), packed ReLU mask in; dy1 out
+    "conv_fwd": 64 + 4096,                       # rollout variant; training adds xhat (4096) + rstd (256) + mask (128)
+    "conv_bwd": 64 + 2 * 4096 + 256,             # obs, dy1, xhat, rstd in
 }
+CONV_FWD_TRAIN_BYTES = 64 + 2 * 4096 + 256 + 128
 
 
 def base_config(num_updates, num_envs=NUM_ENVS, test=False):
@@ -294,13 +298,13 @@ def run_gpu(args, rank, world, local_rank):
     except Exception:
         pass
     # dram__bytes_read+write per launch from the committed `ncu --set full` capture of the same workload
-    # (profiles/r1h_ncu_launch_table.md); keys = bench kernel ids
+    # (profiles/r1k_ncu_launch_table.md); keys = bench kernel ids
     traffic_map = {}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1h_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1k_traffic.json")))
         traffic_map = {"conv_bwd": tj.get("void conv_bwd_mma_kernel<4>"), "conv_fwd": tj.get("void conv_fwd_mma_kernel<4, 1>"),
                        "tc_dense_fwd": tj.get("void tc_gemm_kernel<0, 1, 1>"), "tc_wgrad": tj.get("void tc_gemm_kernel<1, 1, 0>"),
-                       "tc_dgrad": tj.get("void tc_gemm_kernel<0, 0, 3>"), "row_bwd": tj.get("void row_bwd_kernel<128, 1>")}
+                       "tc_dgrad": tj.get("void tc_gemm_kernel<0, 0, 4>"), "row_bwd": tj.get("void row_bwd_kernel<128, 1>")}
     except Exception:
         pass
     total_k_ms = sum(v[0] for v in prof.values()) or 1.0
@@ -308,22 +312,40 @@ def run_gpu(args, rank, world, local_rank):
                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
     roof = None
-    if dom == "conv_fwd":
-        # the conv forward is a store-bound kernel: 64 B of packed obs in, h1 + h1_lo (+ xhat, rstd when training) out
+    if dom == "conv_bwd":
+        # conv backward (per minibatch launch): reads obs + dy1 + xhat + rstd, writes only the reduced gradients
         d_ms, d_n = prof[dom]
         mb = NUM_STEPS * args.envs // 32
-        n_roll = (NUM_STEPS + 1) * args.steps
-        n_mb = d_n - n_roll
-        nbytes = S * (n_roll * args.envs * (64 + 2 * 4096) + n_mb * mb * (64 + 3 * 4096 + 256))
+        nbytes = S * d_n * mb * ALG_BYTES["conv_bwd"]
         hbm = peaks.get("hbm_gbs", 6650.0)
         gbs = nbytes / (d_ms / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s",
                 "frac": round(gbs / hbm, 4),
                 "traffic": traffic_map.get(dom) if (S == 128 and args.envs == NUM_ENVS) else None,
-                "traffic_source": "profiles/r1h_ncu_launch_table.md (ncu --set full, training-variant launch: 6.52 GB written)",
+                "traffic_source": "profiles/r1k_ncu_launch_table.md (ncu --set full, same workload: 4.50 GB read per launch)",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
+                "note": "LayerNorm backward + conv weight gradient (mma.sync, im2col bit patches) from cp.async-staged rows; "
+                        "algorithmic bytes = 8.5 KB in per sample; ncu: issue slots 61% busy, shared-memory pipe 72% -- "
+                        "instruction/shared-memory bound above the HBM floor",
+                "avg_launch_ms": round(d_ms / d_n, 4), "launches": d_n}
+    elif dom == "conv_fwd":
+        # the conv forward: 64 B of packed obs in, h1 (+ xhat, rstd, packed ReLU mask when training) out
+        d_ms, d_n = prof[dom]
+        mb = NUM_STEPS * args.envs // 32
+        n_roll = (NUM_STEPS + 1) * args.steps
+        n_mb = d_n - n_roll
+        nbytes = S * (n_roll * args.envs * ALG_BYTES["conv_fwd"] + n_mb * mb * CONV_FWD_TRAIN_BYTES)
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        gbs = nbytes / (d_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s",
+                "frac": round(gbs / hbm, 4),
+                "traffic": traffic_map.get(dom) if (S == 128 and args.envs == NUM_ENVS) else None,
+                "traffic_source": "profiles/r1k_ncu_launch_table.md (ncu --set full, training-variant launch: 4.44 GB "
+                                  "written; the rollout variant writes 2.09 GB)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                 "note": "conv3x3+LayerNorm+ReLU on warp-level tf32 MMA from bit-packed obs; algorithmic bytes = 64 B in + "
-                        "8 KB out (rollout) or 12.5 KB out (training: + xhat, rstd) per sample",
+                        "4 KB out (rollout) or 8.4 KB out (training: + xhat, rstd, ReLU bitmask) per sample; ncu: issue "
+                        "slots 64-65% busy, mma.sync pipe 33-45% -- instruction-bound above the HBM floor",
                 "avg_launch_ms": round(d_ms / d_n, 4), "launches": d_n}
     elif dom in ALG_FLOPS:
         per_launch_samples = {"dense_fwd": None}.get(dom)
@@ -344,11 +366,12 @@ def run_gpu(args, rank, world, local_rank):
         roof = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
                 "frac": round(achieved / peak, 4),
                 "traffic": traffic_map.get(dom) if (S == 128 and args.envs == NUM_ENVS) else None,
-                "traffic_source": "profiles/r1h_ncu_launch_table.md (ncu --set full, same workload, training-step launch)",
+                "traffic_source": "profiles/r1k_ncu_launch_table.md (ncu --set full, same workload, training-step launch)",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PF sustained (of fallback)",
                 "note": ("fp32-accurate 3xTF32 on tcgen05: each algorithmic FLOP costs 3 tf32 MMAs at half the bf16 "
-                         "rate, so the fp32-equivalent tensor peak is peak/6 = %.0f TFLOP/s; the kernel also streams "
-                         "its A operand (x and x_lo) from HBM" % (peak / 6.0)) if dom.startswith("tc_") else
+                         "rate, so the fp32-equivalent tensor peak is peak/6 = %.0f TFLOP/s; measured limiter is operand "
+                         "feed (shared-memory reads of six operand tiles per k-step + ~40 B/clk/SM L2 ingest), see "
+                         "DESIGN.md section 3" % (peak / 6.0)) if dom.startswith("tc_") else
                         ("warp-level tf32 tensor-core MMA (mma.sync m16n8k8, A operand built from the packed observation "
                          "bits, weights/dz split hi+lo => 2 MMAs per algorithmic one); instruction-issue bound, fraction "
                          "is against the dense bf16 tcgen05 peak") if dom.startswith("conv_") else

@@ -118,7 +118,8 @@ def test_config_composition_matches_hydra_semantics():
 
 def test_library_sass_has_blackwell_tensor_and_tma_ops():
     """The built .so must contain the sm_100a-native paths: tcgen05.mma (UTC*MMA), TMEM loads (LDTM),
-    TMA tensor loads (UTMALDG) and the warp-level tf32 MMA of the conv kernels."""
+    TMA tensor loads (UTMALDG), the warp-level tf32 MMA of the conv kernels, the async-proxy fence of the in-kernel
+    operand converter and the cp.async staging of the conv backward."""
     import shutil
     import subprocess
     from purejaxql_b200 import build
@@ -127,5 +128,5 @@ def test_library_sass_has_blackwell_tensor_and_tma_ops():
     so = build.build()
     sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
     assert "sm_100a" in sass or "SM100" in sass.upper()
-    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR", "HMMA"):
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR", "HMMA", "FENCE.VIEW.ASYNC", "LDGSTS"):
         assert mnemonic in sass, f"{mnemonic} missing from the SASS of {so}"
