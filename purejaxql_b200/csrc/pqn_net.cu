@@ -425,7 +425,6 @@ __global__ void __launch_bounds__(GT) dgrad_kernel(const float* __restrict__ DZ,
 //   then LayerNorm backward -> DZ, accumulating dscale, dbias and db (= sum dz).
 // grid = (ceil(rows/ROWS_PER_CTA), S)
 // ---------------------------------------------------------------------------
-constexpr int RB_ROWS = 128;  // rows per CTA (8 warps x 16)
 
 template <int N, bool HEAD>
 __global__ void __launch_bounds__(256) row_bwd_kernel(
@@ -439,15 +438,20 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
   float* s_dsc = smem;            // [N]
   float* s_dbi = smem + N;        // [N]
   float* s_db = smem + 2 * N;     // [N]
-  float* s_dhw = smem + 3 * N;    // [A*N]  (HEAD)
-  float* s_dhb = s_dhw + (HEAD ? A * N : 0);  // [A]
-  float* s_ls = s_dhb + (HEAD ? A : 0);       // [2] loss, qsa
+  float* s_hw = smem + 3 * N;     // [A][N]  head weights, transposed copy (HEAD)
+  float* s_dhw = s_hw + (HEAD ? A * N : 0);   // [8 warps][A][N]  warp-private head-weight gradient slices (HEAD);
+                                              // 16-byte aligned for the float4 accesses, scalars go last
+  float* s_dhb = s_dhw + (HEAD ? 8 * A * N : 0);  // [A]
+  float* s_ls = s_dhb + (HEAD ? A : 0);           // [2] loss, qsa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int seed = blockIdx.y;
-  const int nsm = 3 * N + (HEAD ? A * N + A + 2 : 0);
+  const float* __restrict__ prm = params + (int64_t)seed * P;
+  const int nsm = 3 * N + (HEAD ? A * N + A + 2 + 8 * A * N : 0);
   for (int i = tid; i < nsm; i += 256) smem[i] = 0.f;
   __syncthreads();
-  const float* __restrict__ prm = params + (int64_t)seed * P;
+  if (HEAD)
+    for (int i = tid; i < A * N; i += 256) s_hw[(i % A) * N + i / A] = __ldg(prm + off_hw + i);
+  __syncthreads();
   float scale[F];
 #pragma unroll
   for (int j = 0; j < F; ++j) scale[j] = __ldg(prm + off_scale + (j >> 2) * 128 + lane * 4 + (j & 3));
@@ -456,10 +460,10 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
   for (int j = 0; j < F; ++j) a_dsc[j] = a_dbi[j] = a_db[j] = 0.f;
   float a_loss = 0.f, a_qsa = 0.f;
   const float invB = 1.0f / (float)rows;
+  float* my_dhw = s_dhw + warp * A * N;
 
-  for (int rr = warp; rr < RB_ROWS; rr += 8) {
-    const int row = blockIdx.x * RB_ROWS + rr;
-    if (row >= rows) break;
+  // grid-stride over the seed's rows, one row per warp (grid.x is sized in whole waves, see conv_mma_ctas)
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const int64_t grow = (int64_t)seed * rows + row;
     float h[F], xh[F], dy[F];
 #pragma unroll
@@ -481,11 +485,12 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
       float pq = 0.f;
       float wcol[F];
 #pragma unroll
-      for (int j = 0; j < F; ++j) {
-        const int f = (j >> 2) * 128 + lane * 4 + (j & 3);
-        wcol[j] = __ldg(prm + off_hw + (int64_t)f * A + act);
-        pq = fmaf(h[j], wcol[j], pq);
+      for (int c = 0; c < F / 4; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(s_hw + act * N + c * 128 + lane * 4);
+        wcol[4 * c] = v.x; wcol[4 * c + 1] = v.y; wcol[4 * c + 2] = v.z; wcol[4 * c + 3] = v.w;
       }
+#pragma unroll
+      for (int j = 0; j < F; ++j) pq = fmaf(h[j], wcol[j], pq);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) pq += __shfl_xor_sync(0xffffffffu, pq, o);
       const float q_sa = pq + __ldg(prm + off_hb + act);
@@ -497,11 +502,15 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
         atomicAdd(s_dhb + act, dq);
       }
 #pragma unroll
-      for (int j = 0; j < F; ++j) {
-        const int f = (j >> 2) * 128 + lane * 4 + (j & 3);
-        atomicAdd(s_dhw + act * N + f, h[j] * dq);
-        dy[j] = h[j] > 0.f ? dq * wcol[j] : 0.f;
+      for (int c = 0; c < F / 4; ++c) {  // warp-private slice: plain read-modify-write, no atomics
+        float4* dst = reinterpret_cast<float4*>(my_dhw + act * N + c * 128 + lane * 4);
+        float4 v = *dst;
+        v.x = fmaf(h[4 * c], dq, v.x); v.y = fmaf(h[4 * c + 1], dq, v.y);
+        v.z = fmaf(h[4 * c + 2], dq, v.z); v.w = fmaf(h[4 * c + 3], dq, v.w);
+        *dst = v;
       }
+#pragma unroll
+      for (int j = 0; j < F; ++j) dy[j] = h[j] > 0.f ? dq * wcol[j] : 0.f;
     } else {
 #pragma unroll
       for (int c = 0; c < F / 4; ++c) {
@@ -566,7 +575,9 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
     // s_dhw is [A][N]; the parameter is [N][A]
     for (int i = tid; i < A * N; i += 256) {
       const int a = i / N, f = i - a * N;
-      const float v = s_dhw[i];
+      float v = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) v += s_dhw[wv * A * N + i];
       if (v != 0.f) atomicAdd(g + off_hw + (int64_t)f * A + a, v);
     }
     if (tid < A) atomicAdd(g + off_hb + tid, s_dhb[tid]);
@@ -1858,6 +1869,20 @@ static int launch_conv_bwd_mma(dim3 grid, cudaStream_t st, const uint32_t* obs, 
   return 0;
 }
 
+// dynamic shared memory of row_bwd_kernel<N, HEAD> (floats: 3N reductions; HEAD: [A][N] weights, A + 2 scalars and
+// eight warp-private [A][N] gradient slices)
+static size_t row_bwd_smem(int N, int A, bool head) {
+  return (size_t)(3 * N + (head ? A * N + A + 2 + 8 * A * N : 0)) * sizeof(float);
+}
+
+template <int N, bool HEAD, typename... Args>
+static void launch_row_bwd(dim3 grid, int A, cudaStream_t st, Args... args) {
+  const size_t sm = row_bwd_smem(N, A, HEAD);
+  if (sm > 48 * 1024) cudaFuncSetAttribute(row_bwd_kernel<N, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  LaunchScope _ls(K_ROW_BWD, st);
+  row_bwd_kernel<N, HEAD><<<grid, 256, sm, st>>>(args...);
+}
+
 // CTAs per seed for the warp-per-sample conv kernels (grid = per_seed x S).  `resident` = CTAs the GPU holds at once
 // (SMs x CTAs/SM): the grid is sized to fill whole waves of that many CTAs -- 1280 CTAs on 296 slots would run a
 // fifth, 32%-full wave -- while staying near 4 waves so that per-CTA setup (weight fragments) stays amortised.
@@ -2119,8 +2144,8 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
       launch_dense<1>(128, dim3(cdiv(rows, 128), S), st, w.h1, rows * FLAT_CNN, FLAT_CNN, params, P, L.d0_w, L.d0_b,
                       L.ln1_scale, L.ln1_bias, 0, 0, A, w.h2, w.xhat2, w.rstd2, nullptr, R, FLAT_CNN);
     }
-    const size_t sm = (size_t)(3 * 128 + A * 128 + A + 2) * sizeof(float);
-    { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, true><<<dim3(cdiv(rows, RB_ROWS), S), 256, sm, st>>>(
+    const dim3 rbg(conv_mma_ctas(S, R, 4), S);
+    { launch_row_bwd<128, true>(rbg, A, st,
         w.h2, w.xhat2, w.rstd2, nullptr, w.dz2, use_tc ? w.dz2_lo : nullptr, params, grads, P, L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d0_b,
         L.head_w, L.head_b, A, gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, R); }
     if (use_tc) {
@@ -2160,19 +2185,17 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
                                                                     bn_sums, R, D); }
     launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.xg, rows * D, D, params, P, L.d0_w, L.d0_b, L.ln0_scale,
                     L.ln0_bias, 0, 0, A, w.h0, w.xhat0, w.rstd0, nullptr, R, D);
-    const size_t smh = (size_t)(3 * H + A * H + A + 2) * sizeof(float);
-    const size_t sml = (size_t)(3 * H) * sizeof(float);
-    dim3 rg(cdiv(rows, RB_ROWS), S);
+    const dim3 rbg(conv_mma_ctas(S, R, 4), S);
     if (d->layers == 2) {
       launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.h0, rows * H, H, params, P, L.d1_w, L.d1_b, L.ln1_scale,
                       L.ln1_bias, 0, 0, A, w.hh1, w.xhat1, w.rstd1, nullptr, R, H);
       if (H == 128)
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, params, grads, P,
+        { launch_row_bwd<128, true>(rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, params, grads, P,
                                                         L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }
       else
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, params, grads, P,
+        { launch_row_bwd<256, true>(rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, params, grads, P,
                                                         L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }
@@ -2183,11 +2206,11 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
       { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(w.dzl, rows * H, H, params, P, L.d1_w, w.h0,
                                                                      w.dh0, rows * H, R, H); }
       if (H == 128)
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, params, grads, P,
+        { launch_row_bwd<128, false>(rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, params, grads, P,
                                                          L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
                                                          nullptr, nullptr, nullptr, 0, nullptr, nullptr, R); }
       else
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, false><<<rg, 256, sml, st>>>(nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, params, grads, P,
+        { launch_row_bwd<256, false>(rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, params, grads, P,
                                                          L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
                                                          nullptr, nullptr, nullptr, 0, nullptr, nullptr, R); }
       const int sp0 = wgrad_splits(H / 128, S, R);
@@ -2195,12 +2218,12 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
                                                                         P, L.d0_w, R, D, sp0); }
     } else {
       if (H == 128)
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<128, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, params, grads, P,
+        { launch_row_bwd<128, true>(rbg, A, st, w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, params, grads, P,
                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }
       else
-        { LaunchScope _ls(K_ROW_BWD, st); row_bwd_kernel<256, true><<<rg, 256, smh, st>>>(w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, params, grads, P,
+        { launch_row_bwd<256, true>(rbg, A, st, w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, params, grads, P,
                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }
