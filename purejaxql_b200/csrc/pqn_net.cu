@@ -913,18 +913,6 @@ struct ConvMma {
   static constexpr int MT = (TAPS + 15) / 16;  // m-blocks of the weight-gradient GEMM (taps)
 };
 
-// bit offset of tap (di,dj,c) relative to the first channel bit of the output pixel's top-left input pixel
-template <int C>
-__device__ __forceinline__ int tap_bit_offset(int tap) {
-  const int c = tap % C, r = tap / C;
-  return ((r / 3) * 10 + (r % 3)) * C + c;
-}
-
-__device__ __forceinline__ uint32_t obs_bit_f32(const uint32_t* __restrict__ so, int idx, bool valid) {
-  const uint32_t bit = (so[idx >> 5] >> (idx & 31)) & 1u;
-  return (valid && bit) ? 0x3F800000u : 0u;  // 1.0f / 0.0f as tf32 bit patterns
-}
-
 // im2col "patch" of one output pixel as bits: bit k = tap k = (di*3+dj)*C + c, i.e. obs bit
 // ((y+di)*10 + x+dj)*C + c.  9C <= 90 bits -> PatchCfg::WORDS words; bits beyond 9C are zero.  Built once per
 // sample into shared memory (patch[pixel][word]); the MMA fragment builders then test bits with a shift instead of
@@ -992,77 +980,6 @@ __device__ __forceinline__ void conv_mma_load_weights(const float* __restrict__ 
   }
 }
 
-// conv pre-activation of the 16 pixels of m-block `mb` (pixel = 16*mb + g [+8]); z[h][0..3] in C-fragment layout:
-// z[h][0],z[h][1] -> pixel g, channels 8h+2t, 8h+2t+1 ; z[h][2],z[h][3] -> pixel g+8, same channels.
-// (forward kernel: fragment bits straight from the packed observation; the patch staging only pays off in the
-// backward kernel, which reuses every patch for the weight-gradient fragments as well)
-template <int C>
-__device__ __forceinline__ void conv_mma_block_direct(const uint32_t* __restrict__ so, const float2* __restrict__ wb_hi,
-                                               const float2* __restrict__ wb_lo, const float* __restrict__ cb, int mb,
-                                               int lane, const int (&off0)[ConvMma<C>::KS],
-                                               const int (&off1)[ConvMma<C>::KS], float (&z)[2][4]) {
-  using M = ConvMma<C>;
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    z[h][0] = z[h][2] = cb[8 * h + 2 * t];
-    z[h][1] = z[h][3] = cb[8 * h + 2 * t + 1];
-  }
-  const int p0 = 16 * mb + g, p1 = p0 + 8;
-  const int base0 = ((p0 >> 3) * 10 + (p0 & 7)) * C, base1 = ((p1 >> 3) * 10 + (p1 & 7)) * C;
-#pragma unroll
-  for (int ks = 0; ks < M::KS; ++ks) {
-    const bool v0 = ks * 8 + t < M::TAPS, v1 = ks * 8 + t + 4 < M::TAPS;
-    uint32_t a[4];
-    a[0] = obs_bit_f32(so, base0 + off0[ks], v0);
-    a[1] = obs_bit_f32(so, base1 + off0[ks], v0);
-    a[2] = obs_bit_f32(so, base0 + off1[ks], v1);
-    a[3] = obs_bit_f32(so, base1 + off1[ks], v1);
-    if (__ballot_sync(0xffffffffu, (a[0] | a[1] | a[2] | a[3]) != 0u) == 0u) continue;  // empty patch slice
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float2 bl = wb_lo[(ks * 2 + h) * 32 + lane];
-      mma_tf32_16n8k8(z[h], a, __float_as_uint(bl.x), __float_as_uint(bl.y));
-      const float2 bh = wb_hi[(ks * 2 + h) * 32 + lane];
-      mma_tf32_16n8k8(z[h], a, __float_as_uint(bh.x), __float_as_uint(bh.y));
-    }
-  }
-}
-
-template <int C>
-__device__ __forceinline__ void conv_mma_block(const uint32_t* __restrict__ patch, const float2* __restrict__ wb_hi,
-                                               const float2* __restrict__ wb_lo, const float* __restrict__ cb, int mb,
-                                               int lane, float (&z)[2][4]) {
-  using M = ConvMma<C>;
-  constexpr int PW = PatchCfg<C>::WORDS;
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    z[h][0] = z[h][2] = cb[8 * h + 2 * t];
-    z[h][1] = z[h][3] = cb[8 * h + 2 * t + 1];
-  }
-  const int p0 = 16 * mb + g, p1 = p0 + 8;
-  uint32_t q0[PW], q1[PW];
-#pragma unroll
-  for (int k = 0; k < PW; ++k) { q0[k] = patch[p0 * PW + k]; q1[k] = patch[p1 * PW + k]; }
-#pragma unroll
-  for (int ks = 0; ks < M::KS; ++ks) {
-    // taps 8ks .. 8ks+7 live in one patch word (32 % 8 == 0); bits beyond 9C are zero
-    const uint32_t w0 = q0[(8 * ks) >> 5], w1 = q1[(8 * ks) >> 5];
-    const int sh = ((8 * ks) & 31) + t;
-    uint32_t a[4];
-    a[0] = bit_f32(w0, sh); a[1] = bit_f32(w1, sh); a[2] = bit_f32(w0, sh + 4); a[3] = bit_f32(w1, sh + 4);
-    if (__ballot_sync(0xffffffffu, (a[0] | a[1] | a[2] | a[3]) != 0u) == 0u) continue;  // empty patch slice
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float2 bl = wb_lo[(ks * 2 + h) * 32 + lane];
-      mma_tf32_16n8k8(z[h], a, __float_as_uint(bl.x), __float_as_uint(bl.y));
-      const float2 bh = wb_hi[(ks * 2 + h) * 32 + lane];
-      mma_tf32_16n8k8(z[h], a, __float_as_uint(bh.x), __float_as_uint(bh.y));
-    }
-  }
-}
-
 // ---- exponent-coded im2col fragments (forward kernel) --------------------------------------------------------
 // A tf32 MMA operand only has to be *some* exactly known value when the input bit is set, not 1.0: a word whose
 // bits 23..30 (the fp32 exponent field) hold eight tap bits turns into an A element with ONE instruction,
@@ -1096,7 +1013,8 @@ __device__ __forceinline__ void build_exp_patch(const uint32_t* __restrict__ so,
 }
 
 // conv pre-activation of the 32 pixels of m-blocks 2*mbp and 2*mbp+1 (two blocks share every B fragment load);
-// z[i][h][0..3] is the C fragment of block 2*mbp+i as in conv_mma_block.
+// z[i][h][0..3] is the C fragment of block mb = 2*mbp+i (pixel = 16*mb + g [+8]):
+// z[i][h][0], z[i][h][1] -> pixel g, channels 8h+2t, 8h+2t+1 ; z[i][h][2], z[i][h][3] -> pixel g+8, same channels.
 template <int C>
 __device__ __forceinline__ void conv_mma_block2_exp(const uint32_t* __restrict__ xp, const float2* __restrict__ wb_hi,
                                                     const float2* __restrict__ wb_lo, const float* __restrict__ cb,
