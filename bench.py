@@ -49,10 +49,12 @@ FLOPS_FWD_PER_SAMPLE = 2 * (64 * 36 * 16 + 1024 * 128 + 128 * 3)        # conv +
 ALG_FLOPS = {  # per launch-unit sample, by kernel
     "dense_fwd": 2 * 1024 * 128, "wgrad": 2 * 1024 * 128, "dgrad": 2 * 1024 * 128,
     "tc_dense_fwd": 2 * 1024 * 128, "tc_wgrad": 2 * 1024 * 128, "tc_dgrad": 2 * 1024 * 128,
+    "tc_dense_fwd_head": 2 * 1024 * 128 + 2 * 128 * 3,
     "conv_fwd": 2 * 64 * 36 * 16, "conv_bwd": 2 * 2 * 64 * 36 * 16,
 }
 ALG_BYTES = {  # HBM bytes per sample per launch the kernel must move
     "tc_dense_fwd": 4096 + 2 * 512 + 4,          # h1 in; h2 + xhat2 + rstd out (training epilogue)
+    "tc_dense_fwd_head": 4096 + 12,              # h1 in; q[A] out (rollout epilogue)
     "tc_wgrad": 4096 + 2 * 512,                  # h1 in; dz2 + its tf32-lo in
     "tc_dgrad": 2 * 512 + 128 + 4096,            # dz2 (+lo), packed ReLU mask in; dy1 out
     "conv_fwd": 64 + 4096,                       # rollout variant; training adds xhat (4096) + rstd (256) + mask (128)
@@ -303,6 +305,8 @@ def run_gpu(args, rank, world, local_rank):
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1k_traffic.json")))
         traffic_map = {"conv_bwd": tj.get("void conv_bwd_mma_kernel<4>"), "conv_fwd": tj.get("void conv_fwd_mma_kernel<4, 1>"),
+                       "conv_fwd_infer": tj.get("void conv_fwd_mma_kernel<4, 0>"),
+                       "tc_dense_fwd_head": tj.get("void tc_gemm_kernel<0, 1, 2>"),
                        "tc_dense_fwd": tj.get("void tc_gemm_kernel<0, 1, 1>"), "tc_wgrad": tj.get("void tc_gemm_kernel<1, 1, 0>"),
                        "tc_dgrad": tj.get("void tc_gemm_kernel<0, 0, 4>"), "row_bwd": tj.get("void row_bwd_kernel<128, 1>")}
     except Exception:
@@ -328,20 +332,19 @@ def run_gpu(args, rank, world, local_rank):
                         "algorithmic bytes = 8.5 KB in per sample; ncu: issue slots 61% busy, shared-memory pipe 72% -- "
                         "instruction/shared-memory bound above the HBM floor",
                 "avg_launch_ms": round(d_ms / d_n, 4), "launches": d_n}
-    elif dom == "conv_fwd":
-        # the conv forward: 64 B of packed obs in, h1 (+ xhat, rstd, packed ReLU mask when training) out
+    elif dom in ("conv_fwd", "conv_fwd_infer"):
+        # the conv forward: 64 B of packed obs in, h1 (+ xhat, rstd, packed ReLU mask when training) out.
+        # "conv_fwd" = training launches (one per minibatch step), "conv_fwd_infer" = rollout launches (E envs each)
         d_ms, d_n = prof[dom]
         mb = NUM_STEPS * args.envs // 32
-        n_roll = (NUM_STEPS + 1) * args.steps
-        n_mb = d_n - n_roll
-        nbytes = S * (n_roll * args.envs * ALG_BYTES["conv_fwd"] + n_mb * mb * CONV_FWD_TRAIN_BYTES)
+        nbytes = S * d_n * (mb * CONV_FWD_TRAIN_BYTES if dom == "conv_fwd" else args.envs * ALG_BYTES["conv_fwd"])
         hbm = peaks.get("hbm_gbs", 6650.0)
         gbs = nbytes / (d_ms / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s",
                 "frac": round(gbs / hbm, 4),
                 "traffic": traffic_map.get(dom) if (S == 128 and args.envs == NUM_ENVS) else None,
-                "traffic_source": "profiles/r1k_ncu_launch_table.md (ncu --set full, training-variant launch: 4.44 GB "
-                                  "written; the rollout variant writes 2.09 GB)",
+                "traffic_source": "profiles/r1k_ncu_launch_table.md (ncu --set full: the training variant writes 4.44 GB "
+                                  "per launch, the rollout variant 2.09 GB)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                 "note": "conv3x3+LayerNorm+ReLU on warp-level tf32 MMA from bit-packed obs; algorithmic bytes = 64 B in + "
                         "4 KB out (rollout) or 8.4 KB out (training: + xhat, rstd, ReLU bitmask) per sample; ncu: issue "
@@ -352,10 +355,12 @@ def run_gpu(args, rank, world, local_rank):
         # samples per launch: minibatch launches process S*4096 samples (T*E/32), rollout forwards S*E
         d_ms, d_n = prof[dom]
         mb = NUM_STEPS * args.envs // 32
-        if dom in ("dense_fwd", "conv_fwd", "tc_dense_fwd"):
+        if dom == "dense_fwd":  # FFMA path: rollout and training launches share one id
             n_roll = (NUM_STEPS + 1) * args.steps
             n_mb = d_n - n_roll
             samples = S * (n_roll * args.envs + n_mb * mb)
+        elif dom == "tc_dense_fwd_head":  # rollout forwards, E envs each
+            samples = S * d_n * args.envs
         else:
             samples = S * d_n * mb
         flops = ALG_FLOPS[dom] * samples
@@ -394,6 +399,20 @@ def run_gpu(args, rank, world, local_rank):
                          f"{sample_envs} envs x {NUM_STEPS} steps ({dt:.1f} s), oracle port (NumPy); the reference's "
                          f"JAX-CPU path is not installable here"}
 
+    # (R) rollout-engine throughput: env step + eps-greedy + Q forward + Q(lambda), from the
+    # CUDA-event spans of the rollout-phase kernels inside the same timed region (kernel time only, this rank)
+    roll_keys = ("rollout_act_step", "rollout_keys", "qlambda", "conv_fwd_infer", "tc_dense_fwd_head")
+    roll_ms = sum(prof[k][0] for k in roll_keys if k in prof)
+    if "tc_split" in prof and "tc_dense_fwd_head" in prof:  # W1_lo split runs once per forward, either phase
+        n_fwd = prof["tc_dense_fwd_head"][1] + prof.get("tc_dense_fwd", (0, 0))[1]
+        roll_ms += prof["tc_split"][0] * prof["tc_dense_fwd_head"][1] / max(n_fwd, 1)
+    rollout_engine = None
+    if roll_ms > 0:
+        rollout_engine = {"value": S * args.steps * NUM_STEPS * args.envs / (roll_ms / 1e3) * world, "unit": UNIT,
+                          "kernel_ms_per_update": round(roll_ms / args.steps, 3),
+                          "what": "rollout phase only (env step + eps-greedy + Q-network forward + Q(lambda) targets): "
+                                  "sum of the per-kernel CUDA-event spans of rank 0 in the timed region, x n_gpus"}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -406,7 +425,7 @@ def run_gpu(args, rank, world, local_rank):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "make_train(config)+train(host rngs): key upload, init, reset, K updates, D2H of metrics+params"},
             "gpu_launches": int(launches),
-            "roofline": roof, "kernel_breakdown": breakdown,
+            "roofline": roof, "rollout_engine": rollout_engine, "kernel_breakdown": breakdown,
             "td_loss_last": float(out["metrics"]["td_loss"][:, -1].mean())}
     if cpu:
         line["cpu_baseline"] = cpu

@@ -1685,7 +1685,7 @@ static int launch_conv_fwd_tc_t(int S, cudaStream_t st, const uint32_t* obs, int
   if (per_seed > tiles) per_seed = tiles;
   if (per_seed < 1) per_seed = 1;
   {
-    LaunchScope _ls(K_CONV_FWD, st);
+    LaunchScope _ls(TRAIN ? K_CONV_FWD : K_CONV_FWD_INFER, st);
     kfn<<<dim3(per_seed, S), 160, ConvTc<C>::SMEM, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows,
                                                          tiles, per_seed);
   }
@@ -1842,7 +1842,7 @@ static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* ob
   }
   if (g_conv_mma) {
     const dim3 mg(conv_mma_ctas((int)grid.y, rows, 3), grid.y);
-    LaunchScope _ls(K_CONV_FWD, st);
+    LaunchScope _ls(TRAIN ? K_CONV_FWD : K_CONV_FWD_INFER, st);
     switch (C) {
       case 4: conv_fwd_mma_kernel<4, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
       case 6: conv_fwd_mma_kernel<6, TRAIN><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
@@ -1853,10 +1853,10 @@ static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* ob
     return 0;
   }
   switch (C) {
-    case 4: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<4, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
-    case 6: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<6, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
-    case 7: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<7, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
-    case 10: { LaunchScope _ls(K_CONV_FWD, st); conv_fwd_kernel<10, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
+    case 4: { LaunchScope _ls(TRAIN ? K_CONV_FWD : K_CONV_FWD_INFER, st); conv_fwd_kernel<4, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
+    case 6: { LaunchScope _ls(TRAIN ? K_CONV_FWD : K_CONV_FWD_INFER, st); conv_fwd_kernel<6, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
+    case 7: { LaunchScope _ls(TRAIN ? K_CONV_FWD : K_CONV_FWD_INFER, st); conv_fwd_kernel<7, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
+    case 10: { LaunchScope _ls(TRAIN ? K_CONV_FWD : K_CONV_FWD_INFER, st); conv_fwd_kernel<10, TRAIN><<<grid, 256, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, bn, rows); } break;
     default: return -1;
   }
   return 0;
@@ -1912,7 +1912,7 @@ static int tc_dense_fwd(int epi, const float* params, int64_t P, const pqn_net_l
   ep.params = params; ep.P = P; ep.off_b = L.d0_b; ep.off_scale = L.ln1_scale; ep.off_bias = L.ln1_bias;
   ep.off_hw = L.head_w; ep.off_hb = L.head_b; ep.A = A; ep.rows = rows;
   ep.H = w.h2; ep.XHAT = w.xhat2; ep.RSTD = w.rstd2; ep.Q = q;
-  return tc::launch_gemm(0, 1, epi, t, gs, ep, st, K_TC_FWD);
+  return tc::launch_gemm(0, 1, epi, t, gs, ep, st, epi == tc::EPI_LN_HEAD ? K_TC_FWD_HEAD : K_TC_FWD);
 }
 
 // dW1 = H1^T . dZ2  -> grads[d0_w]
