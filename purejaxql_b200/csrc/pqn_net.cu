@@ -1201,7 +1201,11 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
   }
 }
 
-constexpr int CDZ_LD = 17;  // staged dz row stride (floats): conflict-free B-fragment reads
+constexpr int CDZ_LD = 16;  // staged dz / dy / xhat row stride (floats)
+// Column swizzle of the [64 pixels][16 channels] shared-memory tiles of the conv backward: rows p and p+2 are 32 banks
+// apart, so the column is XORed with 8 on every second row pair.  The float2 accesses of a fragment (8 pixel rows x
+// 4 column pairs per half-warp pair) and the B-fragment reads (4 pixel rows x 8 columns) then touch every bank once.
+__device__ __forceinline__ int cswz(int p, int col) { return col ^ (((p >> 1) & 1) << 3); }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
@@ -1282,8 +1286,10 @@ __global__ void __launch_bounds__(ConvBwdSmem<C>::WARPS * 32, 2)
       const float* xsrc = XH1 + gr * FLAT_CNN;
 #pragma unroll
       for (int i = 0; i < FLAT_CNN / 4 / 32; ++i) {
-        cp_async16(my_dy + (i * 32 + lane) * 4, dsrc + (i * 32 + lane) * 4);
-        cp_async16(my_xh + (i * 32 + lane) * 4, xsrc + (i * 32 + lane) * 4);
+        const int q = i * 32 + lane, prow = q >> 2;              // 16-byte chunk q = (pixel row, column quad)
+        const int dst = prow * CONV_O + cswz(prow, (q & 3) * 4);  // the XOR moves whole chunks
+        cp_async16(my_dy + dst, dsrc + q * 4);
+        cp_async16(my_xh + dst, xsrc + q * 4);
       }
       if (lane < CONV_PIX / 4) cp_async16(my_rs + lane * 4, RS1 + gr * CONV_PIX + lane * 4);
     }
@@ -1309,10 +1315,10 @@ __global__ void __launch_bounds__(ConvBwdSmem<C>::WARPS * 32, 2)
       float2 dyv[2][2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        dyv[h][0] = *reinterpret_cast<const float2*>(my_dy + p0 * CONV_O + 8 * h + 2 * t);
-        dyv[h][1] = *reinterpret_cast<const float2*>(my_dy + p1 * CONV_O + 8 * h + 2 * t);
-        const float2 a0 = *reinterpret_cast<const float2*>(my_xh + p0 * CONV_O + 8 * h + 2 * t);
-        const float2 a1 = *reinterpret_cast<const float2*>(my_xh + p1 * CONV_O + 8 * h + 2 * t);
+        dyv[h][0] = *reinterpret_cast<const float2*>(my_dy + p0 * CONV_O + cswz(p0, 8 * h + 2 * t));
+        dyv[h][1] = *reinterpret_cast<const float2*>(my_dy + p1 * CONV_O + cswz(p1, 8 * h + 2 * t));
+        const float2 a0 = *reinterpret_cast<const float2*>(my_xh + p0 * CONV_O + cswz(p0, 8 * h + 2 * t));
+        const float2 a1 = *reinterpret_cast<const float2*>(my_xh + p1 * CONV_O + cswz(p1, 8 * h + 2 * t));
         z[h][0] = a0.x; z[h][1] = a0.y; z[h][2] = a1.x; z[h][3] = a1.y;
       }
       const float rstd0 = my_rs[p0], rstd1 = my_rs[p1];
@@ -1341,13 +1347,15 @@ __global__ void __launch_bounds__(ConvBwdSmem<C>::WARPS * 32, 2)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int o = 8 * h + 2 * t;
+        float dzv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float rstd = j < 2 ? rstd0 : rstd1, m1 = j < 2 ? m1a : m1b, m2 = j < 2 ? m2a : m2b;
-          const float dz = rstd * (dxh[h][j] - m1 - z[h][j] * m2);
-          a_dcb[2 * h + (j & 1)] += dz;
-          my_dz[(j < 2 ? p0 : p1) * CDZ_LD + o + (j & 1)] = dz;
+          dzv[j] = rstd * (dxh[h][j] - m1 - z[h][j] * m2);
+          a_dcb[2 * h + (j & 1)] += dzv[j];
         }
+        *reinterpret_cast<float2*>(my_dz + p0 * CDZ_LD + cswz(p0, o)) = make_float2(dzv[0], dzv[1]);
+        *reinterpret_cast<float2*>(my_dz + p1 * CDZ_LD + cswz(p1, o)) = make_float2(dzv[2], dzv[3]);
       }
     }
     __syncwarp();
@@ -1366,7 +1374,8 @@ __global__ void __launch_bounds__(ConvBwdSmem<C>::WARPS * 32, 2)
       uint32_t bh[2][2], bl[2][2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const float v0 = my_dz[(8 * kk + t) * CDZ_LD + 8 * h + g], v1 = my_dz[(8 * kk + t + 4) * CDZ_LD + 8 * h + g];
+        const int r0 = 8 * kk + t, r1 = r0 + 4;
+        const float v0 = my_dz[r0 * CDZ_LD + cswz(r0, 8 * h + g)], v1 = my_dz[r1 * CDZ_LD + cswz(r1, 8 * h + g)];
         bh[h][0] = __float_as_uint(v0) & 0xFFFFE000u; bh[h][1] = __float_as_uint(v1) & 0xFFFFE000u;
         bl[h][0] = __float_as_uint(v0 - __uint_as_float(bh[h][0])); bl[h][1] = __float_as_uint(v1 - __uint_as_float(bh[h][1]));
       }
