@@ -16,4 +16,9 @@ packages that are absent from ``/root/reference`` and not installable here
 * publicly documented jax.random outputs for ``PRNGKey(0)`` (see
   ``tests/golden/README.md``),
 * the reference's own call sites (file:line cited per function).
+
+Modules: ``jax_prng`` (threefry / jax.random), ``gymnax_envs`` (MinAtar + classic control + wrappers), ``pqn_ref``
+(Q-networks with the shipped layer_norm configuration, Q(lambda), RAdam, rollout, update step) and ``pqn_ref_norm``
+(the NORM_TYPE=batch_norm / none and NORM_INPUT=True network variants -- oracle-first groundwork for SURVEY 8(f)
+row 4; no kernel is built or claimed for them yet).
 """
