@@ -242,7 +242,9 @@ def run_gpu(args, rank, world, local_rank):
     # The engine exposes its per-update loop through train(); to time exactly K
     # updates after W warm-up updates with inputs resident in HBM we run one
     # train() of W+K updates and bracket update W..W+K with events (engine callback).
-    cfg = base_config(args.warmup + args.steps, num_envs=args.envs)
+    cfg = base_config(args.warmup + args.steps, num_envs=args.envs, test=args.with_eval)
+    if args.with_eval:  # the reference's cadence at this config: a greedy evaluation every 3 updates (int(76 * 0.05))
+        cfg["TEST_INTERVAL"] = 3.5 / (args.warmup + args.steps)
     train = pqn_minatar.make_train(cfg)
     eng = train.engine
     ev = {"start": torch.cuda.Event(enable_timing=True), "end": torch.cuda.Event(enable_timing=True)}
@@ -417,7 +419,9 @@ def run_gpu(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"Breakout-MinAtar pqn_minatar NUM_ENVS={args.envs} x {seeds_total} seeds "
-                                   f"(BASELINE configs[1]), seeds sharded {per}/GPU, TEST_DURING_TRAINING=False",
+                                   f"(BASELINE configs[1]), seeds sharded {per}/GPU, TEST_DURING_TRAINING="
+                                   + ("True (greedy eval of 128 envs x 1000 steps every 3 updates inside the timed "
+                                      "region; its env-steps are not counted)" if args.with_eval else "False"),
                        "num_steps": NUM_STEPS, "num_minibatches": 32, "num_epochs": 2,
                        "l2": "per-step working set (obs rows + activations, >2 GB) exceeds the 126 MB L2",
                        "parallelism": f"seed-sharded x{world}, no data-path collective"},
@@ -441,6 +445,8 @@ def main():
     ap.add_argument("--seeds", type=int, default=TOTAL_SEEDS)
     ap.add_argument("--envs", type=int, default=NUM_ENVS)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--with-eval", action="store_true",
+                    help="TEST_DURING_TRAINING=True with the reference's cadence (SURVEY 8(d): report both)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
