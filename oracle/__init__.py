@@ -20,5 +20,6 @@ packages that are absent from ``/root/reference`` and not installable here
 Modules: ``jax_prng`` (threefry / jax.random), ``gymnax_envs`` (MinAtar + classic control + wrappers), ``pqn_ref``
 (Q-networks with the shipped layer_norm configuration, Q(lambda), RAdam, rollout, update step) and ``pqn_ref_norm``
 (the NORM_TYPE=batch_norm / none and NORM_INPUT=True network variants -- oracle-first groundwork for SURVEY 8(f)
-row 4; no kernel is built or claimed for them yet).
+row 4; no kernel is built or claimed for them yet) and ``pqn_rnn_ref`` (the GRU network, in-loss Q(lambda) and
+BPTT of ``pqn_rnn_gymnax.py`` -- same status).
 """
