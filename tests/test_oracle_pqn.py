@@ -92,3 +92,21 @@ def test_linear_schedule():
     assert R.linear_schedule(1.0, 0.05, 7.6, 0) == np.float32(1.0)
     assert abs(R.linear_schedule(1.0, 0.05, 7.6, 100) - 0.05) < 1e-7
     assert abs(R.linear_schedule(1.0, 0.05, 10, 5) - 0.525) < 1e-6
+
+
+def test_radam_matches_torch_radam_over_the_rectification_switch():
+    """Independent pin of the optimizer arithmetic: torch.optim.RAdam implements the same algorithm as
+    optax.scale_by_radam (they differ only in where eps enters the bias-corrected denominator, an O(eps) effect)."""
+    import torch
+    rng = np.random.default_rng(0)
+    w0 = rng.standard_normal(16)
+    p = {"w": w0.copy()}
+    opt = R.opt_init(p)
+    tw = torch.tensor(w0.copy(), dtype=torch.float64, requires_grad=True)
+    topt = torch.optim.RAdam([tw], lr=3e-3, betas=(0.9, 0.999), eps=1e-8)
+    for step in range(12):  # steps 1..5 un-rectified, 6.. rectified
+        g = rng.standard_normal(16)
+        p, opt, _ = R.radam_clip_step(p, {"w": g.copy()}, opt, 3e-3, 1e9)
+        tw.grad = torch.tensor(g.copy(), dtype=torch.float64)
+        topt.step()
+        assert np.allclose(p["w"], tw.detach().numpy(), rtol=1e-6, atol=1e-9), step

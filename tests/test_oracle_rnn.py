@@ -88,3 +88,29 @@ def test_targets_equal_reference_reverse_scan_transcription():
         outs.append(lr_)
     want = np.concatenate([np.stack(outs[::-1]), lambda_returns[None]])
     assert got.shape == (T - 1, B) and np.allclose(got, want, rtol=0, atol=1e-13)
+
+
+def test_gru_step_matches_torch_grucell():
+    """Independent pin of the cell arithmetic: torch.nn.GRUCell uses the same gate equations (with two extra recurrent
+    biases, set to zero here); weights are mapped from the flax layout [in, out] to torch's [3H, in] (r, z, n)."""
+    import torch
+    rng = np.random.default_rng(5)
+    D, A, H, B = 8, 2, 8, 6                                                  # no trunk (layers=0): obs (width H) feeds the GRU
+    p = R.random_params(N.rnn_param_shapes(D, A, H, 0), seed=9, dtype=F64)
+    G = N.G
+    cell = torch.nn.GRUCell(D + A, H).double()
+    with torch.no_grad():
+        cell.weight_ih.copy_(torch.tensor(np.concatenate([p[G + g + "/kernel"].T for g in ("ir", "iz", "in")])))
+        cell.weight_hh.copy_(torch.tensor(np.concatenate([p[G + g + "/kernel"].T for g in ("hr", "hz", "hn")])))
+        cell.bias_ih.copy_(torch.tensor(np.concatenate([p[G + g + "/bias"] for g in ("ir", "iz", "in")])))
+        cell.bias_hh.copy_(torch.tensor(np.concatenate([np.zeros(H), np.zeros(H), p[G + "hn/bias"]])))
+    hs = rng.standard_normal((B, H))
+    obs = rng.standard_normal((1, B, H))          # with layers=0 the "trunk output" is the observation itself
+    la = rng.integers(0, A, (1, B))
+    p0 = dict(p)
+    # layers=0 => Dense_0 is the head; rnn_forward reads its input width from the parameter shapes
+    new_h, q = N.rnn_forward(p0, hs, obs[..., :D], np.zeros((1, B), bool), la)
+    onehot = np.eye(A)[la[0]]
+    want = cell(torch.tensor(np.concatenate([obs[0, :, :D], onehot], -1)), torch.tensor(hs)).detach().numpy()
+    assert np.allclose(new_h, want, rtol=0, atol=1e-12)
+    assert np.allclose(q[0], want @ p["Dense_0/kernel"] + p["Dense_0/bias"], rtol=0, atol=1e-12)
