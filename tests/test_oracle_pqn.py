@@ -110,3 +110,48 @@ def test_radam_matches_torch_radam_over_the_rectification_switch():
         tw.grad = torch.tensor(g.copy(), dtype=torch.float64)
         topt.step()
         assert np.allclose(p["w"], tw.detach().numpy(), rtol=1e-6, atol=1e-9), step
+
+
+def test_cnn_and_mlp_grads_match_torch_autograd_f64():
+    """The oracle's hand-written backward against an independent autodiff (torch, fp64) of the same network built from
+    torch primitives (conv2d / layer_norm / relu / matmul), for the MinAtar CNN and the gymnax MLP."""
+    rng = np.random.default_rng(11)
+    F64 = np.float64
+    tt = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, requires_grad=True)
+    # ---- CNN
+    B, C, A = 9, 4, 3
+    p = R.random_params(R.cnn_param_shapes(C, A), 5, dtype=F64)
+    obs = (rng.random((B, 10, 10, C)) < 0.2).astype(F64)
+    act, tgt = rng.integers(0, A, B), rng.standard_normal(B)
+    loss, q_sa, g = R.cnn_loss_and_grads(p, obs, act, tgt)
+    tp = {k: tt(v) for k, v in p.items()}
+    x = torch.tensor(obs).permute(0, 3, 1, 2) / 255.0
+    z = torch.nn.functional.conv2d(x, tp["CNN_0/Conv_0/kernel"].permute(3, 2, 0, 1), tp["CNN_0/Conv_0/bias"]).permute(0, 2, 3, 1)
+    z = torch.nn.functional.layer_norm(z, (16,), tp["CNN_0/LayerNorm_0/scale"], tp["CNN_0/LayerNorm_0/bias"], 1e-6)
+    h = torch.relu(z).reshape(B, -1)
+    z = torch.nn.functional.layer_norm(h @ tp["CNN_0/Dense_0/kernel"] + tp["CNN_0/Dense_0/bias"], (128,),
+                                       tp["CNN_0/LayerNorm_1/scale"], tp["CNN_0/LayerNorm_1/bias"], 1e-6)
+    q = torch.relu(z) @ tp["Dense_0/kernel"] + tp["Dense_0/bias"]
+    tl = 0.5 * ((q[torch.arange(B), torch.tensor(act)] - torch.tensor(tgt)) ** 2).mean()
+    tl.backward()
+    assert abs(float(tl) - loss) < 1e-12
+    for k in p:
+        ref = tp[k].grad.numpy() if tp[k].grad is not None else np.zeros_like(p[k])
+        assert np.allclose(g[k], ref, rtol=1e-9, atol=1e-12), k
+    # ---- MLP
+    D, H = 6, 32
+    p = R.random_params(R.mlp_param_shapes(D, A, H, 2), 6, dtype=F64)
+    x = rng.standard_normal((B, D))
+    loss, q_sa, g = R.mlp_loss_and_grads(p, x, act, tgt)
+    tp = {k: tt(v) for k, v in p.items()}
+    h = torch.tensor(x)
+    for l in range(2):
+        z = h @ tp[f"Dense_{l}/kernel"] + tp[f"Dense_{l}/bias"]
+        h = torch.relu(torch.nn.functional.layer_norm(z, (H,), tp[f"LayerNorm_{l}/scale"], tp[f"LayerNorm_{l}/bias"], 1e-6))
+    q = h @ tp["Dense_2/kernel"] + tp["Dense_2/bias"]
+    tl = 0.5 * ((q[torch.arange(B), torch.tensor(act)] - torch.tensor(tgt)) ** 2).mean()
+    tl.backward()
+    assert abs(float(tl) - loss) < 1e-12
+    for k in p:
+        ref = tp[k].grad.numpy() if tp[k].grad is not None else np.zeros_like(p[k])
+        assert np.allclose(g[k], ref, rtol=1e-9, atol=1e-12), k
