@@ -103,3 +103,32 @@ def test_batch_norm_tree_names_follow_flax_auto_naming():
     assert {"BatchNorm_0/scale", "BatchNorm_1/scale", "BatchNorm_2/scale"} <= set(s) and "LayerNorm_0/scale" not in s
     assert set(N.mlp_batch_stats(4, 256, 2, "batch_norm")) == {"BatchNorm_0", "BatchNorm_1", "BatchNorm_2"}
     assert not any("Norm_1" in k for k in N.cnn_param_shapes(4, 3, "none") if k.startswith("CNN_0"))
+
+
+@pytest.mark.parametrize("norm_input", [False, True])
+def test_cnn_batch_norm_variant_matches_torch_autograd(norm_input):
+    """Independent pin: the batch_norm network built from torch primitives (batch_norm in training mode normalises
+    with the biased batch variance, like flax) and differentiated by torch autograd, fp64."""
+    import torch
+    rng = np.random.default_rng(12)
+    B, C, A = 7, 4, 3
+    p = R.random_params(N.cnn_param_shapes(C, A, "batch_norm"), seed=13, dtype=F64)
+    stats = N.cnn_batch_stats(C, "batch_norm", F64)
+    obs = (rng.random((B, 10, 10, C)) < 0.25).astype(F64)
+    act, tgt = rng.integers(0, A, B), rng.standard_normal(B)
+    loss, _, g, _ = N.cnn_loss_and_grads(p, stats, obs, act, tgt, "batch_norm", norm_input)
+    tp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in p.items()}
+    bn = lambda x, name: torch.nn.functional.batch_norm(x, None, None, tp[name + "/scale"], tp[name + "/bias"],
+                                                        training=True, eps=1e-5)
+    x = torch.tensor(obs).permute(0, 3, 1, 2)                         # NCHW: batch_norm reduces over N, H, W
+    x = bn(x, "BatchNorm_0") if norm_input else x / 255.0
+    z = torch.nn.functional.conv2d(x, tp["CNN_0/Conv_0/kernel"].permute(3, 2, 0, 1), tp["CNN_0/Conv_0/bias"])
+    h = torch.relu(bn(z, "CNN_0/BatchNorm_0")).permute(0, 2, 3, 1).reshape(B, -1)
+    z = bn(h @ tp["CNN_0/Dense_0/kernel"] + tp["CNN_0/Dense_0/bias"], "CNN_0/BatchNorm_1")
+    q = torch.relu(z) @ tp["Dense_0/kernel"] + tp["Dense_0/bias"]
+    tl = 0.5 * ((q[torch.arange(B), torch.tensor(act)] - torch.tensor(tgt)) ** 2).mean()
+    tl.backward()
+    assert abs(float(tl) - loss) < 1e-12
+    for k in p:
+        ref = tp[k].grad.numpy() if tp[k].grad is not None else np.zeros_like(p[k])
+        assert np.allclose(g[k], ref, rtol=1e-8, atol=1e-11), k
