@@ -27,3 +27,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """Every test may assume the in-tree library exists.  Without a GPU (this container, the driver's CPU run) it is
+    built incrementally (nvcc cross-compiles sm_100a); on the GPU box the .so shipped with the snapshot is used as
+    is -- file times are not meaningful there -- and only a missing library triggers a build."""
+    from purejaxql_b200 import build
+    if _has_cuda() and os.path.exists(build.OUT):
+        return build.OUT
+    return build.build()
