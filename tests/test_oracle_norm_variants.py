@@ -128,7 +128,7 @@ def test_cnn_batch_norm_variant_matches_torch_autograd(norm_input):
     q = torch.relu(z) @ tp["Dense_0/kernel"] + tp["Dense_0/bias"]
     tl = 0.5 * ((q[torch.arange(B), torch.tensor(act)] - torch.tensor(tgt)) ** 2).mean()
     tl.backward()
-    assert abs(float(tl) - loss) < 1e-12
+    assert abs(float(tl.detach()) - loss) < 1e-12
     for k in p:
         ref = tp[k].grad.numpy() if tp[k].grad is not None else np.zeros_like(p[k])
         assert np.allclose(g[k], ref, rtol=1e-8, atol=1e-11), k

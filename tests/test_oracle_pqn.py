@@ -134,7 +134,7 @@ def test_cnn_and_mlp_grads_match_torch_autograd_f64():
     q = torch.relu(z) @ tp["Dense_0/kernel"] + tp["Dense_0/bias"]
     tl = 0.5 * ((q[torch.arange(B), torch.tensor(act)] - torch.tensor(tgt)) ** 2).mean()
     tl.backward()
-    assert abs(float(tl) - loss) < 1e-12
+    assert abs(float(tl.detach()) - loss) < 1e-12
     for k in p:
         ref = tp[k].grad.numpy() if tp[k].grad is not None else np.zeros_like(p[k])
         assert np.allclose(g[k], ref, rtol=1e-9, atol=1e-12), k
@@ -151,7 +151,7 @@ def test_cnn_and_mlp_grads_match_torch_autograd_f64():
     q = h @ tp["Dense_2/kernel"] + tp["Dense_2/bias"]
     tl = 0.5 * ((q[torch.arange(B), torch.tensor(act)] - torch.tensor(tgt)) ** 2).mean()
     tl.backward()
-    assert abs(float(tl) - loss) < 1e-12
+    assert abs(float(tl.detach()) - loss) < 1e-12
     for k in p:
         ref = tp[k].grad.numpy() if tp[k].grad is not None else np.zeros_like(p[k])
         assert np.allclose(g[k], ref, rtol=1e-9, atol=1e-12), k
