@@ -258,15 +258,19 @@ def q_lambda_targets(reward, done, q_val, last_q, gamma, lam):
 # --------------------------------------------------------------------------- #
 def radam_scalars(count_inc, b1=0.9, b2=0.999, threshold=5.0):
     """Per-step scalars of optax.scale_by_radam for 1-based step ``count_inc``:
-    (bias_corr1, bias_corr2, rect, use_rect)."""
-    ro_inf = 2.0 / (1.0 - b2) - 1.0
-    b2t = b2 ** count_inc
-    ro = ro_inf - 2.0 * count_inc * b2t / (1.0 - b2t)
-    bc1 = 1.0 - b1 ** count_inc
-    bc2 = 1.0 - b2t
-    use = ro >= threshold
-    rect = np.sqrt(max((ro - 4) * (ro - 2) * ro_inf / ((ro_inf - 4) * (ro_inf - 2) * ro), 0.0)) if use else 0.0
-    return bc1, bc2, rect, bool(use)
+    (bias_corr1, bias_corr2, rect, use_rect).  float32 in optax's operation order: the traced program
+    evaluates ``b2t = b2**count_inc; ro = ro_inf - 2*count_inc*b2t/(1-b2t)`` on weak-typed float32 scalars, and
+    the cancellation in ``ro`` is visible at that precision for small counts."""
+    f = F32
+    t = f(count_inc)
+    ro_inf = f(2.0) / (f(1.0) - f(b2)) - f(1.0)
+    b2t = np.power(f(b2), t, dtype=F32)
+    ro = ro_inf - f(2.0) * t * b2t / (f(1.0) - b2t)
+    bc1 = f(1.0) - np.power(f(b1), t, dtype=F32)
+    bc2 = f(1.0) - b2t
+    use = bool(ro >= f(threshold))
+    rect = np.sqrt((ro - f(4)) * (ro - f(2)) * ro_inf / ((ro_inf - f(4)) * (ro_inf - f(2)) * ro), dtype=F32) if use else f(0.0)
+    return float(bc1), float(bc2), float(rect), use
 
 
 def radam_clip_step(p, g, opt, lr, max_grad_norm, b1=0.9, b2=0.999, eps=1e-8):
@@ -302,9 +306,15 @@ def opt_init(p):
 # --------------------------------------------------------------------------- #
 # rollout (pqn_minatar.py:181-219) for ONE seed
 # --------------------------------------------------------------------------- #
-def rollout(env, forward, params, obs, env_state, rng, num_steps, eps, rew_scale=1.0):
+def rollout(env, forward, params, obs, env_state, rng, num_steps, eps, rew_scale=1.0, forced_actions=None,
+            tie_log=None):
     """T x _step_env.  ``rng`` is the scan's initial carry (``_rng`` of :213).
-    Returns (obs_T, state_T, rng_final, transitions dict of [T,...] arrays, infos)."""
+    Returns (obs_T, state_T, rng_final, transitions dict of [T,...] arrays, infos).
+
+    ``forced_actions`` [T,N] (parity tests with eps < 1): the oracle still computes its own eps-greedy
+    action, records every disagreement in ``tie_log`` as (t, env, own action, forced action, gap between the
+    two Q-values involved) and then steps the env with the forced action, so that one argmax flip on a
+    numerical Q tie does not desynchronise the rest of the comparison."""
     N = obs.shape[0]
     tr = {k: [] for k in ("obs", "action", "reward", "done", "next_obs", "q_val")}
     infos = {}
@@ -313,6 +323,14 @@ def rollout(env, forward, params, obs, env_state, rng, num_steps, eps, rew_scale
         rng, rng_a, rng_s = ks[0], ks[1], ks[2]
         q = forward(params, obs)                                    # :184-191
         action = eps_greedy(jr.split(rng_a, N), q, eps)             # :194-196
+        if forced_actions is not None:
+            fa = np.asarray(forced_actions[len(tr["action"])]).astype(np.int32)
+            bad = np.nonzero(fa != action)[0]
+            if tie_log is not None:
+                for e in bad:
+                    tie_log.append((len(tr["action"]), int(e), int(action[e]), int(fa[e]),
+                                    float(abs(q[e, action[e]] - q[e, fa[e]]))))
+            action = fa
         new_obs, env_state, reward, done, info = env.step(jr.split(rng_s, N), env_state, action)
         tr["obs"].append(obs); tr["action"].append(action)
         tr["reward"].append((F32(rew_scale) * reward).astype(F32)); tr["done"].append(done)
@@ -325,7 +343,8 @@ def rollout(env, forward, params, obs, env_state, rng, num_steps, eps, rew_scale
     return obs, env_state, rng, tr, infos
 
 
-def update_step(env, kind, params, opt, batch_stats, obs, env_state, rng, cfg, n_updates, lr_fn):
+def update_step(env, kind, params, opt, batch_stats, obs, env_state, rng, cfg, n_updates, lr_fn, forced_actions=None,
+                tie_log=None):
     """One ``_update_step`` (pqn_minatar.py:176-338) for one seed, exact key chain
     of SURVEY Appendix B.  ``kind`` is "cnn" or "mlp".  Returns the new carry and
     the metrics dict."""
@@ -336,7 +355,7 @@ def update_step(env, kind, params, opt, batch_stats, obs, env_state, rng, cfg, n
                           cfg["EPS_DECAY"] * cfg["NUM_UPDATES_DECAY"], n_updates)
     ks = jr.split(rng, 2); rng, _rng = ks[0], ks[1]                 # :213
     obs, env_state, rng, tr, infos = rollout(env, fwd, params, obs, env_state, _rng, T, eps,
-                                             cfg.get("REW_SCALE", 1))
+                                             cfg.get("REW_SCALE", 1), forced_actions, tie_log)
     last_q = fwd(params, tr["next_obs"][-1]).max(-1)                # :227-235
     targets = q_lambda_targets(tr["reward"], tr["done"], tr["q_val"], last_q,
                                cfg["GAMMA"], cfg["LAMBDA"])
@@ -359,3 +378,42 @@ def update_step(env, kind, params, opt, batch_stats, obs, env_state, rng, cfg, n
     metrics = {"td_loss": float(np.mean(losses)), "qvals": float(np.mean(qvs))}
     metrics.update({k: float(v.astype(np.float64).mean()) for k, v in infos.items()})
     return params, opt, batch_stats, obs, env_state, rng, metrics, tr, targets
+
+
+# --------------------------------------------------------------------------- #
+# greedy evaluation rollout (pqn_minatar.py:371-413 / pqn_gymnax.py:364-406) for ONE seed
+# --------------------------------------------------------------------------- #
+INFO_KEYS = ("returned_episode_returns", "returned_episode_lengths", "timestep", "returned_episode", "discount")
+
+
+def get_test_metrics(env, forward, params, rng, num_envs, num_steps, eps_test):
+    """``get_test_metrics(train_state, rng)``.  Restated with its key quirks:
+
+    * ``rng, _rng = split(rng)`` (:396); the reset uses ``split(_rng, N)`` (:397 via vmap_reset :107-109)
+      and the scan carry starts at the SAME ``_rng`` (:399-401);
+    * every step: ``rng, _rng = split(rng)`` (:378); the action keys are ``split(_rng, N)`` (:388-390)
+      and the env keys are ``split(_rng, N)`` again inside ``vmap_step`` (:391-393, :110-112) -- the
+      same per-env keys feed ``eps_greedy_exploration`` and ``env.step``;
+    * result: for every info leaf, ``nanmean(where(infos["returned_episode"], x, nan))`` over the
+      whole [T, N] block (:403-412) -- NaN when no episode ended."""
+    ks = jr.split(rng, 2)
+    _rng = ks[1]
+    obs, state = env.reset(jr.split(_rng, num_envs))
+    carry = _rng
+    infos = {}
+    for _ in range(num_steps):
+        ks = jr.split(carry, 2)
+        carry, sub = ks[0], ks[1]
+        q = forward(params, obs)
+        env_keys = jr.split(sub, num_envs)
+        action = eps_greedy(env_keys, q, eps_test)
+        obs, state, reward, done, info = env.step(env_keys, state, action)
+        for k, v in info.items():
+            infos.setdefault(k, []).append(np.asarray(v))
+    infos = {k: np.stack(v) for k, v in infos.items()}
+    mask = infos["returned_episode"].astype(bool)
+    out = {}
+    for k, v in infos.items():
+        sel = v.astype(np.float64)[mask]
+        out[k] = float(sel.mean()) if sel.size else float("nan")
+    return out

@@ -12,6 +12,33 @@ import torch
 from . import config_loader, jaxrandom as jr
 
 
+def init_distributed():
+    """Under torchrun (RANK / LOCAL_RANK / WORLD_SIZE set) bind this process to its GPU and join the process
+    group; a plain `python -m purejaxql_b200.pqn_minatar` run is left untouched.  Returns (rank, world)."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if torch.cuda.is_available():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group("gloo")
+    return dist.get_rank(), dist.get_world_size()
+
+
+def seed_slice(num_seeds, rank, world):
+    """Contiguous slice [lo, hi) of the seed axis owned by `rank` (may be empty when num_seeds < world)."""
+    per = (num_seeds + world - 1) // world
+    lo = min(num_seeds, rank * per)
+    return lo, min(num_seeds, lo + per)
+
+
 def _shard_seeds(rngs):
     """Seeds are independent runs (jax.vmap over rngs, pqn_minatar.py:459-461):
     under torchrun each rank trains a contiguous slice of the same split(key, NUM_SEEDS)."""
@@ -19,9 +46,8 @@ def _shard_seeds(rngs):
     if not (dist.is_available() and dist.is_initialized()):
         return rngs, 0, 1
     r, w = dist.get_rank(), dist.get_world_size()
-    S = rngs.shape[0]
-    per = (S + w - 1) // w
-    return rngs[r * per:min(S, (r + 1) * per)], r, w
+    lo, hi = seed_slice(rngs.shape[0], r, w)
+    return rngs[lo:hi], r, w
 
 
 def single_run(config, make_train, alg_file_name="pqn"):
@@ -35,10 +61,16 @@ def single_run(config, make_train, alg_file_name="pqn"):
         wandb.init(entity=config["ENTITY"], project=config["PROJECT"],
                    tags=[alg_name.upper(), env_name.upper(), "b200_native"],
                    name=f'{config["ALG_NAME"]}_{config["ENV_NAME"]}', config=config, mode=config["WANDB_MODE"])
+    init_distributed()
     rng = jr.PRNGKey(config["SEED"])                                  # :456
     t0 = time.time()
     rngs = jr.split(rng, config["NUM_SEEDS"], int(config.get("JAX_THREEFRY_PARTITIONABLE", 0)))   # :459
     local_rngs, rank, world = _shard_seeds(rngs)
+    if local_rngs.shape[0] == 0:
+        # NUM_SEEDS < world size in the seed-sharded mode: this rank has no run of its own (the env-sharded
+        # mode, DATA_PARALLEL=envs, is what uses every GPU for a single seed)
+        print(f"rank {rank}: no seeds assigned (NUM_SEEDS={config['NUM_SEEDS']} < world size {world})")
+        return None
     train = make_train(config)
     outs = train(local_rngs)                                          # :460-461 (seed axis is native)
     torch.cuda.synchronize()
@@ -56,7 +88,7 @@ def single_run(config, make_train, alg_file_name="pqn"):
         for i in range(per):
             def pick(d):
                 return {k: (pick(v) if isinstance(v, dict) else v[i]) for k, v in d.items()}
-            gi = rank * ((config["NUM_SEEDS"] + world - 1) // world) + i
+            gi = seed_slice(config["NUM_SEEDS"], rank, world)[0] + i
             save_params(pick(model_state.params),
                         os.path.join(save_dir, f'{alg_name}_{env_name}_seed{config["SEED"]}_vmap{gi}.safetensors'))
     return outs

@@ -17,6 +17,9 @@ enum KernelId : int {
   K_CONV_FWD_INFER /* rollout / evaluation variant */, K_TC_FWD_HEAD /* forward GEMM with the Q-head epilogue */, K_COUNT
 };
 
+// SM count of the CURRENT device (cached per device ordinal, not per process)
+int device_sm_count();
+
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 

@@ -25,6 +25,17 @@ int check_launch(const char* what) {
   return set_error(PQN_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
+int device_sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
+
 static const char* const kNames[K_COUNT] = {
     "env_reset", "env_step", "env_obs", "eps_greedy", "rollout_act_step", "rollout_keys", "qlambda", "rng",
     "conv_fwd", "dense_fwd", "row_bwd", "wgrad", "dgrad", "conv_bwd", "gather_rows", "sqnorm", "radam", "advance",

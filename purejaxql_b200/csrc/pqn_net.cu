@@ -68,6 +68,14 @@ static int make_layout(const pqn_net_desc_t* d, pqn_net_layout_t* L) {
 static int check_desc(const pqn_net_desc_t* d, const char* who) {
   if (!d) return set_error(PQN_E_INVALID, "%s: desc is NULL", who);
   if (d->num_actions < 1 || d->num_actions > 32) return set_error(PQN_E_INVALID, "%s: num_actions=%d out of [1,32]", who, d->num_actions);
+  {
+    // row_bwd_kernel keeps [A][N] head weights + eight warp-private [A][N] gradient slices in shared memory
+    const int Nh = d->kind == PQN_NET_MINATAR_CNN ? 128 : d->hidden;
+    const size_t need = (size_t)(3 * Nh + 9 * d->num_actions * Nh + d->num_actions + 2) * sizeof(float);
+    if (need > 227u * 1024u)
+      return set_error(PQN_E_UNSUPPORTED, "%s: hidden=%d with num_actions=%d needs %zu B of shared memory for the head "
+                       "backward (limit 227 KB)", who, Nh, d->num_actions, need);
+  }
   if (d->kind == PQN_NET_MINATAR_CNN) {
     if (d->in_c != 4 && d->in_c != 6 && d->in_c != 7 && d->in_c != 10)
       return set_error(PQN_E_UNSUPPORTED, "%s: CNN in_c=%d (MinAtar uses 4/6/7/10)", who, d->in_c);
@@ -1682,12 +1690,8 @@ static int launch_conv_fwd_tc_t(int S, cudaStream_t st, const uint32_t* obs, int
                                 const float* params, int64_t P, const pqn_net_layout_t& L, float* h1, float* h1lo,
                                 float* xh1, float* rs1, float* bn, int rows) {
   auto kfn = conv_fwd_tc_kernel<C, TRAIN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTc<C>::SMEM) != cudaSuccess)
-      return check_launch("conv_fwd_tc(cudaFuncSetAttribute)");
-    attr_set = true;
-  }
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTc<C>::SMEM) != cudaSuccess)
+    return check_launch("conv_fwd_tc(cudaFuncSetAttribute)");
   const int tiles = (rows + 1) / 2;
   // all CTAs co-resident (3 per SM by shared memory): a second partial wave would double the time
   int per_seed = (148 * 3) / S;
@@ -1785,12 +1789,8 @@ static int launch_conv_bwd_mma(dim3 grid, cudaStream_t st, const uint32_t* obs, 
                                const float* params, int64_t P, const pqn_net_layout_t& L, const float* dy1,
                                const float* xh1, const float* rs1, float* grads, int rows) {
   auto kfn = conv_bwd_mma_kernel<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvBwdSmem<C>::BYTES) != cudaSuccess)
-      return check_launch("conv_bwd_mma(cudaFuncSetAttribute)");
-    attr_set = true;
-  }
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvBwdSmem<C>::BYTES) != cudaSuccess)
+    return check_launch("conv_bwd_mma(cudaFuncSetAttribute)");
   kfn<<<grid, ConvBwdSmem<C>::WARPS * 32, ConvBwdSmem<C>::BYTES, st>>>(obs, orps, gather, params, P, L, dy1, xh1, rs1,
                                                                        grads, rows);
   return 0;
@@ -1803,23 +1803,21 @@ static size_t row_bwd_smem(int N, int A, bool head) {
 }
 
 template <int N, bool HEAD, typename... Args>
-static void launch_row_bwd(dim3 grid, int A, cudaStream_t st, Args... args) {
+static int launch_row_bwd(dim3 grid, int A, cudaStream_t st, Args... args) {
   const size_t sm = row_bwd_smem(N, A, HEAD);
-  if (sm > 48 * 1024) cudaFuncSetAttribute(row_bwd_kernel<N, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (sm > 48 * 1024 &&
+      cudaFuncSetAttribute(row_bwd_kernel<N, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+    return check_launch("row_bwd(cudaFuncSetAttribute)");
   LaunchScope _ls(K_ROW_BWD, st);
   row_bwd_kernel<N, HEAD><<<grid, 256, sm, st>>>(args...);
+  return 0;
 }
 
 // CTAs per seed for the warp-per-sample conv kernels (grid = per_seed x S).  `resident` = CTAs the GPU holds at once
 // (SMs x CTAs/SM): the grid is sized to fill whole waves of that many CTAs -- 1280 CTAs on 296 slots would run a
 // fifth, 32%-full wave -- while staying near 4 waves so that per-CTA setup (weight fragments) stays amortised.
 static unsigned conv_mma_ctas(int S, int rows, int ctas_per_sm) {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   const int resident = sms * ctas_per_sm;
   const int maxc = (rows + CONV_MMA_WARPS - 1) / CONV_MMA_WARPS;
   int best = 1;

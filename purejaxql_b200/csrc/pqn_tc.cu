@@ -562,26 +562,13 @@ int make_tmap(CUtensorMap* tm, const float* base, uint64_t inner, uint64_t mid, 
   return PQN_OK;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int num_sms() { return device_sm_count(); }
 
 template <int A_MN, int B_MN, int EPI>
 static int launch_t(const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep, cudaStream_t st, int kid) {
   auto kfn = tc_gemm_kernel<A_MN, B_MN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
-      return check_launch("tc_gemm(cudaFuncSetAttribute)");
-    attr_set = true;
-  }
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+    return check_launch("tc_gemm(cudaFuncSetAttribute)");
   const int tiles = gs.m_tiles * gs.n_tiles * gs.S;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   {

@@ -45,17 +45,25 @@ def linear_schedule(init, end, transition_steps, count):
 
 def radam_schedule_table(num_steps, lr_fn, b1=0.9, b2=0.999, threshold=5.0):
     """[num_steps,4] float32 rows (lr_t, 1-b1^t, 1-b2^t, rect_t or 0) of
-    optax.scale_by_radam + scale_by_learning_rate for optimizer steps t=1.."""
+    optax.scale_by_radam + scale_by_learning_rate for optimizer steps t=1..
+
+    Evaluated in float32 in optax's operation order (the traced program computes ``b2t = b2**count_inc``,
+    ``ro = ro_inf - 2*count_inc*b2t/(1-b2t)`` and the rectification term on weak-typed float32 scalars): the
+    cancellation in ``ro`` is visible in float32 for the first few hundred steps, so a float64 table would not
+    match the reference optimizer to 1e-5 there.  (XLA's f32 pow may still differ from numpy's by an ulp, which
+    the cancellation amplifies; this cannot be pinned without an optax install -- DESIGN.md section 5.)"""
+    f = np.float32
     tab = np.zeros((max(num_steps, 1), 4), np.float32)
-    ro_inf = 2.0 / (1.0 - b2) - 1.0
+    ro_inf = f(2.0) / (f(1.0) - f(b2)) - f(1.0)
     for i in range(num_steps):
-        t = i + 1
-        b2t = b2 ** t
-        ro = ro_inf - 2.0 * t * b2t / (1.0 - b2t)
-        rect = 0.0
-        if ro >= threshold:
-            rect = float(np.sqrt((ro - 4) * (ro - 2) * ro_inf / ((ro_inf - 4) * (ro_inf - 2) * ro)))
-        tab[i] = (lr_fn(i), 1.0 - b1 ** t, 1.0 - b2t, rect)
+        t = f(i + 1)
+        b2t = np.power(f(b2), t, dtype=np.float32)
+        b1t = np.power(f(b1), t, dtype=np.float32)
+        ro = ro_inf - f(2.0) * t * b2t / (f(1.0) - b2t)
+        rect = f(0.0)
+        if ro >= f(threshold):
+            rect = np.sqrt((ro - f(4)) * (ro - f(2)) * ro_inf / ((ro_inf - f(4)) * (ro_inf - f(2)) * ro), dtype=np.float32)
+        tab[i] = (lr_fn(i), f(1.0) - b1t, f(1.0) - b2t, rect)
     return tab
 
 
@@ -83,6 +91,7 @@ class PQNEngine:
         self.NU = int(c["NUM_UPDATES"])
         self.A = self.env.num_actions
         self.binary = self.env.binary_obs
+        self.network = network
         if network == "cnn":
             if not self.binary:
                 raise ValueError("the MinAtar CNN needs a (10,10,C) binary-observation env")
@@ -180,7 +189,9 @@ class PQNEngine:
         self._write_obs(state, obs_buf, T, S)                        # update_body moves row T to row 0
         rng = jr.split(K3, 2, mode)[:, 1].contiguous()              # :422-423 runner rng
 
-        metric_names = ["env_step", "update_steps", "env_frame", "grad_steps", "td_loss", "qvals", *INFO_KEYS]
+        # pqn_minatar.py:330-338 reports env_frame; pqn_gymnax.py:324-331 does not
+        metric_names = ["env_step", "update_steps", *(["env_frame"] if self.network == "cnn" else []), "grad_steps",
+                        "td_loss", "qvals", *INFO_KEYS]
         metrics = {m: torch.zeros((S, max(NU, 1)), dtype=torch.float64, device=dev) for m in metric_names}
         test_hist = None
         test_every = None
@@ -260,24 +271,34 @@ class PQNEngine:
         # eagerly (warms every code path), later updates replay the captured graph.
         want_graph = c.get("CUDA_GRAPH", "auto")
         use_graph = (S * E * T <= (1 << 21)) if want_graph == "auto" else bool(want_graph)
-        use_graph = use_graph and NU > 2 and getattr(self, "on_update_begin", None) is None
+        use_graph = use_graph and NU > 2
         graph = None
         self.graph_captured = False
+        self.graph_replays = 0
+        self.graph_launches_per_replay = 0
 
-        on_update_begin = getattr(self, "on_update_begin", None)      # bench/profiling hook
+        # hooks (bench / tests): both are called on the host OUTSIDE the captured region, so they do not prevent
+        # CUDA-graph replay.  on_update_end receives the static rollout buffers of the update that just ran.
+        on_update_begin = getattr(self, "on_update_begin", None)
+        on_update_end = getattr(self, "on_update_end", None)
+        dbg = dict(obs=obs_buf, action=act_buf, reward=rew_buf, done=done_buf, maxq=maxq_buf, targets=targets,
+                   params=params, state=state, rng=rng_buf)
         for n_updates in range(NU):
             if on_update_begin is not None:
                 on_update_begin(n_updates)
             if graph is not None:
                 graph.replay()
+                self.graph_replays += 1
             else:
                 update_body()
                 if use_graph and n_updates == 0:
                     try:
                         torch.cuda.synchronize(dev)
                         g = torch.cuda.CUDAGraph()
+                        l0 = L.pqn_launch_count()
                         with torch.cuda.graph(g):
                             update_body()
+                        self.graph_launches_per_replay = int(L.pqn_launch_count() - l0)
                         graph = g
                         self.graph_captured = True
                     except Exception as e:                            # capture is an optimisation only
@@ -286,6 +307,8 @@ class PQNEngine:
                         graph = None
                         use_graph = False
                         torch.cuda.synchronize(dev)
+            if on_update_end is not None:
+                on_update_end(n_updates, dbg)
             timesteps += T * E                                       # :222-225
             grad_steps += self.nmb * self.epochs
             # ================= metrics (:329-338)
@@ -293,7 +316,8 @@ class PQNEngine:
             col = n_updates
             metrics["env_step"][:, col] = timesteps
             metrics["update_steps"][:, col] = n_done
-            metrics["env_frame"][:, col] = timesteps * obs_channels
+            if "env_frame" in metrics:
+                metrics["env_frame"][:, col] = timesteps * obs_channels
             metrics["grad_steps"][:, col] = grad_steps
             metrics["td_loss"][:, col] = m_cur[:, 0]
             metrics["qvals"][:, col] = m_cur[:, 1]

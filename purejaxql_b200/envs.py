@@ -29,10 +29,12 @@ ENV_IDS = {
     "Asterix-MinAtar": 1,
     "SpaceInvaders-MinAtar": 2,
     "Freeway-MinAtar": 3,
-    "Seaquest-MinAtar": 4,
     "CartPole-v1": 16,
     "Acrobot-v1": 17,
 }
+# PQN_ENV_SEAQUEST (4) is reserved in include/pqn_b200.h but not built: gymnax 0.0.6 (the reference's pin) does not
+# register "Seaquest-MinAtar" in gymnax.make either, so the reference cannot run it.
+MINATAR_GAMES = ("Breakout-MinAtar", "Asterix-MinAtar", "SpaceInvaders-MinAtar", "Freeway-MinAtar")
 
 LOG_FIELDS = ("episode_returns", "episode_lengths", "returned_episode_returns",
               "returned_episode_lengths", "timestep")

@@ -130,3 +130,96 @@ def test_library_sass_has_blackwell_tensor_and_tma_ops():
     assert "sm_100a" in sass or "SM100" in sass.upper()
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR", "HMMA", "FENCE.VIEW.ASYNC", "LDGSTS"):
         assert mnemonic in sass, f"{mnemonic} missing from the SASS of {so}"
+
+
+# --------------------------------------------------------------------------- #
+# golden vectors generated by the REAL jax + gymnax (tests/golden/make_golden_from_ref.py); present only once a
+# machine with the reference stack has been reachable.  Until then these tests skip and parity stays "unpinned".
+# --------------------------------------------------------------------------- #
+import glob
+import json
+
+_REF_FILES = sorted(glob.glob(os.path.join(GOLD, "*_traj_*_ref.npz")))
+_REF_NAMES = {"breakout": "Breakout-MinAtar", "asterix": "Asterix-MinAtar", "spaceinvaders": "SpaceInvaders-MinAtar",
+              "freeway": "Freeway-MinAtar", "cartpole": "CartPole-v1", "acrobot": "Acrobot-v1"}
+
+
+@pytest.mark.skipif(not _REF_FILES, reason="no reference-generated golden vectors committed (jax/gymnax never reachable)")
+@pytest.mark.parametrize("path", _REF_FILES or ["none"])
+def test_oracle_against_reference_generated_golden(path):
+    base = os.path.basename(path)
+    game, _, layout, _ = base.split("_")
+    env_name = _REF_NAMES[game]
+    g = dict(np.load(path))
+    jr.DEFAULT_PARTITIONABLE = layout == "partitionable"
+    try:
+        minatar = env_name.endswith("MinAtar")
+        env = G.make(env_name, flatten=not minatar)
+        n = g["reset_keys"].shape[0]
+        o_obs, o_st = env.reset(g["reset_keys"])
+        D = int(np.prod(env.obs_shape))
+        if minatar:
+            assert np.array_equal(o_obs.reshape(n, -1), np.unpackbits(g["obs0"], axis=-1)[:, :D].astype(np.float32))
+        else:
+            assert np.allclose(o_obs, g["obs0"], atol=1e-6, rtol=0)
+        for t in range(g["action"].shape[0]):
+            if not minatar:   # fp32 physics: teacher-force nothing, but compare with a tolerance
+                pass
+            o_obs, o_st, o_r, o_d, info = env.step(g["step_keys"][t], o_st, g["action"][t])
+            if minatar:
+                assert np.array_equal(o_obs.reshape(n, -1), np.unpackbits(g["obs"][t], axis=-1)[:, :D].astype(np.float32)), t
+                assert np.array_equal(o_r, g["reward"][t]) and np.array_equal(o_d, g["done"][t]), t
+                assert np.array_equal(info["returned_episode_returns"], g["ret"][t]), t
+            else:
+                assert np.allclose(o_obs, g["obs"][t], atol=2e-5, rtol=0), t
+                assert np.array_equal(o_d, g["done"][t]), t
+    finally:
+        jr.DEFAULT_PARTITIONABLE = False
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLD, "jax_prng_ref.json")),
+                    reason="no reference-generated PRNG vectors committed")
+def test_oracle_prng_against_reference_generated_values():
+    ref = json.load(open(os.path.join(GOLD, "jax_prng_ref.json")))
+    for tag, vals in ref.items():
+        jr.DEFAULT_PARTITIONABLE = tag == "partitionable"
+        try:
+            k = jr.PRNGKey(1234)
+            assert jr.split(k, 2).tolist() == vals["split2"]
+            assert jr.split(k, 5).tolist() == vals["split5"]
+            assert jr.random_bits(k, (7,)).tolist() == vals["bits7"]
+            assert float(jr.uniform(k, ())) == vals["uniform"]
+            assert int(jr.randint(k, (), 0, 3)) == vals["randint3"]
+            assert jr.permutation_indices(k, 40).tolist() == vals["permutation40"]
+        finally:
+            jr.DEFAULT_PARTITIONABLE = False
+
+
+def test_bench_gpu_arm_does_not_import_oracle():
+    """bench.py may execute oracle/ only in its CPU legs (cpu_baseline / --impl reference): every `oracle` import must
+    sit inside cpu_port_steps, never at module level or in the GPU arm."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    offenders = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef):
+            for sub in ast.walk(node):
+                if isinstance(sub, (ast.Import, ast.ImportFrom)):
+                    names = [a.name for a in sub.names] if isinstance(sub, ast.Import) else [sub.module or ""]
+                    if any(n.split(".")[0] == "oracle" for n in names) and node.name != "cpu_port_steps":
+                        offenders.append(node.name)
+    for node in tree.body:
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            names = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""]
+            assert not any(n.split(".")[0] == "oracle" for n in names), "module-level oracle import in bench.py"
+    assert not offenders, offenders
+
+
+def test_seed_slices_cover_the_seed_axis_once():
+    from purejaxql_b200._runner import seed_slice
+    for S in (1, 2, 3, 8, 16, 128):
+        for w in (1, 2, 4, 8):
+            got = [seed_slice(S, r, w) for r in range(w)]
+            flat = [i for lo, hi in got for i in range(lo, hi)]
+            assert flat == list(range(S)), (S, w, got)
+    assert seed_slice(1, 1, 2) == (1, 1)          # NUM_SEEDS < world: the extra rank owns an empty slice
