@@ -120,12 +120,15 @@ int pqn_eps_greedy(const uint32_t* keys /*[N][2]*/, const float* q /*[N][A]*/, c
  *              (returned_episode_returns, returned_episode_lengths, timestep,
  *               returned_episode, discount) — :338 takes their means.  With
  *              info_done_only != 0 only steps with done contribute (the
- *              nanmean-where-returned_episode of get_test_metrics, :403-412). */
+ *              nanmean-where-returned_episode of get_test_metrics, :403-412).
+ *   env_total / env_offset: the E envs of this call are envs [env_offset, env_offset + E) of a vmap over env_total
+ *              envs (env-sharded data parallelism): per-env keys are split(key, env_total)[env_offset + e].
+ *              env_total <= 0 means env_total = E, env_offset = 0. */
 int pqn_rollout_act_step(int env_id, const uint32_t* step_keys, const float* q, const float* eps,
                          uint32_t* state, void* obs_next, int64_t obs_seed_stride, int32_t* action,
                          float* reward, uint8_t* done, float* maxq, int64_t tr_seed_stride, double* info_sums,
-                         int info_done_only, int32_t S, int32_t E, int max_steps, float rew_scale, int rng_mode,
-                         void* stream);
+                         int info_done_only, int32_t S, int32_t E, int32_t env_total, int32_t env_offset, int max_steps,
+                         float rew_scale, int rng_mode, void* stream);
 /* keys_out[T][S][2][2], rng_inout[S][2]: the scan carry chain
  * rng, rng_a, rng_s = split(rng, 3) for T steps (pqn_minatar.py:183). */
 int pqn_rollout_keys(uint32_t* rng_inout, uint32_t* keys_out, int32_t S, int32_t T, int rng_mode, void* stream);
@@ -224,6 +227,14 @@ int pqn_tc_split_lo(const float* x, float* lo, int64_t n, void* stream);
  *  split3: 3xTF32 with the *_lo operands from pqn_tc_split_lo; else one TF32 pass.  N % 128 == 0. */
 int pqn_tc_gemm_test(const float* a, const float* a_lo, const float* b, const float* b_lo, float* d, int32_t S,
                      int32_t M, int32_t N, int32_t K, int a_mn, int b_mn, int split3, void* stream);
+
+/* fp16-split planes for the default tensor-core path: hi = fp16(x*scale), lo = fp16((x*scale - hi) * 2^11), so that
+ * x*scale = hi + lo * 2^-11 to 22 significant bits (saturating at +-65000).  hi/lo: __half[n]. */
+int pqn_tc_split16(const float* x, void* hi, void* lo, int64_t n, float scale, void* stream);
+/* Test hook: D[s] = (A[s].B[s]) * out_scale through TMA -> tcgen05.mma(kind::f16) -> TMEM with the operands given as
+ * (hi, lo) fp16 planes (3 products per k-step: hi.hi into the main accumulator, lo.hi + hi.lo into the 2^-11 one). */
+int pqn_tc_gemm16_test(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* d, int32_t S,
+                       int32_t M, int32_t N, int32_t K, int a_mn, int b_mn, float out_scale, void* stream);
 
 /* Debug hook: one 128x128x32 tile; dumps the TMA-written smem tiles and the TMEM accumulator. */
 int pqn_tc_debug(const float* a, const float* b, float* dump_a, float* dump_b, float* out_d, uint32_t* info,

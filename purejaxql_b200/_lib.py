@@ -55,7 +55,7 @@ _SIGS = {
     "pqn_eps_greedy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int, c_void_p]),
     "pqn_rollout_act_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int32, c_int32,
-                                     c_int, c_float, c_int, c_void_p]),
+                                     c_int32, c_int32, c_int, c_float, c_int, c_void_p]),
     "pqn_rollout_keys": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int, c_void_p]),
     "pqn_qlambda": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                             c_float, c_float, c_void_p]),
@@ -73,6 +73,9 @@ _SIGS = {
     "pqn_set_tensor_core_path": (c_int, [c_int]),
     "pqn_set_conv_mma_path": (c_int, [c_int]),
     "pqn_tc_split_lo": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pqn_tc_split16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "pqn_tc_gemm16_test": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                   c_int32, c_int, c_int, c_float, c_void_p]),
     "pqn_tc_debug": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pqn_tc_gemm_test": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                  c_int32, c_int, c_int, c_int, c_void_p]),

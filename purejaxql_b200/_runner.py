@@ -39,6 +39,26 @@ def seed_slice(num_seeds, rank, world):
     return lo, min(num_seeds, lo + per)
 
 
+def pick_data_parallel(config, world):
+    """"seeds" | "envs" for this run: DATA_PARALLEL (this repo's key, not in the reference) = "seeds" shards the
+    independent seeds over the ranks (no collective); "envs" shards NUM_ENVS of every seed and all-reduces the
+    gradient once per minibatch step; "auto" (default) picks "envs" when there are fewer seeds than GPUs (the
+    shipped default is NUM_SEEDS=1, config/config.yaml:2)."""
+    if world <= 1:
+        return "seeds"
+    dp = config.get("DATA_PARALLEL", "auto")
+    if dp not in ("auto", "seeds", "envs"):
+        raise ValueError(f"DATA_PARALLEL={dp!r}: expected auto, seeds or envs")
+    if dp == "auto":
+        dp = "envs" if int(config["NUM_SEEDS"]) < world else "seeds"
+    if dp == "envs":
+        ne = int(config["NUM_ENVS"])
+        if ne % world or (int(config["NUM_STEPS"]) * ne // world) % int(config["NUM_MINIBATCHES"]):
+            raise ValueError(f"DATA_PARALLEL=envs: NUM_ENVS={ne} must split evenly over {world} ranks and "
+                             f"NUM_MINIBATCHES must divide NUM_STEPS*NUM_ENVS/{world}")
+    return dp
+
+
 def _shard_seeds(rngs):
     """Seeds are independent runs (jax.vmap over rngs, pqn_minatar.py:459-461):
     under torchrun each rank trains a contiguous slice of the same split(key, NUM_SEEDS)."""
@@ -61,21 +81,27 @@ def single_run(config, make_train, alg_file_name="pqn"):
         wandb.init(entity=config["ENTITY"], project=config["PROJECT"],
                    tags=[alg_name.upper(), env_name.upper(), "b200_native"],
                    name=f'{config["ALG_NAME"]}_{config["ENV_NAME"]}', config=config, mode=config["WANDB_MODE"])
-    init_distributed()
+    d_rank, d_world = init_distributed()
+    env_sharded = pick_data_parallel(config, d_world) == "envs"
     rng = jr.PRNGKey(config["SEED"])                                  # :456
     t0 = time.time()
     rngs = jr.split(rng, config["NUM_SEEDS"], int(config.get("JAX_THREEFRY_PARTITIONABLE", 0)))   # :459
-    local_rngs, rank, world = _shard_seeds(rngs)
+    if env_sharded:
+        local_rngs, rank, world = rngs, 0, 1                          # every rank trains every seed on its env shard;
+    else:                                                             # rank 0 alone saves (parameters are replicated)
+        local_rngs, rank, world = _shard_seeds(rngs)
     if local_rngs.shape[0] == 0:
         # NUM_SEEDS < world size in the seed-sharded mode: this rank has no run of its own (the env-sharded
         # mode, DATA_PARALLEL=envs, is what uses every GPU for a single seed)
         print(f"rank {rank}: no seeds assigned (NUM_SEEDS={config['NUM_SEEDS']} < world size {world})")
         return None
     train = make_train(config)
+    if env_sharded:
+        train.engine.env_shard = (d_rank, d_world)
     outs = train(local_rngs)                                          # :460-461 (seed axis is native)
     torch.cuda.synchronize()
     print(f"Took {time.time() - t0} seconds to complete.")
-    if config.get("SAVE_PATH", None) is not None:                     # :464-483
+    if config.get("SAVE_PATH", None) is not None and not (env_sharded and d_rank != 0):   # :464-483
         from .utils.save_load import save_params
         model_state = outs["runner_state"][0]
         save_dir = os.path.join(config["SAVE_PATH"], env_name)

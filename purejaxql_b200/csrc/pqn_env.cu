@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(ENV_BLOCK)
                             float* __restrict__ reward_out, uint8_t* __restrict__ done_out,
                             float* __restrict__ maxq_out, double* __restrict__ info_sums, int E, int max_steps,
                             float rew_scale, int part, int64_t obs_seed_stride, int64_t tr_seed_stride,
-                            int info_done_only) {
+                            int info_done_only, int E_total, int env_offset) {
   __shared__ uint32_t obs_smem[ObsScratch<Env>::WORDS];
   const int seed = blockIdx.y;
   const int e = blockIdx.x * ENV_BLOCK + threadIdx.x;
@@ -219,7 +219,10 @@ __global__ void __launch_bounds__(ENV_BLOCK)
     const Key ks{step_keys[seed * 4 + 2], step_keys[seed * 4 + 3]};
     const float eps = eps_p[0];
     float mq;
-    const int a = eps_greedy_one(split_at(ka, (uint32_t)E, (uint32_t)e, part), q + i * Env::NUM_ACTIONS,
+    // per-env keys are element (env_offset + e) of split(key, E_total): an env shard of a larger vmap (env-sharded
+    // data parallelism) draws exactly the keys the unsharded run gives those envs
+    const uint32_t ge = (uint32_t)(env_offset + e);
+    const int a = eps_greedy_one(split_at(ka, (uint32_t)E_total, ge, part), q + i * Env::NUM_ACTIONS,
                                  Env::NUM_ACTIONS, eps, part, mq);
     typename Env::State s;
     Env::load(s, state, N, i);
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(ENV_BLOCK)
     log_load(lg, state, N, i, Env::CORE_WORDS);
     float r;
     bool d;
-    env_step_full<Env>(split_at(ks, (uint32_t)E, (uint32_t)e, part), part, max_steps, s, lg, a, r, d);
+    env_step_full<Env>(split_at(ks, (uint32_t)E_total, ge, part), part, max_steps, s, lg, a, r, d);
     Env::store(s, state, N, i);
     log_store(lg, state, N, i, Env::CORE_WORDS);
     const int64_t io = (int64_t)seed * obs_seed_stride + e;
@@ -451,16 +454,21 @@ int pqn_eps_greedy(const uint32_t* keys, const float* q, const float* eps, int32
 int pqn_rollout_act_step(int env_id, const uint32_t* step_keys, const float* q, const float* eps, uint32_t* state,
                          void* obs_next, int64_t obs_seed_stride, int32_t* action, float* reward, uint8_t* done,
                          float* maxq, int64_t tr_seed_stride, double* info_sums, int info_done_only, int32_t S,
-                         int32_t E, int max_steps, float rew_scale, int rng_mode, void* stream) {
+                         int32_t E, int32_t env_total, int32_t env_offset, int max_steps, float rew_scale, int rng_mode,
+                         void* stream) {
   if (!step_keys || !q || !eps || !state || !obs_next || !action || !reward || !done || !maxq || S <= 0 || E <= 0)
     return set_error(PQN_E_INVALID, "pqn_rollout_act_step: bad argument");
+  if (env_total <= 0) { env_total = E; env_offset = 0; }
+  if (env_offset < 0 || env_offset + E > env_total)
+    return set_error(PQN_E_INVALID, "pqn_rollout_act_step: env shard [%d, %d) outside [0, %d)", env_offset,
+                     env_offset + E, env_total);
   if (S > 65535) return set_error(PQN_E_INVALID, "pqn_rollout_act_step: S=%d exceeds gridDim.y", S);
   PQN_ENV_DISPATCH(env_id, {
     const int ms = max_steps > 0 ? max_steps : EnvT::DEFAULT_MAX_STEPS;
     dim3 grid(blocks_for(E, ENV_BLOCK), (unsigned)S);
     { LaunchScope _ls(K_ROLLOUT_ACT_STEP, (cudaStream_t)stream); rollout_act_step_kernel<EnvT><<<grid, ENV_BLOCK, 0, (cudaStream_t)stream>>>(
         step_keys, q, eps, state, obs_next, action, reward, done, maxq, info_sums, E, ms, rew_scale, rng_mode,
-        obs_seed_stride, tr_seed_stride, info_done_only); }
+        obs_seed_stride, tr_seed_stride, info_done_only, env_total, env_offset); }
   });
   return check_launch("pqn_rollout_act_step");
 }

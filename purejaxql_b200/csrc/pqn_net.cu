@@ -29,7 +29,7 @@ constexpr int HID_CNN = 128;
 constexpr int FLAT_CNN = CONV_PIX * CONV_O;  // 1024
 
 // tcgen05 path for the CNN dense layer (pqn_set_tensor_core_path); default on
-static int g_use_tc = 2;  // 0 FFMA, 1 tcgen05 with A_lo tensors in memory, 2 tcgen05 with in-kernel A_lo (default)
+static int g_use_tc = 2;  // 0 FFMA, 1 tcgen05 3xTF32 (A_lo derived in the kernel), 2 tcgen05 fp16-split planes (default)
 // warp-level tensor-core (mma.sync tf32) conv kernels (pqn_set_conv_mma_path); default on
 static int g_conv_mma = 1;   // 0: fp32 CUDA cores, 1: mma.sync tf32, 2: tcgen05 forward (+ mma.sync backward)
 
@@ -437,7 +437,8 @@ __global__ void __launch_bounds__(GT) dgrad_kernel(const float* __restrict__ DZ,
 template <int N, bool HEAD>
 __global__ void __launch_bounds__(256) row_bwd_kernel(
     const float* __restrict__ Hh, const float* __restrict__ XHAT, const float* __restrict__ RSTD,
-    const float* DH, float* DZ, float* DZLO, const float* __restrict__ params, float* __restrict__ grads, int64_t P,
+    const float* DH, float* DZ, float* DZLO, __half* DZ16H, __half* DZ16L, float gscale,
+    const float* __restrict__ params, float* __restrict__ grads, int64_t P,
     int64_t off_scale, int64_t off_dscale, int64_t off_dbias, int64_t off_db, int64_t off_hw, int64_t off_hb, int A,
     const int32_t* __restrict__ gather, const int32_t* __restrict__ action, const float* __restrict__ target,
     int64_t tr_rows_per_seed, float* __restrict__ loss_sum, float* __restrict__ qsa_sum, int rows) {
@@ -552,6 +553,16 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
 #pragma unroll
     for (int c = 0; c < F / 4; ++c)
     {
+      if (DZ16H != nullptr) {  // fp16-split planes of dz * gscale for the tensor-core wgrad / dgrad (no fp32 copy)
+        __half2 h0, h1, l0, l1;
+        tc::split16x2(dz[4 * c] * gscale, dz[4 * c + 1] * gscale, h0, l0);
+        tc::split16x2(dz[4 * c + 2] * gscale, dz[4 * c + 3] * gscale, h1, l1);
+        *reinterpret_cast<uint2*>(DZ16H + grow * N + c * 128 + lane * 4) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(DZ16L + grow * N + c * 128 + lane * 4) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+        continue;
+      }
       *reinterpret_cast<float4*>(DZ + grow * N + c * 128 + lane * 4) =
           make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
       if (DZLO != nullptr)
@@ -1084,7 +1095,10 @@ __device__ __forceinline__ void ln16_quad(const float (&z)[2][4], float& mean0, 
 
 constexpr int CONV_MMA_WARPS = 8;
 
-template <int C, bool TRAIN>
+// H16: the activation goes out as the two fp16 planes of the fp16-split tensor-core path (H1 = hi plane, H1LO = lo'
+// plane, both __half[rows][1024]) instead of fp32 h1 -- the same 4 bytes per element, so the dense GEMMs read
+// (hi, lo') straight through TMA and no operand conversion happens in the GEMM kernel.
+template <int C, bool TRAIN, bool H16 = false>
 __global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
     conv_fwd_mma_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
                         const float* __restrict__ params, int64_t P, pqn_net_layout_t L, float* __restrict__ H1,
@@ -1140,8 +1154,10 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
     build_exp_patch<C>(my_so, lane, sxp[warp] + lane * ExpPatch<C>::LD);
     build_exp_patch<C>(my_so, lane + 32, sxp[warp] + (lane + 32) * ExpPatch<C>::LD);
     __syncwarp();
-    float* __restrict__ hrow = H1 + ((int64_t)seed * rows + row) * FLAT_CNN;
-    float* __restrict__ lrow = H1LO ? H1LO + ((int64_t)seed * rows + row) * FLAT_CNN : nullptr;
+    float* __restrict__ hrow = H16 ? nullptr : H1 + ((int64_t)seed * rows + row) * FLAT_CNN;
+    float* __restrict__ lrow = (!H16 && H1LO) ? H1LO + ((int64_t)seed * rows + row) * FLAT_CNN : nullptr;
+    __half* __restrict__ hrow16 = H16 ? reinterpret_cast<__half*>(H1) + ((int64_t)seed * rows + row) * FLAT_CNN : nullptr;
+    __half* __restrict__ lrow16 = H16 ? reinterpret_cast<__half*>(H1LO) + ((int64_t)seed * rows + row) * FLAT_CNN : nullptr;
     float* __restrict__ xrow = (TRAIN && XH1) ? XH1 + ((int64_t)seed * rows + row) * FLAT_CNN : nullptr;
     float* __restrict__ rrow = (TRAIN && RS1) ? RS1 + ((int64_t)seed * rows + row) * CONV_PIX : nullptr;
     // packed ReLU mask for the dense dgrad epilogue: bit (pixel * 16 + channel) = (h1 > 0), 16 bits per pixel
@@ -1167,8 +1183,18 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
         v1.x = fmaxf((z[h][2] - mean1) * rstd1 * sc[o] + bi[o], 0.f);
         v1.y = fmaxf((z[h][3] - mean1) * rstd1 * sc[o + 1] + bi[o + 1], 0.f);
         const int p0 = 16 * mb + g, p1 = p0 + 8;
-        *reinterpret_cast<float2*>(hrow + p0 * CONV_O + o) = v0;
-        *reinterpret_cast<float2*>(hrow + p1 * CONV_O + o) = v1;
+        if (H16) {
+          __half2 h0, l0, h1v, l1;
+          tc::split16x2(v0.x, v0.y, h0, l0);
+          tc::split16x2(v1.x, v1.y, h1v, l1);
+          *reinterpret_cast<__half2*>(hrow16 + p0 * CONV_O + o) = h0;
+          *reinterpret_cast<__half2*>(lrow16 + p0 * CONV_O + o) = l0;
+          *reinterpret_cast<__half2*>(hrow16 + p1 * CONV_O + o) = h1v;
+          *reinterpret_cast<__half2*>(lrow16 + p1 * CONV_O + o) = l1;
+        } else {
+          *reinterpret_cast<float2*>(hrow + p0 * CONV_O + o) = v0;
+          *reinterpret_cast<float2*>(hrow + p1 * CONV_O + o) = v1;
+        }
         if (TRAIN) {
           rb0 |= ((v0.x > 0.f ? 1u : 0u) | (v0.y > 0.f ? 2u : 0u)) << o;
           rb1 |= ((v1.x > 0.f ? 1u : 0u) | (v1.y > 0.f ? 2u : 0u)) << o;
@@ -1836,7 +1862,8 @@ static unsigned conv_mma_ctas(int S, int rows, int ctas_per_sm) {
 template <bool TRAIN>
 static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
                            const float* params, int64_t P, const pqn_net_layout_t& L, float* h1, float* h1lo, float* bn,
-                           int rows, float* xh1 = nullptr, float* rs1 = nullptr, uint32_t* rb = nullptr) {
+                           int rows, float* xh1 = nullptr, float* rs1 = nullptr, uint32_t* rb = nullptr,
+                           bool h16 = false) {
   if (g_conv_mma == 2) {
     const int S = (int)grid.y;
     switch (C) {
@@ -1846,6 +1873,18 @@ static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* ob
       case 10: return launch_conv_fwd_tc_t<10, TRAIN>(S, st, obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, bn, rows);
       default: return -1;
     }
+  }
+  if (g_conv_mma && h16) {  // h1 / h1lo are the fp16 (hi, lo') planes
+    const dim3 mg(conv_mma_ctas((int)grid.y, rows, 3), grid.y);
+    LaunchScope _ls(TRAIN ? K_CONV_FWD : K_CONV_FWD_INFER, st);
+    switch (C) {
+      case 4: conv_fwd_mma_kernel<4, TRAIN, true><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
+      case 6: conv_fwd_mma_kernel<6, TRAIN, true><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
+      case 7: conv_fwd_mma_kernel<7, TRAIN, true><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
+      case 10: conv_fwd_mma_kernel<10, TRAIN, true><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
+      default: return -1;
+    }
+    return 0;
   }
   if (g_conv_mma) {
     const dim3 mg(conv_mma_ctas((int)grid.y, rows, 3), grid.y);
@@ -1903,6 +1942,106 @@ static void launch_split_w1(const float* params, int64_t P, int64_t off_w, float
   split_lo_strided_kernel<<<dim3(cdiv(n / 4, 256), S), 256, 0, st>>>(params + off_w, P, w1_lo, n);
 }
 
+// ---- fp16-split tensor-core path (g_use_tc == 2) ------------------------------------------------------------------
+// planes inside the workspace (no extra memory: they alias the fp32 "lo" tensors of the tf32 path, same byte size):
+//   h1 planes  : w.h1_lo  region  -> __half hi[R][1024], lo'[R][1024]
+//   dz2 planes : w.dz2_lo region  -> __half hi[R][128],  lo'[R][128]      (dz2 * gscale)
+//   W1 planes  : w.w1_lo  region  -> __half hi[S][1024][128], lo'[S][1024][128]
+struct Planes16 { __half *h1_hi, *h1_lo, *dz_hi, *dz_lo, *w1_hi, *w1_lo; };
+static Planes16 planes16(const Workspace& w, int S, int64_t rows) {
+  const int64_t R = (int64_t)S * rows;
+  Planes16 p;
+  p.h1_hi = reinterpret_cast<__half*>(w.h1_lo); p.h1_lo = p.h1_hi + R * FLAT_CNN;
+  p.dz_hi = reinterpret_cast<__half*>(w.dz2_lo); p.dz_lo = p.dz_hi + R * HID_CNN;
+  p.w1_hi = reinterpret_cast<__half*>(w.w1_lo); p.w1_lo = p.w1_hi + (int64_t)S * FLAT_CNN * HID_CNN;
+  return p;
+}
+// dz2 is pre-scaled by a power of two so that gradient-sized values (|dz2| ~ |diff| / rows) sit in the middle of the
+// fp16 range: gscale = 16 * 2^ceil(log2(rows)); the GEMM epilogues multiply by 1 / gscale (exact).
+static float grad_scale(int64_t rows) {
+  float s = 16.f;
+  while (rows > 1) { s *= 2.f; rows = (rows + 1) >> 1; }
+  return s;
+}
+
+__global__ void split16_strided_kernel(const float* __restrict__ src, int64_t src_seed_stride, __half* __restrict__ hi,
+                                       __half* __restrict__ lo, int64_t n_per_seed) {
+  const int seed = blockIdx.y;
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n_per_seed) return;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)seed * src_seed_stride) + i4);
+  __half2 h0, h1, l0, l1;
+  tc::split16x2(v.x, v.y, h0, l0);
+  tc::split16x2(v.z, v.w, h1, l1);
+  reinterpret_cast<uint2*>(hi + (int64_t)seed * n_per_seed)[i4] =
+      make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  reinterpret_cast<uint2*>(lo + (int64_t)seed * n_per_seed)[i4] =
+      make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+}
+
+static void launch_split16_w1(const float* params, int64_t P, int64_t off_w, const Planes16& pl, int S, cudaStream_t st) {
+  const int64_t n = (int64_t)FLAT_CNN * HID_CNN;
+  LaunchScope _ls(K_TC_SPLIT, st);
+  split16_strided_kernel<<<dim3(cdiv(n / 4, 256), S), 256, 0, st>>>(params + off_w, P, pl.w1_hi, pl.w1_lo, n);
+}
+// fp32 h1 (conv paths that do not write planes themselves) -> planes
+static void launch_split16_h1(const float* h1, const Planes16& pl, int64_t n, cudaStream_t st) {
+  LaunchScope _ls(K_TC_SPLIT, st);
+  split16_strided_kernel<<<dim3(cdiv(n / 4, 256), 1), 256, 0, st>>>(h1, 0, pl.h1_hi, pl.h1_lo, n);
+}
+
+static int tc16_dense_fwd(int epi, const float* params, int64_t P, const pqn_net_layout_t& L, const Workspace& w,
+                          const Planes16& pl, int A, float* q, int S, int rows, cudaStream_t st) {
+  CUtensorMap t[4];
+  int rc;
+  if ((rc = tc::make_tmap16(&t[0], pl.h1_hi, FLAT_CNN, rows, S, FLAT_CNN, (uint64_t)rows * FLAT_CNN, 128))) return rc;
+  if ((rc = tc::make_tmap16(&t[1], pl.h1_lo, FLAT_CNN, rows, S, FLAT_CNN, (uint64_t)rows * FLAT_CNN, 128))) return rc;
+  if ((rc = tc::make_tmap16(&t[2], pl.w1_hi, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)FLAT_CNN * HID_CNN, 64))) return rc;
+  if ((rc = tc::make_tmap16(&t[3], pl.w1_lo, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)FLAT_CNN * HID_CNN, 64))) return rc;
+  tc::GemmShape gs = {};
+  gs.S = S; gs.M = rows; gs.m_tiles = (rows + 127) / 128; gs.n_tiles = 1; gs.k_blocks = FLAT_CNN / tc::TC_BK16; gs.split3 = 1;
+  tc::EpiParams ep = {};
+  ep.params = params; ep.P = P; ep.off_b = L.d0_b; ep.off_scale = L.ln1_scale; ep.off_bias = L.ln1_bias;
+  ep.off_hw = L.head_w; ep.off_hb = L.head_b; ep.A = A; ep.rows = rows;
+  ep.H = w.h2; ep.XHAT = w.xhat2; ep.RSTD = w.rstd2; ep.Q = q;
+  return tc::launch_gemm16(0, 1, epi, t, gs, ep, st, epi == tc::EPI_LN_HEAD ? K_TC_FWD_HEAD : K_TC_FWD);
+}
+
+static int tc16_wgrad(float* grads, int64_t P, const pqn_net_layout_t& L, const Planes16& pl, int S, int rows,
+                      float gscale, cudaStream_t st) {
+  CUtensorMap t[4];
+  int rc;
+  if ((rc = tc::make_tmap16(&t[0], pl.h1_hi, FLAT_CNN, rows, S, FLAT_CNN, (uint64_t)rows * FLAT_CNN, 64))) return rc;
+  if ((rc = tc::make_tmap16(&t[1], pl.h1_lo, FLAT_CNN, rows, S, FLAT_CNN, (uint64_t)rows * FLAT_CNN, 64))) return rc;
+  if ((rc = tc::make_tmap16(&t[2], pl.dz_hi, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 64))) return rc;
+  if ((rc = tc::make_tmap16(&t[3], pl.dz_lo, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 64))) return rc;
+  tc::GemmShape gs = {};
+  gs.S = S; gs.M = FLAT_CNN; gs.m_tiles = FLAT_CNN / 128; gs.n_tiles = 1;
+  gs.k_blocks = (rows + tc::TC_BK16 - 1) / tc::TC_BK16; gs.split3 = 1;
+  tc::EpiParams ep = {};
+  ep.out = grads + L.d0_w; ep.ld_out = HID_CNN; ep.out_seed_stride = P; ep.out_scale = 1.0f / gscale;
+  return tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD);
+}
+
+// dY1 = relu_mask * (dZ2 . W1^T) into w.h1 (fp32; the fp16 path has no fp32 h1, so this is not in place unless the
+// mask itself is the fp32 h1 of a conv path that wrote one)
+static int tc16_dgrad(const Workspace& w, const Planes16& pl, int S, int rows, bool have_bits, float gscale,
+                      cudaStream_t st) {
+  CUtensorMap t[4];
+  int rc;
+  if ((rc = tc::make_tmap16(&t[0], pl.dz_hi, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 128))) return rc;
+  if ((rc = tc::make_tmap16(&t[1], pl.dz_lo, HID_CNN, rows, S, HID_CNN, (uint64_t)rows * HID_CNN, 128))) return rc;
+  if ((rc = tc::make_tmap16(&t[2], pl.w1_hi, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)FLAT_CNN * HID_CNN, 128))) return rc;
+  if ((rc = tc::make_tmap16(&t[3], pl.w1_lo, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)FLAT_CNN * HID_CNN, 128))) return rc;
+  tc::GemmShape gs = {};
+  gs.S = S; gs.M = rows; gs.m_tiles = (rows + 127) / 128; gs.n_tiles = FLAT_CNN / 128; gs.k_blocks = HID_CNN / tc::TC_BK16;
+  gs.split3 = 1;
+  tc::EpiParams ep = {};
+  ep.out = w.h1; ep.mask = w.h1; ep.ld_out = FLAT_CNN; ep.out_seed_stride = (int64_t)rows * FLAT_CNN;
+  ep.relu_bits = w.relu_bits; ep.rows = rows; ep.out_scale = 1.0f / gscale;
+  return tc::launch_gemm16(0, 0, have_bits ? tc::EPI_RELU_BITS : tc::EPI_RELU_MASK, t, gs, ep, st, K_TC_DGRAD);
+}
+
 // Z = H1 . W1 on the tcgen05 path with the LayerNorm/ReLU(/head) epilogue.  epi = EPI_LN_TRAIN or EPI_LN_HEAD.
 static int tc_dense_fwd(int epi, const float* params, int64_t P, const pqn_net_layout_t& L, const Workspace& w, int A,
                         float* q, int S, int rows, cudaStream_t st) {
@@ -1914,7 +2053,7 @@ static int tc_dense_fwd(int epi, const float* params, int64_t P, const pqn_net_l
   if ((rc = tc::make_tmap(&t[3], w.w1_lo, HID_CNN, FLAT_CNN, S, HID_CNN, (uint64_t)FLAT_CNN * HID_CNN, 32, 1))) return rc;
   tc::GemmShape gs = {};
   gs.S = S; gs.M = rows; gs.m_tiles = (rows + 127) / 128; gs.n_tiles = 1; gs.k_blocks = FLAT_CNN / tc::TC_BK; gs.split3 = 1;
-  gs.a_lo_inline = g_use_tc == 2;
+  gs.a_lo_inline = 1;
   tc::EpiParams ep = {};
   ep.params = params; ep.P = P; ep.off_b = L.d0_b; ep.off_scale = L.ln1_scale; ep.off_bias = L.ln1_bias;
   ep.off_hw = L.head_w; ep.off_hb = L.head_b; ep.A = A; ep.rows = rows;
@@ -1934,7 +2073,7 @@ static int tc_wgrad(float* grads, int64_t P, const pqn_net_layout_t& L, const Wo
   tc::GemmShape gs = {};
   gs.S = S; gs.M = FLAT_CNN; gs.m_tiles = FLAT_CNN / 128; gs.n_tiles = 1; gs.k_blocks = (rows + tc::TC_BK - 1) / tc::TC_BK;
   gs.split3 = 1;
-  gs.a_lo_inline = g_use_tc == 2;
+  gs.a_lo_inline = 1;
   tc::EpiParams ep = {};
   ep.out = grads + L.d0_w; ep.ld_out = HID_CNN; ep.out_seed_stride = P;
   return tc::launch_gemm(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD);
@@ -2002,9 +2141,17 @@ int pqn_qnet_forward(const pqn_net_desc_t* d, const float* params, const void* o
   const int A = d->num_actions;
   if (d->kind == PQN_NET_MINATAR_CNN) {
     const bool use_tc = g_use_tc && A <= PQN_TC_MAX_A;
+    const bool f16 = use_tc && g_use_tc == 2;
+    const Planes16 pl = planes16(w, S, rows);
+    const bool conv16 = f16 && g_conv_mma == 1;   // the mma.sync conv writes the fp16 planes itself
     launch_conv_fwd<false>(d->in_c, dim3(cdiv(rows, 4), S), st, (const uint32_t*)obs, obs_rows_per_seed, gather, params,
-                           L.total, L, w.h1, (use_tc && g_use_tc == 1) ? w.h1_lo : nullptr, nullptr, (int)rows);
-    if (use_tc) {
+                           L.total, L, conv16 ? (float*)pl.h1_hi : w.h1, conv16 ? (float*)pl.h1_lo : nullptr, nullptr,
+                           (int)rows, nullptr, nullptr, nullptr, conv16);
+    if (f16) {
+      if (!conv16) launch_split16_h1(w.h1, pl, (int64_t)S * rows * FLAT_CNN, st);
+      launch_split16_w1(params, L.total, L.d0_w, pl, S, st);
+      if ((rc = tc16_dense_fwd(tc::EPI_LN_HEAD, params, L.total, L, w, pl, A, q, S, (int)rows, st))) return rc;
+    } else if (use_tc) {
       launch_split_w1(params, L.total, L.d0_w, w.w1_lo, S, st);
       if ((rc = tc_dense_fwd(tc::EPI_LN_HEAD, params, L.total, L, w, A, q, S, (int)rows, st))) return rc;
     } else {
@@ -2059,10 +2206,19 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
   if (d->kind == PQN_NET_MINATAR_CNN) {
     const uint32_t* ob = (const uint32_t*)obs;
     const bool use_tc = g_use_tc && A <= PQN_TC_MAX_A;
-    launch_conv_fwd<true>(d->in_c, dim3(cdiv(rows, 4), S), st, ob, obs_rows_per_seed, gather, params, P, L, w.h1,
-                          (use_tc && g_use_tc == 1) ? w.h1_lo : nullptr, bn_sums, R, g_conv_mma ? w.cxhat : nullptr,
-                          g_conv_mma ? w.crstd : nullptr, g_conv_mma == 1 ? w.relu_bits : nullptr);
-    if (use_tc) {
+    const bool f16 = use_tc && g_use_tc == 2;
+    const Planes16 pl = planes16(w, S, rows);
+    const bool conv16 = f16 && g_conv_mma == 1;
+    const float gscale = f16 ? grad_scale(rows) : 1.0f;
+    launch_conv_fwd<true>(d->in_c, dim3(cdiv(rows, 4), S), st, ob, obs_rows_per_seed, gather, params, P, L,
+                          conv16 ? (float*)pl.h1_hi : w.h1, conv16 ? (float*)pl.h1_lo : nullptr, bn_sums, R,
+                          g_conv_mma ? w.cxhat : nullptr, g_conv_mma ? w.crstd : nullptr,
+                          g_conv_mma == 1 ? w.relu_bits : nullptr, conv16);
+    if (f16) {
+      if (!conv16) launch_split16_h1(w.h1, pl, (int64_t)S * rows * FLAT_CNN, st);
+      launch_split16_w1(params, P, L.d0_w, pl, S, st);
+      if ((rc = tc16_dense_fwd(tc::EPI_LN_TRAIN, params, P, L, w, pl, A, nullptr, S, R, st))) return rc;
+    } else if (use_tc) {
       launch_split_w1(params, P, L.d0_w, w.w1_lo, S, st);
       if ((rc = tc_dense_fwd(tc::EPI_LN_TRAIN, params, P, L, w, A, nullptr, S, R, st))) return rc;
     } else {
@@ -2070,10 +2226,14 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
                       L.ln1_scale, L.ln1_bias, 0, 0, A, w.h2, w.xhat2, w.rstd2, nullptr, R, FLAT_CNN);
     }
     const dim3 rbg(conv_mma_ctas(S, R, 4), S);
-    { launch_row_bwd<128, true>(rbg, A, st,
-        w.h2, w.xhat2, w.rstd2, nullptr, w.dz2, use_tc ? w.dz2_lo : nullptr, params, grads, P, L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d0_b,
-        L.head_w, L.head_b, A, gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, R); }
-    if (use_tc) {
+    if ((rc = launch_row_bwd<128, true>(rbg, A, st,
+        w.h2, w.xhat2, w.rstd2, nullptr, w.dz2, (use_tc && !f16) ? w.dz2_lo : nullptr, f16 ? pl.dz_hi : nullptr,
+        f16 ? pl.dz_lo : nullptr, gscale, params, grads, P, L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d0_b,
+        L.head_w, L.head_b, A, gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, R))) return rc;
+    if (f16) {
+      if ((rc = tc16_wgrad(grads, P, L, pl, S, R, gscale, st))) return rc;
+      if ((rc = tc16_dgrad(w, pl, S, R, g_conv_mma == 1, gscale, st))) return rc;
+    } else if (use_tc) {
       if ((rc = tc_wgrad(grads, P, L, w, S, R, st))) return rc;
       if ((rc = tc_dgrad(params, P, L, w, S, R, g_conv_mma == 1, st))) return rc;
     } else {
@@ -2115,12 +2275,12 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
       launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.h0, rows * H, H, params, P, L.d1_w, L.d1_b, L.ln1_scale,
                       L.ln1_bias, 0, 0, A, w.hh1, w.xhat1, w.rstd1, nullptr, R, H);
       if (H == 128)
-        { launch_row_bwd<128, true>(rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, params, grads, P,
+        { launch_row_bwd<128, true>(rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
                                                         L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }
       else
-        { launch_row_bwd<256, true>(rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, params, grads, P,
+        { launch_row_bwd<256, true>(rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
                                                         L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }
@@ -2131,11 +2291,11 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
       { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(w.dzl, rows * H, H, params, P, L.d1_w, w.h0,
                                                                      w.dh0, rows * H, R, H); }
       if (H == 128)
-        { launch_row_bwd<128, false>(rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, params, grads, P,
+        { launch_row_bwd<128, false>(rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
                                                          L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
                                                          nullptr, nullptr, nullptr, 0, nullptr, nullptr, R); }
       else
-        { launch_row_bwd<256, false>(rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, params, grads, P,
+        { launch_row_bwd<256, false>(rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
                                                          L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
                                                          nullptr, nullptr, nullptr, 0, nullptr, nullptr, R); }
       const int sp0 = wgrad_splits(H / 128, S, R);
@@ -2143,12 +2303,12 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
                                                                         P, L.d0_w, R, D, sp0); }
     } else {
       if (H == 128)
-        { launch_row_bwd<128, true>(rbg, A, st, w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, params, grads, P,
+        { launch_row_bwd<128, true>(rbg, A, st, w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }
       else
-        { launch_row_bwd<256, true>(rbg, A, st, w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, params, grads, P,
+        { launch_row_bwd<256, true>(rbg, A, st, w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
                                                         L.head_b, A, gather, action, target, tr_rows_per_seed,
                                                         loss_sum, qsa_sum, R); }

@@ -210,7 +210,7 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[1
 // back and awaited once (FIRST: all four 32-column loads straight into acc; otherwise two at a time, 64 staging
 // registers) -- the per-load round trip to TMEM was the longest part of the epilogue's dependent chain.
 template <bool FIRST>
-__device__ __forceinline__ void tmem_accumulate_row(uint32_t row_addr, float (&acc)[128]) {
+__device__ __forceinline__ void tmem_accumulate_row(uint32_t row_addr, float (&acc)[128], float scale = 1.0f) {
   if constexpr (FIRST) {
     uint32_t v0[32], v1[32], v2[32], v3[32];
     tmem_ld_32x32b_x32(row_addr, v0);
@@ -232,8 +232,8 @@ __device__ __forceinline__ void tmem_accumulate_row(uint32_t row_addr, float (&a
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        acc[c * 64 + j] += __uint_as_float(v0[j]);
-        acc[c * 64 + 32 + j] += __uint_as_float(v1[j]);
+        acc[c * 64 + j] = fmaf(__uint_as_float(v0[j]), scale, acc[c * 64 + j]);   // scale == 1: exact add
+        acc[c * 64 + 32 + j] = fmaf(__uint_as_float(v1[j]), scale, acc[c * 64 + 32 + j]);
       }
     }
   }
@@ -251,7 +251,7 @@ __device__ __forceinline__ void tmem_accumulate_row(uint32_t row_addr, float (&a
 //     buffer with accumulate=0.
 // TMEM columns: main[2] at 0/128, corr[2] at 256/384.
 // ---------------------------------------------------------------------------
-template <int A_MN, int B_MN, int EPI>
+template <int A_MN, int B_MN, int EPI, bool F16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -300,7 +300,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int tiles_per_seed = gs.m_tiles * gs.n_tiles;
   const int num_tiles = tiles_per_seed * gs.S;
 
-  const bool a_lo_tma = gs.split3 && !gs.a_lo_inline;
+  // F16: fp16 operand planes (hi, lo'), 64-element k-blocks, A_lo' always comes from memory (no converter warps)
+  const bool a_lo_tma = gs.split3 && (F16 || !gs.a_lo_inline);
+  const bool a_lo_conv = !F16 && gs.split3 && gs.a_lo_inline;
+  constexpr int BKE = F16 ? TC_BK16 : TC_BK;              // elements per k-block
+  constexpr int MNB = F16 ? 2 : 4;                        // MN-major TMA boxes per 128-wide tile
+  constexpr int MNB_ELEMS = F16 ? 64 : 32, MNB_BYTES = F16 ? 8192 : 4096;
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -314,12 +319,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           mbar_wait(&empty[stage], phase ^ 1u);
           const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
           mbar_expect_tx(&full[stage], gs.split3 ? (a_lo_tma ? TC_STAGE_BYTES : 3 * TC_TILE_BYTES) : TC_STAGE_BYTES / 2);
-          const int k0 = kb * TC_BK;
+          const int k0 = kb * BKE;
           if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              tma_load_3d(sb + TC_A_HI + j * 4096, &tm_a_hi, &full[stage], m0 + 32 * j, k0, seed);
-              if (a_lo_tma) tma_load_3d(sb + TC_A_LO + j * 4096, &tm_a_lo, &full[stage], m0 + 32 * j, k0, seed);
+            for (int j = 0; j < MNB; ++j) {
+              tma_load_3d(sb + TC_A_HI + j * MNB_BYTES, &tm_a_hi, &full[stage], m0 + MNB_ELEMS * j, k0, seed);
+              if (a_lo_tma) tma_load_3d(sb + TC_A_LO + j * MNB_BYTES, &tm_a_lo, &full[stage], m0 + MNB_ELEMS * j, k0, seed);
             }
           } else {
             tma_load_3d(sb + TC_A_HI, &tm_a_hi, &full[stage], k0, m0, seed);
@@ -327,9 +332,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              tma_load_3d(sb + TC_B_HI + j * 4096, &tm_b_hi, &full[stage], n0 + 32 * j, k0, seed);
-              if (gs.split3) tma_load_3d(sb + TC_B_LO + j * 4096, &tm_b_lo, &full[stage], n0 + 32 * j, k0, seed);
+            for (int j = 0; j < MNB; ++j) {
+              tma_load_3d(sb + TC_B_HI + j * MNB_BYTES, &tm_b_hi, &full[stage], n0 + MNB_ELEMS * j, k0, seed);
+              if (gs.split3) tma_load_3d(sb + TC_B_LO + j * MNB_BYTES, &tm_b_lo, &full[stage], n0 + MNB_ELEMS * j, k0, seed);
             }
           } else {
             tma_load_3d(sb + TC_B_HI, &tm_b_hi, &full[stage], k0, n0, seed);
@@ -342,7 +347,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, 128, A_MN, B_MN);
+      const uint32_t idesc = F16 ? make_idesc_f16(128, 128, A_MN, B_MN) : make_idesc_tf32(128, 128, A_MN, B_MN);
+      auto sdesc_a = [](uint32_t tile, int ks) { return F16 ? make_sdesc16<A_MN>(tile, ks) : make_sdesc<A_MN>(tile, ks); };
+      auto sdesc_b = [](uint32_t tile, int ks) { return F16 ? make_sdesc16<B_MN>(tile, ks) : make_sdesc<B_MN>(tile, ks); };
+      auto umma = [](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+        if (F16) umma_f16(d, da, db, id, acc); else umma_tf32(d, da, db, id, acc);
+      };
       int stage = 0;
       uint32_t phase = 0;
       int mb = 0, cb = 0;
@@ -350,7 +360,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       // Short-K mode (k_blocks <= TC_PROMOTE, e.g. dgrad with K = 128): the whole tile is one promotion chunk, so the
       // correction terms share the main accumulator (a chain of <= 48 MMAs keeps the truncation drift ~1e-6) and the
       // four 128-column TMEM regions form one ring of accumulators: the epilogue reads each tile once.
-      const bool single_acc = gs.split3 && gs.k_blocks <= TC_PROMOTE;
+      // (tf32 only: the f16 path keeps the cross products in units of 2^-11, so they need their own accumulator)
+      const bool single_acc = !F16 && gs.split3 && gs.k_blocks <= TC_PROMOTE;
       if (single_acc) {
         int ab = 0;
         uint32_t ab_phase = 0;
@@ -363,16 +374,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           bool first = true;
           for (int kb = 0; kb < gs.k_blocks; ++kb) {
             mbar_wait(&full[stage], phase);
-            if (gs.a_lo_inline) mbar_wait(&lo_full[stage], phase);
+            if (a_lo_conv) mbar_wait(&lo_full[stage], phase);
             tcgen05_fence_after();
             const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
 #pragma unroll
-            for (int ks = 0; ks < TC_BK / 8; ++ks) {
-              const uint64_t a_hi = make_sdesc<A_MN>(sb + TC_A_HI, ks), a_lo = make_sdesc<A_MN>(sb + TC_A_LO, ks);
-              const uint64_t b_hi = make_sdesc<B_MN>(sb + TC_B_HI, ks), b_lo = make_sdesc<B_MN>(sb + TC_B_LO, ks);
-              umma_tf32(d_acc, a_lo, b_hi, idesc, first ? 0u : 1u);
-              umma_tf32(d_acc, a_hi, b_lo, idesc, 1u);
-              umma_tf32(d_acc, a_hi, b_hi, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t a_hi = sdesc_a(sb + TC_A_HI, ks), a_lo = sdesc_a(sb + TC_A_LO, ks);
+              const uint64_t b_hi = sdesc_b(sb + TC_B_HI, ks), b_lo = sdesc_b(sb + TC_B_LO, ks);
+              umma(d_acc, a_lo, b_hi, idesc, first ? 0u : 1u);
+              umma(d_acc, a_hi, b_lo, idesc, 1u);
+              umma(d_acc, a_hi, b_hi, idesc, 1u);
               first = false;
             }
             umma_commit(&empty[stage]);
@@ -397,21 +408,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           const uint32_t d_main = tmem_base + mb * 128;
           mbar_wait(&full[stage], phase);
-          if (gs.a_lo_inline) mbar_wait(&lo_full[stage], phase);
+          if (a_lo_conv) mbar_wait(&lo_full[stage], phase);
           tcgen05_fence_after();
           const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            const uint64_t a_hi = make_sdesc<A_MN>(sb + TC_A_HI, ks);
-            const uint64_t b_hi = make_sdesc<B_MN>(sb + TC_B_HI, ks);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t a_hi = sdesc_a(sb + TC_A_HI, ks);
+            const uint64_t b_hi = sdesc_b(sb + TC_B_HI, ks);
             if (gs.split3) {
-              const uint64_t a_lo = make_sdesc<A_MN>(sb + TC_A_LO, ks);
-              const uint64_t b_lo = make_sdesc<B_MN>(sb + TC_B_LO, ks);
-              umma_tf32(d_corr, a_lo, b_hi, idesc, first_corr ? 0u : 1u);
-              umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+              const uint64_t a_lo = sdesc_a(sb + TC_A_LO, ks);
+              const uint64_t b_lo = sdesc_b(sb + TC_B_LO, ks);
+              umma(d_corr, a_lo, b_hi, idesc, first_corr ? 0u : 1u);
+              umma(d_corr, a_hi, b_lo, idesc, 1u);
               first_corr = false;
             }
-            umma_tf32(d_main, a_hi, b_hi, idesc, first_main ? 0u : 1u);
+            umma(d_main, a_hi, b_hi, idesc, first_main ? 0u : 1u);
             first_main = false;
           }
           umma_commit(&empty[stage]);  // smem slot free once these MMAs retire
@@ -431,7 +442,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // ===================== converter warps (6..7) =====================
     // The split is elementwise, so it is independent of the (swizzled) tile layout: byte i of the A_hi tile maps
     // to byte i of the A_lo tile.  TMA zero-fills out-of-range rows, whose lo is 0 as well.
-    if (gs.split3 && gs.a_lo_inline) {
+    if (a_lo_conv) {
       const int ct = threadIdx.x - 6 * 32;
       int stage = 0;
       uint32_t phase = 0;
@@ -464,7 +475,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     int mb = 0, cb = 0, ab = 0;
     uint32_t mb_phase = 0, cb_phase = 0, ab_phase = 0;
     const int partials = (gs.k_blocks + TC_PROMOTE - 1) / TC_PROMOTE;
-    const bool single_acc = gs.split3 && gs.k_blocks <= TC_PROMOTE;  // see the MMA issuer
+    const bool single_acc = !F16 && gs.split3 && gs.k_blocks <= TC_PROMOTE;  // see the MMA issuer
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int seed = tile / tiles_per_seed;
       const int rem = tile - seed * tiles_per_seed;
@@ -506,12 +517,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (gs.split3) {
         mbar_wait(&corr_full[cb], cb_phase);
         tcgen05_fence_after();
-        tmem_accumulate_row<false>(tmem_base + 256 + cb * 128 + lane_off, acc);
+        tmem_accumulate_row<false>(tmem_base + 256 + cb * 128 + lane_off, acc, F16 ? TC_LO_INV : 1.0f);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&corr_empty[cb]);
         if (++cb == 2) { cb = 0; cb_phase ^= 1u; }
       }
+      }
+      if (F16 && ep.out_scale != 0.f) {   // undo the power-of-two pre-scaling of an operand (exact)
+#pragma unroll
+        for (int j = 0; j < 128; ++j) acc[j] *= ep.out_scale;
       }
       epilogue_row<EPI>(ep, acc, stage_all + (warp - 2) * 32 * STG_LD, sp_all, lane, seed, m0 + quad * 32, n0, gs.M,
                         mask_bits);
@@ -564,9 +579,9 @@ int make_tmap(CUtensorMap* tm, const float* base, uint64_t inner, uint64_t mid, 
 
 static int num_sms() { return device_sm_count(); }
 
-template <int A_MN, int B_MN, int EPI>
+template <int A_MN, int B_MN, int EPI, bool F16 = false>
 static int launch_t(const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep, cudaStream_t st, int kid) {
-  auto kfn = tc_gemm_kernel<A_MN, B_MN, EPI>;
+  auto kfn = tc_gemm_kernel<A_MN, B_MN, EPI, F16>;
   if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
     return check_launch("tc_gemm(cudaFuncSetAttribute)");
   const int tiles = gs.m_tiles * gs.n_tiles * gs.S;
@@ -593,6 +608,36 @@ int launch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap* t, const GemmSha
   return set_error(PQN_E_UNSUPPORTED, "tc_gemm: combination a_mn=%d b_mn=%d epi=%d not instantiated", a_mn, b_mn, epi);
 }
 
+int launch_gemm16(int a_mn, int b_mn, int epi, const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep,
+                  cudaStream_t st, int kernel_id) {
+#define PQN_TC_CASE(A, B, E) \
+  if (a_mn == A && b_mn == B && epi == E) return launch_t<A, B, E, true>(t, gs, ep, st, kernel_id);
+  PQN_TC_CASE(0, 1, EPI_STORE)
+  PQN_TC_CASE(0, 1, EPI_LN_TRAIN)
+  PQN_TC_CASE(0, 1, EPI_LN_HEAD)
+  PQN_TC_CASE(1, 1, EPI_STORE)
+  PQN_TC_CASE(0, 0, EPI_STORE)
+  PQN_TC_CASE(0, 0, EPI_RELU_MASK)
+  PQN_TC_CASE(0, 0, EPI_RELU_BITS)
+#undef PQN_TC_CASE
+  return set_error(PQN_E_UNSUPPORTED, "tc_gemm16: combination a_mn=%d b_mn=%d epi=%d not instantiated", a_mn, b_mn, epi);
+}
+
+int make_tmap16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t mid, uint64_t seeds, uint64_t mid_stride_elems,
+                uint64_t seed_stride_elems, uint32_t box_mid) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(PQN_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {inner, mid, seeds};
+  cuuint64_t strides[2] = {mid_stride_elems * 2, seed_stride_elems * 2};
+  cuuint32_t box[3] = {64, box_mid, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(PQN_E_CUDA, "cuTensorMapEncodeTiled(fp16) failed (%d)", (int)r);
+  return PQN_OK;
+}
+
 __global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, int64_t n4) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -600,6 +645,20 @@ __global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__
   float4 o;
   o.x = tf32_lo(v.x); o.y = tf32_lo(v.y); o.z = tf32_lo(v.z); o.w = tf32_lo(v.w);
   reinterpret_cast<float4*>(lo)[i] = o;
+}
+
+// fp16 split planes of an fp32 tensor (optionally pre-scaled by a power of two): hi = fp16(x*scale),
+// lo = fp16((x*scale - hi) * 2^11)
+__global__ void split16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4,
+                               float scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+  __half2 h0, h1, l0, l1;
+  split16x2(v.x * scale, v.y * scale, h0, l0);
+  split16x2(v.z * scale, v.w * scale, h1, l1);
+  reinterpret_cast<uint2*>(hi)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  reinterpret_cast<uint2*>(lo)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
 }
 
 // Debug kernel: one CTA, one 128x128x32 tile, no pipelining.  Dumps the smem tiles TMA produced and the TMEM
@@ -693,6 +752,41 @@ int pqn_tc_split_lo(const float* x, float* lo, int64_t n, void* stream) {
     split_lo_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, lo, n / 4);
   }
   return check_launch("pqn_tc_split_lo");
+}
+
+int pqn_tc_split16(const float* x, void* hi, void* lo, int64_t n, float scale, void* stream) {
+  if (!x || !hi || !lo || n < 0 || (n & 3)) return set_error(PQN_E_INVALID, "pqn_tc_split16: bad argument (n %% 4 == 0)");
+  if (n == 0) return PQN_OK;
+  {
+    LaunchScope _ls(K_TC_SPLIT, (cudaStream_t)stream);
+    split16_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)hi, (__half*)lo, n / 4,
+                                                                                       scale);
+  }
+  return check_launch("pqn_tc_split16");
+}
+
+// Test hook: D[s] = A[s] . B[s] * out_scale on the fp16-split tcgen05 path; operands are the (hi, lo') planes written
+// by pqn_tc_split16.  Layout flags as in pqn_tc_gemm_test; N % 128 == 0.
+int pqn_tc_gemm16_test(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* d, int32_t S,
+                       int32_t M, int32_t N, int32_t K, int a_mn, int b_mn, float out_scale, void* stream) {
+  if (!a_hi || !a_lo || !b_hi || !b_lo || !d || S <= 0 || M <= 0 || N <= 0 || K <= 0 || (N % 128) || (K % 8) || (M % 8))
+    return set_error(PQN_E_INVALID, "pqn_tc_gemm16_test: bad argument");
+  CUtensorMap t[4];
+  int rc;
+  const void* ap[2] = {a_hi, a_lo};
+  const void* bp[2] = {b_hi, b_lo};
+  for (int i = 0; i < 2; ++i) {
+    if (a_mn) { if ((rc = make_tmap16(&t[i], ap[i], M, K, S, M, (uint64_t)M * K, 64))) return rc; }
+    else { if ((rc = make_tmap16(&t[i], ap[i], K, M, S, K, (uint64_t)M * K, 128))) return rc; }
+    if (b_mn) { if ((rc = make_tmap16(&t[2 + i], bp[i], N, K, S, N, (uint64_t)N * K, 64))) return rc; }
+    else { if ((rc = make_tmap16(&t[2 + i], bp[i], K, N, S, K, (uint64_t)N * K, 128))) return rc; }
+  }
+  GemmShape gs = {};
+  gs.S = S; gs.M = M; gs.m_tiles = (M + 127) / 128; gs.n_tiles = N / 128; gs.k_blocks = (K + TC_BK16 - 1) / TC_BK16;
+  gs.split3 = 1;
+  EpiParams ep = {};
+  ep.out = d; ep.ld_out = N; ep.out_seed_stride = (int64_t)M * N; ep.out_scale = out_scale;
+  return launch_gemm16(a_mn, b_mn, EPI_STORE, t, gs, ep, (cudaStream_t)stream);
 }
 
 // Debug hook (tests only): single 128x128x32 tile; a: [128][32] (a_mn=0) or [32][128] (a_mn=1); same for b.

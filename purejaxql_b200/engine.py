@@ -136,6 +136,21 @@ class PQNEngine:
         assert keys.dim() == 2 and keys.shape[1] == 2, "train(rngs) takes the [NUM_SEEDS, 2] key array"
         S = keys.shape[0]
         mode = self.rng_mode
+        # ---- env-sharded data parallelism (needed when NUM_SEEDS < #GPUs).  Rank r owns envs
+        # [r*E/W, (r+1)*E/W) of EVERY seed; rollouts are local (per-env keys are those of the unsharded vmap), each
+        # minibatch step all-reduces (mean) the flat [S][P] gradient once before clip + RAdam, so parameters stay
+        # bit-identical across ranks.  The minibatch permutation is per rank (statistically equivalent to the
+        # reference's global shuffle, not sample-identical).
+        shard = getattr(self, "env_shard", None)
+        E_total, env_lo, world, rank = E, 0, 1, 0
+        if shard is not None and shard[1] > 1:
+            import torch.distributed as dist
+            rank, world = int(shard[0]), int(shard[1])
+            assert E % world == 0, f"NUM_ENVS={E} must be divisible by the {world} env shards"
+            E = E // world
+            env_lo = rank * E
+            assert (T * E) % self.nmb == 0, "NUM_MINIBATCHES must divide NUM_STEPS * NUM_ENVS / world"
+        mb = T * E // self.nmb                                        # minibatch rows of THIS rank
         spec, P = self.spec, self.spec.total
         W = self.row_words
 
@@ -182,7 +197,7 @@ class PQNEngine:
         step_keys = torch.zeros((T, S, 2, 2), dtype=torch.int32, device=dev)
         eps_dev = torch.zeros(1, device=dev)
         # ---- reset (vmap_reset, :107-109,419)
-        reset_keys = jr.split(kR, E, mode).reshape(S * E, 2).contiguous()
+        reset_keys = jr.split(kR, E_total, mode)[:, env_lo:env_lo + E].reshape(S * E, 2).contiguous()
         state = torch.empty((self.env.state_words, S * E), dtype=torch.int32, device=dev)
         _lib.check(L.pqn_env_reset(self.env.env_id, _lib.p(reset_keys), _lib.p(state), None, S * E, self.max_steps,
                                    mode, _lib.stream_ptr()), "pqn_env_reset")
@@ -209,9 +224,15 @@ class PQNEngine:
         kT_buf = torch.zeros((S, 2), dtype=torch.int32, device=dev)  # eval key of this update (:341)
         upd_idx = torch.zeros(1, dtype=torch.int64, device=dev)      # n_updates on the device
         m_cur = torch.zeros((S, 7), dtype=torch.float64, device=dev)  # td_loss, qvals, 5 info means
-        ws = self._workspace(S, max(self.mb, E))
+        ws = self._workspace(S, max(mb, E))
         denom = float(self.epochs * self.nmb)
-        bn_count = float(self.mb * (100 if self.binary else 1))
+        bn_count = float(mb * world * (100 if self.binary else 1))
+
+        def allreduce_(t, avg):
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)              # in-stream: the consumer kernels just follow
+                if avg:
+                    t.mul_(1.0 / world)
 
         def update_body():
             """One `_update_step` (pqn_minatar.py:176-350) on the current stream; reads/writes only the static
@@ -229,8 +250,8 @@ class PQNEngine:
                     _lib.raw(obs_buf[:, t + 1]), seed_stride_obs,
                     _lib.raw(act_buf[:, t]), _lib.raw(rew_buf[:, t]),
                     _lib.raw(done_buf[:, t]), _lib.raw(maxq_buf[:, t]),
-                    seed_stride_tr, _lib.p(info_sums), 0, S, E, self.max_steps, self.rew_scale, mode, sp()),
-                    "pqn_rollout_act_step")
+                    seed_stride_tr, _lib.p(info_sums), 0, S, E, E_total, env_lo, self.max_steps, self.rew_scale, mode,
+                    sp()), "pqn_rollout_act_step")
             r = carry                                                # scan's final carry (:214)
             # ================= bootstrap + Q(lambda) (:227-260)
             self.forward(params, obs_buf[:, T], S, E, seed_stride_obs, q_buf)
@@ -243,14 +264,18 @@ class PQNEngine:
             for _ in range(self.epochs):
                 k = jr.split(r, 2, mode)                             # :309
                 r, kperm = k[:, 0].contiguous(), k[:, 1].contiguous()
+                if world > 1:                                        # a different local permutation on every rank
+                    kperm = jr.split(kperm, world, mode)[:, rank].contiguous()
                 perm = jr.permutation_indices(kperm, T * E, mode)    # :299-315 same perm for every leaf
-                perm_view = perm.view(S, self.nmb, self.mb).transpose(0, 1).contiguous()
+                perm_view = perm.view(S, self.nmb, mb).transpose(0, 1).contiguous()
                 r = jr.split(r, 2, mode)[:, 0].contiguous()          # :317
                 for mbi in range(self.nmb):
                     _lib.check(L.pqn_qnet_loss_grad(
                         spec.desc, _lib.p(params), _lib.p(obs_buf), _lib.p(perm_view[mbi]), seed_stride_obs,
                         _lib.p(act_buf), _lib.p(targets), seed_stride_tr, _lib.p(grads), _lib.p(loss_sum),
-                        _lib.p(qsa_sum), _lib.p(bn_sums), S, self.mb, _lib.p(ws), sp()), "pqn_qnet_loss_grad")
+                        _lib.p(qsa_sum), _lib.p(bn_sums), S, mb, _lib.p(ws), sp()), "pqn_qnet_loss_grad")
+                    allreduce_(grads, True)                          # the ONE collective of the data path
+                    allreduce_(bn_sums, False)
                     _lib.check(L.pqn_radam_clip_step(_lib.p(params), _lib.p(grads), _lib.p(mu), _lib.p(nu),
                                                      _lib.p(sched), _lib.p(step_counter), _lib.p(gnorm), S, P,
                                                      float(c["MAX_GRAD_NORM"]), 0.9, 0.999, 1e-8, sp()),
@@ -262,15 +287,18 @@ class PQNEngine:
                 r = k[:, 0].contiguous()
                 kT_buf.copy_(k[:, 1])
             rng_buf.copy_(r)
+            allreduce_(loss_sum, True)
+            allreduce_(qsa_sum, True)
+            allreduce_(info_sums, False)
             m_cur[:, 0] = loss_sum.double() / denom
             m_cur[:, 1] = qsa_sum.double() / denom
-            m_cur[:, 2:7] = info_sums / float(T * E)
+            m_cur[:, 2:7] = info_sums / float(T * E_total)
             upd_idx.add_(1)
 
         # CUDA graph: "auto" captures the update when the run is launch-bound (small S*E); the first update runs
         # eagerly (warms every code path), later updates replay the captured graph.
         want_graph = c.get("CUDA_GRAPH", "auto")
-        use_graph = (S * E * T <= (1 << 21)) if want_graph == "auto" else bool(want_graph)
+        use_graph = (S * E * T <= (1 << 21) and world == 1) if want_graph == "auto" else bool(want_graph)
         use_graph = use_graph and NU > 2
         graph = None
         self.graph_captured = False
@@ -309,7 +337,7 @@ class PQNEngine:
                         torch.cuda.synchronize(dev)
             if on_update_end is not None:
                 on_update_end(n_updates, dbg)
-            timesteps += T * E                                       # :222-225
+            timesteps += T * E_total                                 # :222-225
             grad_steps += self.nmb * self.epochs
             # ================= metrics (:329-338)
             n_done = n_updates + 1

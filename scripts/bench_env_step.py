@@ -74,7 +74,7 @@ def main():
 
     def fused():
         _lib.check(L.pqn_rollout_act_step(env.env_id, _lib.p(sk), _lib.p(q), _lib.p(eps), _lib.p(st), _lib.raw(obsn[:, 1]),
-                                          2 * E, _lib.p(a), _lib.p(rw), _lib.p(dn), _lib.p(mq), E, _lib.p(sums), 0, S, E,
+                                          2 * E, _lib.p(a), _lib.p(rw), _lib.p(dn), _lib.p(mq), E, _lib.p(sums), 0, S, E, 0, 0,
                                           1000, 1.0, 0, _lib.stream_ptr()))
     ms = time_ms(fused, iters=50)
     bytes_per = (44 + 12) + (44 + 64 + 4 + 4 + 1 + 4)                    # read state + q ; write state, packed obs, a, r, done, maxq

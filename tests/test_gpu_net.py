@@ -53,11 +53,11 @@ def _ws(spec, S, rows):
 
 
 @pytest.fixture(params=[(2, 1), (1, 1), (0, 0), (1, 0), (2, 2)],
-                ids=["tcgen05_inline_lo+mma_conv", "tcgen05+mma_conv", "ffma", "tcgen05+cuda_conv",
-                     "tcgen05_inline_lo+tcgen05_conv"])
+                ids=["tcgen05_f16split+mma_conv", "tcgen05_3xtf32+mma_conv", "ffma", "tcgen05_3xtf32+cuda_conv",
+                     "tcgen05_f16split+tcgen05_conv"])
 def dense_path(request):
-    """Runs the CNN tests on the implementation variants: dense layer on tcgen05 3xTF32 or fp32 FFMA,
-    conv on warp-level tf32 MMA or fp32 CUDA cores."""
+    """Runs the CNN tests on the implementation variants: dense layer on tcgen05 (fp16-split planes = default,
+    or 3xTF32) or fp32 FFMA; conv on warp-level tf32 MMA (default), fp32 CUDA cores or tcgen05."""
     from purejaxql_b200 import _lib
     _lib.lib().pqn_set_tensor_core_path(request.param[0])
     _lib.lib().pqn_set_conv_mma_path(request.param[1])
