@@ -143,13 +143,15 @@ class ClockSampler:
 # --------------------------------------------------------------------------- #
 # CPU arm: oracle port on a bounded sample
 # --------------------------------------------------------------------------- #
-SAMPLE_T = 4          # rollout steps per CPU "step" (of the workload's 32): bounded sample, same E and minibatch
+SAMPLE_T = 1          # rollout steps per CPU "step" (of the workload's 32): bounded sample
+SAMPLE_E = 1024       # envs per CPU worker (of the workload's 4096) => minibatch 1024 rows: large enough for BLAS to
+                      # run at its large-GEMM rate; 128 workers x 4096 envs made one sample step take ~60 s
 
 
-def cpu_port_steps(num_steps, warmup=0, sample_envs=NUM_ENVS, sample_t=SAMPLE_T):
-    """Times `num_steps` sample steps of the oracle port for ONE seed: NUM_ENVS=`sample_envs` envs, a rollout of
-    `sample_t` of the 32 steps, Q(lambda), and sample_t minibatches x 2 epochs of minibatch size `sample_envs`
-    (the workload's minibatch: T*E/32 = E).  Returns (env_steps_per_s, seconds)."""
+def cpu_port_steps(num_steps, warmup=0, sample_envs=SAMPLE_E, sample_t=SAMPLE_T):
+    """Times `num_steps` sample steps of the oracle port for ONE seed: `sample_envs` envs, a rollout of `sample_t` of
+    the 32 steps, Q(lambda), and sample_t minibatches x 2 epochs of `sample_envs` rows (the workload has T*E/32 = E
+    rows per minibatch).  Returns (env_steps_per_s, seconds)."""
     from oracle import gymnax_envs as G
     from oracle import jax_prng as jr
     from oracle import pqn_ref as R
@@ -183,7 +185,7 @@ def _cpu_worker(q, num_steps, warmup, sample_envs, seed):
         q.put(("error", repr(e)))
 
 
-def cpu_port_parallel(num_steps, warmup=0, sample_envs=NUM_ENVS, max_workers=128):
+def cpu_port_parallel(num_steps, warmup=0, sample_envs=SAMPLE_E, max_workers=128):
     """Oracle port on all host cores: one process (1 BLAS thread) per core, one seed each.
     Returns (aggregate env_steps_per_s, seconds of the slowest worker's timed region, workers)."""
     import multiprocessing as mp
@@ -208,10 +210,10 @@ def cpu_port_parallel(num_steps, warmup=0, sample_envs=NUM_ENVS, max_workers=128
 
 def cpu_sample_text(workers, steps, dt):
     return (f"{steps} sample steps of {workers} independent seeds (one process + 1 BLAS thread per host core); each sample "
-            f"step = the workload's update step at its true NUM_ENVS={NUM_ENVS} and minibatch={NUM_ENVS} cut to "
-            f"{SAMPLE_T} of the {NUM_STEPS} rollout steps (=> {SAMPLE_T} minibatches x 2 epochs: same grad-steps per "
-            f"env-step), {dt:.1f} s; oracle port (NumPy) -- the reference's JAX-CPU path is not installable here "
-            f"(no jax/gymnax wheels)")
+            f"step = a bounded sample of the workload's update step: {SAMPLE_E} of the {NUM_ENVS} envs and {SAMPLE_T} of "
+            f"the {NUM_STEPS} rollout steps per seed (Q forward + eps-greedy + env step, Q(lambda), then {SAMPLE_T} "
+            f"minibatch(es) x 2 epochs of {SAMPLE_E} rows: the workload's grad-steps per env-step), {dt:.1f} s; oracle "
+            f"port (NumPy) -- the reference's JAX-CPU path is not installable here (no jax/gymnax wheels)")
 
 
 def headline_config(seeds_total, world, envs, with_eval=False):
