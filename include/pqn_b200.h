@@ -152,7 +152,13 @@ typedef struct pqn_net_desc_t {
   int32_t hidden;      /* CNN: 128 (fixed)                      | MLP: HIDDEN_SIZE */
   int32_t layers;      /* CNN: ignored                          | MLP: NUM_LAYERS (1 or 2) */
   int32_t num_actions; /* A */
+  int32_t norm_type;   /* NORM_TYPE: 0 layer_norm (default), 1 batch_norm, 2 none   (pqn_minatar.py:31-36) */
+  int32_t norm_input;  /* NORM_INPUT: 1 = the input BatchNorm normalises the observation (replaces x/255 in the CNN)
+                          and is trained; 0 = it is the dummy of pqn_minatar.py:61-66 */
 } pqn_net_desc_t;
+#define PQN_NORM_LAYER 0
+#define PQN_NORM_BATCH 1
+#define PQN_NORM_NONE 2
 
 /* offsets (in floats) of each tensor inside one seed's parameter block; flax
  * names: see SURVEY Appendix C.  Unused entries are -1. */
@@ -168,6 +174,10 @@ typedef struct pqn_net_layout_t {
 } pqn_net_layout_t;
 
 int pqn_net_layout(const pqn_net_desc_t* desc_host, pqn_net_layout_t* out_host);
+/* floats per seed of the batch_stats block (flax "batch_stats" collection): [mean in][var in] of the input BatchNorm,
+ * then, for norm_type == batch_norm, (mean[n], var[n]) of every hidden BatchNorm in network order (CNN: 16, 128;
+ * MLP: hidden x layers).  With norm_type none the ln*_scale / ln*_bias layout entries are -1 (no such parameters). */
+int64_t pqn_net_stats_floats(const pqn_net_desc_t* desc_host);
 /* bytes of scratch the forward/backward need for `rows` samples per seed */
 int64_t pqn_net_workspace_bytes(const pqn_net_desc_t* desc_host, int32_t S, int64_t rows);
 
@@ -179,8 +189,9 @@ int pqn_net_init(const pqn_net_desc_t* desc_host, const uint32_t* keys, float* p
  *  obs: packed uint32[S][rows_total][packed_words] (CNN) or float32[S][rows_total][D] (MLP);
  *  gather (may be NULL): int32[S][rows] row indices into the seed's obs rows
  *  (minibatch gather of preprocess_transition, :299-307); obs_rows_per_seed is
- *  the stride of the obs buffer in rows. */
-int pqn_qnet_forward(const pqn_net_desc_t* desc_host, const float* params, const void* obs,
+ *  the stride of the obs buffer in rows.  batch_stats: float32[S][pqn_net_stats_floats] running statistics, read by
+ *  the batch_norm / NORM_INPUT variants (train=False => use_running_average); may be NULL for the default network. */
+int pqn_qnet_forward(const pqn_net_desc_t* desc_host, const float* params, const float* batch_stats, const void* obs,
                      const int32_t* gather, int64_t obs_rows_per_seed, float* q, int32_t S, int64_t rows,
                      void* workspace, void* stream);
 
@@ -188,8 +199,10 @@ int pqn_qnet_forward(const pqn_net_desc_t* desc_host, const float* params, const
  * action/target: [S][tr_rows_per_seed] indexed through `gather` like obs;
  * grads[S][P] (overwritten), loss_sum[S] += loss, qsa_sum[S] += mean(q_sa),
  * bn_sums: float32[S][2*in] += per-feature (sum x, sum x^2) of the raw obs minibatch
- * (dummy BatchNorm statistics, :65,293-296); may be NULL. */
-int pqn_qnet_loss_grad(const pqn_net_desc_t* desc_host, const float* params, const void* obs,
+ * (input BatchNorm statistics, :65,293-296; consumed by pqn_bn_stats_update); may be NULL.
+ * batch_stats (may be NULL for the default network): the running statistics of the HIDDEN BatchNorm layers are
+ * updated in place (train=True, mutable batch_stats, :277-281); the input BatchNorm's go through bn_sums. */
+int pqn_qnet_loss_grad(const pqn_net_desc_t* desc_host, const float* params, float* batch_stats, const void* obs,
                        const int32_t* gather, int64_t obs_rows_per_seed, const int32_t* action,
                        const float* target, int64_t tr_rows_per_seed, float* grads, float* loss_sum,
                        float* qsa_sum, float* bn_sums, int32_t S, int64_t rows, void* workspace, void* stream);
@@ -205,9 +218,10 @@ int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu,
 /* dummy input BatchNorm running statistics (flax nn.BatchNorm momentum 0.99;
  * pqn_minatar.py:65,293-296): batch_stats float32[S][2][F] (mean, var),
  * bn_sums float32[S][2][F] (sum x, sum x^2 over `count` elements per feature);
- * bn_sums is zeroed for the next minibatch. */
-int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F, float count, float momentum,
-                        void* stream);
+ * bn_sums is zeroed for the next minibatch.  stats_seed_stride: floats between the seeds' batch_stats blocks
+ * (pqn_net_stats_floats; 0 => 2*F). */
+int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F, int64_t stats_seed_stride,
+                        float count, float momentum, void* stream);
 
 /* The CNN's dense layer (forward, wgrad, dgrad) runs on the tcgen05 3xTF32 path: 2 (default) derives the "lo"
  * half of the activation operand inside the GEMM kernel, 1 reads it from a tensor the conv forward wrote,

@@ -40,22 +40,25 @@ static int make_layout(const pqn_net_desc_t* d, pqn_net_layout_t* L) {
   auto take = [&](int64_t n) { int64_t o = off; off += align4(n); return o; };
   L->d1_w = L->d1_b = L->ln1_scale = L->ln1_bias = L->conv_w = L->conv_b = -1;
   const int A = d->num_actions;
+  const bool has_norm = d->norm_type != PQN_NORM_NONE;   // layer_norm and batch_norm have (scale, bias) of the same shape
   if (d->kind == PQN_NET_MINATAR_CNN) {
     const int C = d->in_c;
     L->bn_scale = take(C); L->bn_bias = take(C);
     L->conv_w = take(9 * C * CONV_O); L->conv_b = take(CONV_O);
-    L->ln0_scale = take(CONV_O); L->ln0_bias = take(CONV_O);
+    L->ln0_scale = L->ln0_bias = -1;   // norm_type none: the network has no normalisation parameters
+    if (has_norm) { L->ln0_scale = take(CONV_O); L->ln0_bias = take(CONV_O); }
     L->d0_w = take((int64_t)FLAT_CNN * HID_CNN); L->d0_b = take(HID_CNN);
-    L->ln1_scale = take(HID_CNN); L->ln1_bias = take(HID_CNN);
+    if (has_norm) { L->ln1_scale = take(HID_CNN); L->ln1_bias = take(HID_CNN); }
     L->head_w = take((int64_t)HID_CNN * A); L->head_b = take(A);
   } else if (d->kind == PQN_NET_MLP) {
     const int D = d->in_c, H = d->hidden;
     L->bn_scale = take(D); L->bn_bias = take(D);
     L->d0_w = take((int64_t)D * H); L->d0_b = take(H);
-    L->ln0_scale = take(H); L->ln0_bias = take(H);
+    L->ln0_scale = L->ln0_bias = -1;
+    if (has_norm) { L->ln0_scale = take(H); L->ln0_bias = take(H); }
     if (d->layers == 2) {
       L->d1_w = take((int64_t)H * H); L->d1_b = take(H);
-      L->ln1_scale = take(H); L->ln1_bias = take(H);
+      if (has_norm) { L->ln1_scale = take(H); L->ln1_bias = take(H); }
     }
     L->head_w = take((int64_t)H * A); L->head_b = take(A);
   } else {
@@ -68,6 +71,8 @@ static int make_layout(const pqn_net_desc_t* d, pqn_net_layout_t* L) {
 static int check_desc(const pqn_net_desc_t* d, const char* who) {
   if (!d) return set_error(PQN_E_INVALID, "%s: desc is NULL", who);
   if (d->num_actions < 1 || d->num_actions > 32) return set_error(PQN_E_INVALID, "%s: num_actions=%d out of [1,32]", who, d->num_actions);
+  if (d->norm_type < 0 || d->norm_type > 2 || d->norm_input < 0 || d->norm_input > 1)
+    return set_error(PQN_E_INVALID, "%s: norm_type=%d norm_input=%d", who, d->norm_type, d->norm_input);
   {
     // row_bwd_kernel keeps [A][N] head weights + eight warp-private [A][N] gradient slices in shared memory
     const int Nh = d->kind == PQN_NET_MINATAR_CNN ? 128 : d->hidden;
@@ -134,6 +139,7 @@ __device__ __forceinline__ float4 load4_guard(const float* __restrict__ src, int
 //   MODE 0: write H          (inference hidden layer)
 //   MODE 1: write H, XHAT, RSTD  (training forward: what the backward needs)
 //   MODE 2: write Q = H @ Wh + bh only (inference last layer, Q-head fused)
+//   MODE 3: write the raw pre-activation X @ W + b to H (no LayerNorm; modular NORM_TYPE path)
 // grid = (ceil(rows/BM), S)
 // ---------------------------------------------------------------------------
 template <int BN, int MODE>
@@ -220,6 +226,17 @@ __global__ void __launch_bounds__(GT) dense_fwd_kernel(
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int row = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+    if (MODE == 3) {  // raw pre-activation (bias only): the modular NORM_TYPE path normalises in its own kernels
+      if (row < rows) {
+        const int64_t grow3 = (int64_t)seed * rows + row;
+#pragma unroll
+        for (int c = 0; c < TN / 4; ++c)
+          *reinterpret_cast<float4*>(H + grow3 * BN + c * 64 + tx * 4) =
+              make_float4(acc[i][4 * c] + colb[4 * c], acc[i][4 * c + 1] + colb[4 * c + 1], acc[i][4 * c + 2] + colb[4 * c + 2],
+                          acc[i][4 * c + 3] + colb[4 * c + 3]);
+      }
+      continue;
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
@@ -2098,11 +2115,20 @@ static int tc_dgrad(const float* params, int64_t P, const pqn_net_layout_t& L, c
   return tc::launch_gemm(0, 0, have_bits ? tc::EPI_RELU_BITS : tc::EPI_RELU_MASK, t, gs, ep, st, K_TC_DGRAD);
 }
 
+#include "pqn_norm.cuh"
+
+static inline bool modular_net(const pqn_net_desc_t* d) { return d->norm_type != PQN_NORM_LAYER || d->norm_input != 0; }
+
 }  // namespace pqn
 
 using namespace pqn;
 
 extern "C" {
+
+int64_t pqn_net_stats_floats(const pqn_net_desc_t* d) {
+  if (check_desc(d, "pqn_net_stats_floats")) return -1;
+  return nrm::stats_floats(d);
+}
 
 int pqn_set_conv_mma_path(int on) {
   g_conv_mma = on < 0 ? 0 : (on > 2 ? 2 : on);
@@ -2124,11 +2150,13 @@ int pqn_net_layout(const pqn_net_desc_t* d, pqn_net_layout_t* out) {
 
 int64_t pqn_net_workspace_bytes(const pqn_net_desc_t* d, int32_t S, int64_t rows) {
   if (check_desc(d, "pqn_net_workspace_bytes")) return -1;
+  if (modular_net(d)) return nrm::carve_norm(d, S, rows, nullptr, nullptr);
   return carve(d, S, rows, nullptr, nullptr);
 }
 
-int pqn_qnet_forward(const pqn_net_desc_t* d, const float* params, const void* obs, const int32_t* gather,
-                     int64_t obs_rows_per_seed, float* q, int32_t S, int64_t rows, void* workspace, void* stream) {
+int pqn_qnet_forward(const pqn_net_desc_t* d, const float* params, const float* batch_stats, const void* obs,
+                     const int32_t* gather, int64_t obs_rows_per_seed, float* q, int32_t S, int64_t rows, void* workspace,
+                     void* stream) {
   int rc = check_desc(d, "pqn_qnet_forward");
   if (rc) return rc;
   if (!params || !obs || !q || !workspace || S <= 0 || rows <= 0 || S > 65535)
@@ -2136,6 +2164,12 @@ int pqn_qnet_forward(const pqn_net_desc_t* d, const float* params, const void* o
   cudaStream_t st = (cudaStream_t)stream;
   pqn_net_layout_t L;
   make_layout(d, &L);
+  if (modular_net(d)) {
+    nrm::NormWs nw;
+    nrm::carve_norm(d, S, rows, (char*)workspace, &nw);
+    return nrm::norm_forward(d, L, params, const_cast<float*>(batch_stats), obs, gather, obs_rows_per_seed, q, S, (int)rows,
+                            0, nullptr, nw, st);
+  }
   Workspace w;
   carve(d, S, rows, (char*)workspace, &w);
   const int A = d->num_actions;
@@ -2183,8 +2217,8 @@ int pqn_qnet_forward(const pqn_net_desc_t* d, const float* params, const void* o
   return check_launch("pqn_qnet_forward");
 }
 
-int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void* obs, const int32_t* gather,
-                       int64_t obs_rows_per_seed, const int32_t* action, const float* target,
+int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batch_stats, const void* obs,
+                       const int32_t* gather, int64_t obs_rows_per_seed, const int32_t* action, const float* target,
                        int64_t tr_rows_per_seed, float* grads, float* loss_sum, float* qsa_sum, float* bn_sums,
                        int32_t S, int64_t rows, void* workspace, void* stream) {
   int rc = check_desc(d, "pqn_qnet_loss_grad");
@@ -2202,6 +2236,12 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, const void*
   const int R = (int)rows;
   if (cudaMemsetAsync(grads, 0, (size_t)S * P * sizeof(float), st) != cudaSuccess)
     return check_launch("pqn_qnet_loss_grad(memset)");
+  if (modular_net(d)) {
+    nrm::NormWs nw;
+    nrm::carve_norm(d, S, rows, (char*)workspace, &nw);
+    return nrm::norm_loss_grad(d, L, params, batch_stats, obs, gather, obs_rows_per_seed, action, target, tr_rows_per_seed,
+                              grads, loss_sum, qsa_sum, bn_sums, S, R, nw, st);
+  }
 
   if (d->kind == PQN_NET_MINATAR_CNN) {
     const uint32_t* ob = (const uint32_t*)obs;

@@ -90,12 +90,12 @@ __global__ void __launch_bounds__(256) radam_kernel(float* __restrict__ params, 
 
 __global__ void advance_kernel(int32_t* step_counter) { step_counter[0] += 1; }
 
-__global__ void bn_update_kernel(float* __restrict__ batch_stats, float* __restrict__ bn_sums, int F, float count,
-                                 float momentum) {
+__global__ void bn_update_kernel(float* __restrict__ batch_stats, float* __restrict__ bn_sums, int F, int64_t stride,
+                                 float count, float momentum) {
   const int seed = blockIdx.x;
   const int f = threadIdx.x;
   if (f >= F) return;
-  float* bs = batch_stats + (int64_t)seed * 2 * F;
+  float* bs = batch_stats + (int64_t)seed * stride;
   float* sm = bn_sums + (int64_t)seed * 2 * F;
   const float mean = sm[f] / count;
   const float var = fmaxf(sm[F + f] / count - mean * mean, 0.f);
@@ -209,11 +209,13 @@ int pqn_net_init(const pqn_net_desc_t* d, const uint32_t* keys, float* params, i
   return check_launch("pqn_net_init");
 }
 
-int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F, float count, float momentum,
-                        void* stream) {
-  if (!batch_stats || !bn_sums || S <= 0 || F <= 0 || F > 1024 || count <= 0.f)
+int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F, int64_t stats_seed_stride, float count,
+                        float momentum, void* stream) {
+  if (!batch_stats || !bn_sums || S <= 0 || F <= 0 || F > 1024 || count <= 0.f ||
+      (stats_seed_stride != 0 && stats_seed_stride < 2 * F))
     return set_error(PQN_E_INVALID, "pqn_bn_stats_update: bad argument");
-  { LaunchScope _ls(K_BN_UPDATE, (cudaStream_t)stream); bn_update_kernel<<<S, ((F + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(batch_stats, bn_sums, F, count, momentum); }
+  const int64_t stride = stats_seed_stride ? stats_seed_stride : 2 * (int64_t)F;
+  { LaunchScope _ls(K_BN_UPDATE, (cudaStream_t)stream); bn_update_kernel<<<S, ((F + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(batch_stats, bn_sums, F, stride, count, momentum); }
   return check_launch("pqn_bn_stats_update");
 }
 

@@ -428,7 +428,7 @@ class PQNEngine:
             _lib.check(L.pqn_rollout_act_step(
                 self.env.env_id, _lib.p(sk), _lib.p(q), _lib.p(eps), _lib.p(state),
                 _lib.raw(obs[:, nxt]), 2 * N, _lib.p(scratch_i), _lib.p(scratch_f), _lib.p(scratch_b),
-                _lib.p(scratch_f2), N, _lib.p(sums), 1, S, N, self.max_steps, 1.0, mode, _lib.stream_ptr()),
+                _lib.p(scratch_f2), N, _lib.p(sums), 1, S, N, 0, 0, self.max_steps, 1.0, mode, _lib.stream_ptr()),
                 "pqn_rollout_act_step")
         cnt = sums[:, 3]
         out = {}
