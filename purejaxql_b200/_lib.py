@@ -22,7 +22,10 @@ class EnvInfo(Structure):
 
 class NetDesc(Structure):
     _fields_ = [("kind", c_int32), ("in_c", c_int32), ("hidden", c_int32), ("layers", c_int32),
-                ("num_actions", c_int32)]
+                ("num_actions", c_int32), ("norm_type", c_int32), ("norm_input", c_int32)]
+
+
+NORM_TYPES = {"layer_norm": 0, "batch_norm": 1}          # any other string: no normalisation (pqn_minatar.py:35-36)
 
 
 class NetLayout(Structure):
@@ -60,16 +63,17 @@ _SIGS = {
     "pqn_qlambda": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                             c_float, c_float, c_void_p]),
     "pqn_net_layout": (c_int, [POINTER(NetDesc), POINTER(NetLayout)]),
+    "pqn_net_stats_floats": (c_int64, [POINTER(NetDesc)]),
     "pqn_net_workspace_bytes": (c_int64, [POINTER(NetDesc), c_int32, c_int64]),
     "pqn_net_init": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_int32, c_void_p]),
-    "pqn_qnet_forward": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32,
+    "pqn_qnet_forward": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32,
                                  c_int64, c_void_p, c_void_p]),
-    "pqn_qnet_loss_grad": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
-                                   c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p,
-                                   c_void_p]),
+    "pqn_qnet_loss_grad": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                   c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64,
+                                   c_void_p, c_void_p]),
     "pqn_radam_clip_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                     c_int64, c_float, c_float, c_float, c_float, c_void_p]),
-    "pqn_bn_stats_update": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_void_p]),
+    "pqn_bn_stats_update": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_float, c_float, c_void_p]),
     "pqn_set_tensor_core_path": (c_int, [c_int]),
     "pqn_set_conv_mma_path": (c_int, [c_int]),
     "pqn_tc_split_lo": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

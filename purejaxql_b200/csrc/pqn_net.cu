@@ -1202,8 +1202,9 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
         const int p0 = 16 * mb + g, p1 = p0 + 8;
         if (H16) {
           __half2 h0, l0, h1v, l1;
-          tc::split16x2(v0.x, v0.y, h0, l0);
-          tc::split16x2(v1.x, v1.y, h1v, l1);
+          // post-ReLU values are >= 0: one-sided saturation is enough
+          tc::split16x2<false>(fminf(v0.x, 65000.f), fminf(v0.y, 65000.f), h0, l0);
+          tc::split16x2<false>(fminf(v1.x, 65000.f), fminf(v1.y, 65000.f), h1v, l1);
           *reinterpret_cast<__half2*>(hrow16 + p0 * CONV_O + o) = h0;
           *reinterpret_cast<__half2*>(lrow16 + p0 * CONV_O + o) = l0;
           *reinterpret_cast<__half2*>(hrow16 + p1 * CONV_O + o) = h1v;

@@ -7,7 +7,7 @@
 // no float atomics).  BatchNorm needs the two passes anyway (batch statistics before normalisation, the
 // sum_dy / sum_dy_xhat terms before dz), and these configurations are not the headline workload.
 //
-// flax semantics restated (oracle/pqn_ref_norm.py has the NumPy version and the reference line numbers):
+// flax semantics restated (the test-side NumPy restatement, pqn_ref_norm, carries the reference line numbers):
 //   nn.BatchNorm(use_running_average=not train): reduce over all axes but the last, eps 1e-5, momentum 0.99,
 //   fast variance max(E[x^2]-E[x]^2, 0); train: batch statistics normalise, running = .99 running + .01 batch.
 //   NORM_INPUT=True: the input BatchNorm replaces x/255 (CNN) or the raw observation (MLP) and gets gradients;

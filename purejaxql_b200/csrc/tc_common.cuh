@@ -186,9 +186,13 @@ __device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn((x - __half2float(hi)) * TC_LO_SCALE);
 }
+// SAT = false: the caller guarantees |x| < 65504 (e.g. LayerNorm outputs: |xhat| <= sqrt(n - 1))
+template <bool SAT = true>
 __device__ __forceinline__ void split16x2(float x0, float x1, __half2& hi, __half2& lo) {
-  x0 = fminf(fmaxf(x0, -65000.0f), 65000.0f);
-  x1 = fminf(fmaxf(x1, -65000.0f), 65000.0f);
+  if (SAT) {
+    x0 = fminf(fmaxf(x0, -65000.0f), 65000.0f);
+    x1 = fminf(fmaxf(x1, -65000.0f), 65000.0f);
+  }
   hi = __floats2half2_rn(x0, x1);
   const float2 hf = __half22float2(hi);
   lo = __floats2half2_rn((x0 - hf.x) * TC_LO_SCALE, (x1 - hf.y) * TC_LO_SCALE);

@@ -81,8 +81,7 @@ class PQNEngine:
             raise _lib.PqnError("purejaxql_b200 needs a CUDA device: there is no CPU fallback")
         _lib.lib()
         c = config
-        if c.get("NORM_TYPE", "layer_norm") != "layer_norm" or c.get("NORM_INPUT", False):
-            raise NotImplementedError("only NORM_TYPE=layer_norm, NORM_INPUT=False are built (shipped defaults)")
+        norm_type, norm_input = c.get("NORM_TYPE", "layer_norm"), bool(c.get("NORM_INPUT", False))
         self.rng_mode = int(c.get("JAX_THREEFRY_PARTITIONABLE", 0))
         self.env, self.env_params = envs.make(c["ENV_NAME"], flatten_obs=flatten_obs, rng_mode=self.rng_mode)
         self.max_steps = int(self.env_params.max_steps_in_episode)
@@ -95,12 +94,13 @@ class PQNEngine:
         if network == "cnn":
             if not self.binary:
                 raise ValueError("the MinAtar CNN needs a (10,10,C) binary-observation env")
-            self.spec = QNetworkSpec(NET_CNN, self.env.info.obs_shape[2], self.A)
+            self.spec = QNetworkSpec(NET_CNN, self.env.info.obs_shape[2], self.A, norm_type=norm_type,
+                                     norm_input=norm_input)
             self.row_words = self.env.packed_obs_words          # int32 words per obs row
             self.obs_dtype = torch.int32
         else:
             self.spec = QNetworkSpec(NET_MLP, self.env.obs_dim, self.A, int(c.get("HIDDEN_SIZE", 128)),
-                                     int(c.get("NUM_LAYERS", 2)))
+                                     int(c.get("NUM_LAYERS", 2)), norm_type=norm_type, norm_input=norm_input)
             if self.binary:
                 raise NotImplementedError("MLP on packed MinAtar observations is not built")
             self.row_words = self.env.obs_dim
@@ -121,9 +121,13 @@ class PQNEngine:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def forward(self, params, obs, S, rows, obs_rows_per_seed, q_out, gather=None):
+    def forward(self, params, obs, S, rows, obs_rows_per_seed, q_out, gather=None, batch_stats=None):
+        """network.apply({"params", "batch_stats"}, obs, train=False) (pqn_minatar.py:184-191)."""
         ws = self._workspace(S, rows)
-        _lib.check(_lib.lib().pqn_qnet_forward(self.spec.desc, _lib.p(params), _lib.raw(obs), _lib.p(gather),
+        if batch_stats is None:
+            batch_stats = getattr(self, "_cur_stats", None)
+        _lib.check(_lib.lib().pqn_qnet_forward(self.spec.desc, _lib.p(params), _lib.p(batch_stats), _lib.raw(obs),
+                                               _lib.p(gather),
                                                obs_rows_per_seed, _lib.p(q_out), S, rows, _lib.p(ws),
                                                _lib.stream_ptr()), "pqn_qnet_forward")
         return q_out
@@ -150,6 +154,10 @@ class PQNEngine:
             E = E // world
             env_lo = rank * E
             assert (T * E) % self.nmb == 0, "NUM_MINIBATCHES must divide NUM_STEPS * NUM_ENVS / world"
+            if self.spec.norm_type == "batch_norm" or self.spec.norm_input:
+                raise NotImplementedError("env-sharded data parallelism with batch statistics on the path "
+                                          "(NORM_TYPE=batch_norm / NORM_INPUT) would need their all-reduce; use "
+                                          "DATA_PARALLEL=seeds")
         mb = T * E // self.nmb                                        # minibatch rows of THIS rank
         spec, P = self.spec, self.spec.total
         W = self.row_words
@@ -173,7 +181,8 @@ class PQNEngine:
         nu = torch.zeros_like(params)
         grads = torch.zeros_like(params)
         F = spec.in_c
-        batch_stats = torch.cat([torch.zeros(S, F), torch.ones(S, F)], 1).to(dev).contiguous()  # mean 0, var 1
+        batch_stats = spec.init_stats(S, dev)                       # flax BatchNorm running statistics: mean 0, var 1
+        self._cur_stats = batch_stats                               # read by forward() (train=False => running stats)
         bn_sums = torch.zeros(S, 2 * F, device=dev)
         step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         gnorm = torch.zeros(S, device=dev)
@@ -271,7 +280,8 @@ class PQNEngine:
                 r = jr.split(r, 2, mode)[:, 0].contiguous()          # :317
                 for mbi in range(self.nmb):
                     _lib.check(L.pqn_qnet_loss_grad(
-                        spec.desc, _lib.p(params), _lib.p(obs_buf), _lib.p(perm_view[mbi]), seed_stride_obs,
+                        spec.desc, _lib.p(params), _lib.p(batch_stats), _lib.p(obs_buf), _lib.p(perm_view[mbi]),
+                        seed_stride_obs,
                         _lib.p(act_buf), _lib.p(targets), seed_stride_tr, _lib.p(grads), _lib.p(loss_sum),
                         _lib.p(qsa_sum), _lib.p(bn_sums), S, mb, _lib.p(ws), sp()), "pqn_qnet_loss_grad")
                     allreduce_(grads, True)                          # the ONE collective of the data path
@@ -280,8 +290,8 @@ class PQNEngine:
                                                      _lib.p(sched), _lib.p(step_counter), _lib.p(gnorm), S, P,
                                                      float(c["MAX_GRAD_NORM"]), 0.9, 0.999, 1e-8, sp()),
                                "pqn_radam_clip_step")
-                    _lib.check(L.pqn_bn_stats_update(_lib.p(batch_stats), _lib.p(bn_sums), S, F, bn_count, 0.99, sp()),
-                               "pqn_bn_stats_update")
+                    _lib.check(L.pqn_bn_stats_update(_lib.p(batch_stats), _lib.p(bn_sums), S, F, spec.stats_total,
+                                                     bn_count, 0.99, sp()), "pqn_bn_stats_update")
             if self.test:                                            # :341  rng, _rng = split(rng)
                 k = jr.split(r, 2, mode)
                 r = k[:, 0].contiguous()
@@ -368,7 +378,7 @@ class PQNEngine:
             out_metrics.update({f"test/{kk}": v[:, :NU].float() for kk, v in test_hist.items()})
         train_state = TrainState(
             params=spec.unflatten(params), params_flat=params,
-            batch_stats={"BatchNorm_0": {"mean": batch_stats[:, :F], "var": batch_stats[:, F:]}},
+            batch_stats=spec.unflatten_stats(batch_stats), batch_stats_flat=batch_stats,
             opt_state=SimpleNamespace(mu=mu, nu=nu, count=grad_steps),
             timesteps=torch.full((S,), timesteps, dtype=torch.int64), n_updates=torch.full((S,), NU),
             grad_steps=torch.full((S,), grad_steps))

@@ -72,7 +72,9 @@ def permutation_indices(keys: torch.Tensor, n: int, rng_mode: int = 0) -> torch.
     for _ in range(rounds):
         ks = split(key, 2, rng_mode)
         key, sub = ks[:, 0].contiguous(), ks[:, 1].contiguous()
-        bits = random_bits(sub, n, rng_mode).to(torch.int64).bitwise_and_(0xFFFFFFFF)
+        # uint32 sort keys as int32 with the sign bit flipped: signed order == unsigned order, and the radix sort runs
+        # over 32 key bits instead of the 64 of an int64 view
+        bits = random_bits(sub, n, rng_mode).bitwise_xor_(-0x80000000)
         order = torch.sort(bits, dim=1, stable=True).indices
         idx = torch.gather(idx, 1, order)
     return idx.to(torch.int32)

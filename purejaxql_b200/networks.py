@@ -4,8 +4,13 @@ block that libpqn_b200's kernels consume (``pqn_net_layout``).
 Reference modules: ``QNetwork``/``CNN`` purejaxql/pqn_minatar.py:24-69 and MLP
 ``QNetwork`` purejaxql/pqn_gymnax.py:29-58; parameter tree names per SURVEY
 Appendix C (flax auto-naming), e.g. ``params["CNN_0"]["Dense_0"]["kernel"]``.
-Only NORM_TYPE="layer_norm", NORM_INPUT=False (the shipped defaults of
-pqn_minatar.yaml / pqn_cartpole.yaml) are built.
+``NORM_TYPE`` in {"layer_norm", "batch_norm", anything else = none} and
+``NORM_INPUT`` follow pqn_minatar.py:31-36,61-66 / pqn_gymnax.py:38-51: with
+batch_norm the two (or NUM_LAYERS) normalisations are ``BatchNorm`` modules —
+flax auto-names them ``CNN_0/BatchNorm_0``, ``CNN_0/BatchNorm_1`` inside the CNN
+and ``BatchNorm_1..L`` in the MLP (they share the module counter with the input
+``BatchNorm_0``) — and own running statistics in ``batch_stats``; with "none"
+the network has no normalisation parameters at all.
 """
 from __future__ import annotations
 
@@ -21,9 +26,14 @@ NET_MLP = 1
 
 
 class QNetworkSpec:
-    def __init__(self, kind: int, in_c: int, num_actions: int, hidden: int = 128, layers: int = 2):
+    def __init__(self, kind: int, in_c: int, num_actions: int, hidden: int = 128, layers: int = 2,
+                 norm_type: str = "layer_norm", norm_input: bool = False):
         self.kind, self.in_c, self.num_actions, self.hidden, self.layers = kind, in_c, num_actions, hidden, layers
-        self.desc = _lib.NetDesc(kind, in_c, hidden, layers, num_actions)
+        self.norm_type = norm_type if norm_type in _lib.NORM_TYPES else "none"
+        self.norm_input = bool(norm_input)
+        self.desc = _lib.NetDesc(kind, in_c, hidden, layers, num_actions, _lib.NORM_TYPES.get(norm_type, 2),
+                                 int(self.norm_input))
+        self.stats_total = int(_lib.lib().pqn_net_stats_floats(self.desc))
         lay = _lib.NetLayout()
         _lib.check(_lib.lib().pqn_net_layout(self.desc, lay), "pqn_net_layout")
         self.layout = lay
@@ -34,36 +44,79 @@ class QNetworkSpec:
     def _entries(self):
         L, A = self.layout, self.num_actions
         e = []
+
+        def norm(prefix, idx, off_s, off_b, n):
+            # flax auto-names: LayerNorm_i, or BatchNorm_i (CNN) / BatchNorm_{i+1} (MLP: the input one is BatchNorm_0)
+            if self.norm_type == "layer_norm":
+                name = f"LayerNorm_{idx}"
+            elif self.norm_type == "batch_norm":
+                name = f"BatchNorm_{idx if prefix else idx + 1}"
+            else:
+                return []
+            return [(prefix + (name, "scale"), off_s, (n,), "ones"), (prefix + (name, "bias"), off_b, (n,), "zeros")]
         if self.kind == NET_CNN:
             C = self.in_c
             e += [(("BatchNorm_0", "scale"), L.bn_scale, (C,), "ones"),
                   (("BatchNorm_0", "bias"), L.bn_bias, (C,), "zeros"),
                   (("CNN_0", "Conv_0", "kernel"), L.conv_w, (3, 3, C, 16), "he"),
-                  (("CNN_0", "Conv_0", "bias"), L.conv_b, (16,), "zeros"),
-                  (("CNN_0", "LayerNorm_0", "scale"), L.ln0_scale, (16,), "ones"),
-                  (("CNN_0", "LayerNorm_0", "bias"), L.ln0_bias, (16,), "zeros"),
-                  (("CNN_0", "Dense_0", "kernel"), L.d0_w, (1024, 128), "he"),
-                  (("CNN_0", "Dense_0", "bias"), L.d0_b, (128,), "zeros"),
-                  (("CNN_0", "LayerNorm_1", "scale"), L.ln1_scale, (128,), "ones"),
-                  (("CNN_0", "LayerNorm_1", "bias"), L.ln1_bias, (128,), "zeros"),
-                  (("Dense_0", "kernel"), L.head_w, (128, A), "lecun"),
+                  (("CNN_0", "Conv_0", "bias"), L.conv_b, (16,), "zeros")]
+            e += norm(("CNN_0",), 0, L.ln0_scale, L.ln0_bias, 16)
+            e += [(("CNN_0", "Dense_0", "kernel"), L.d0_w, (1024, 128), "he"),
+                  (("CNN_0", "Dense_0", "bias"), L.d0_b, (128,), "zeros")]
+            e += norm(("CNN_0",), 1, L.ln1_scale, L.ln1_bias, 128)
+            e += [(("Dense_0", "kernel"), L.head_w, (128, A), "lecun"),
                   (("Dense_0", "bias"), L.head_b, (A,), "zeros")]
         else:
             D, H = self.in_c, self.hidden
             e += [(("BatchNorm_0", "scale"), L.bn_scale, (D,), "ones"),
                   (("BatchNorm_0", "bias"), L.bn_bias, (D,), "zeros"),
                   (("Dense_0", "kernel"), L.d0_w, (D, H), "lecun"),
-                  (("Dense_0", "bias"), L.d0_b, (H,), "zeros"),
-                  (("LayerNorm_0", "scale"), L.ln0_scale, (H,), "ones"),
-                  (("LayerNorm_0", "bias"), L.ln0_bias, (H,), "zeros")]
+                  (("Dense_0", "bias"), L.d0_b, (H,), "zeros")]
+            e += norm((), 0, L.ln0_scale, L.ln0_bias, H)
             if self.layers == 2:
                 e += [(("Dense_1", "kernel"), L.d1_w, (H, H), "lecun"),
-                      (("Dense_1", "bias"), L.d1_b, (H,), "zeros"),
-                      (("LayerNorm_1", "scale"), L.ln1_scale, (H,), "ones"),
-                      (("LayerNorm_1", "bias"), L.ln1_bias, (H,), "zeros")]
+                      (("Dense_1", "bias"), L.d1_b, (H,), "zeros")]
+                e += norm((), 1, L.ln1_scale, L.ln1_bias, H)
             e += [((f"Dense_{self.layers}", "kernel"), L.head_w, (H, A), "lecun"),
                   ((f"Dense_{self.layers}", "bias"), L.head_b, (A,), "zeros")]
         return e
+
+    # ------------------------------------------------------------------ #
+    def stats_entries(self):
+        """(flax batch_stats path, offset of `mean` in the per-seed block, n); `var` follows at offset + n."""
+        F = self.in_c
+        out = [(("BatchNorm_0",), 0, F)]
+        if self.norm_type == "batch_norm":
+            if self.kind == NET_CNN:
+                out += [(("CNN_0", "BatchNorm_0"), 2 * F, 16), (("CNN_0", "BatchNorm_1"), 2 * F + 32, 128)]
+            else:
+                out += [((f"BatchNorm_{l + 1}",), 2 * F + 2 * self.hidden * l, self.hidden) for l in range(self.layers)]
+        return out
+
+    def init_stats(self, S, device="cuda") -> torch.Tensor:
+        """flax BatchNorm initial running statistics: mean 0, var 1 -> float32[S, stats_total]."""
+        st = torch.zeros((S, self.stats_total), dtype=torch.float32)
+        for _, off, n in self.stats_entries():
+            st[:, off + n:off + 2 * n] = 1.0
+        return st.to(device)
+
+    def unflatten_stats(self, st: torch.Tensor) -> dict:
+        tree: dict = {}
+        for path, off, n in self.stats_entries():
+            d = tree
+            for k in path[:-1]:
+                d = d.setdefault(k, {})
+            d[path[-1]] = {"mean": st[:, off:off + n], "var": st[:, off + n:off + 2 * n]}
+        return tree
+
+    def flatten_stats(self, stats: dict, S: int = 1, device="cuda") -> torch.Tensor:
+        """{"A/B": {"mean","var"}} (oracle) -> float32[S, stats_total]."""
+        st = torch.zeros((S, self.stats_total), dtype=torch.float32)
+        for path, off, n in self.stats_entries():
+            d = stats["/".join(path)]
+            st[:, off:off + n] = torch.as_tensor(np.asarray(d["mean"]), dtype=torch.float32).reshape(-1, n)
+            st[:, off + n:off + 2 * n] = torch.as_tensor(np.asarray(d["var"]), dtype=torch.float32).reshape(-1, n)
+        return st.to(device)
 
     # ------------------------------------------------------------------ #
     def unflatten(self, flat: torch.Tensor) -> dict:

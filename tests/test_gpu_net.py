@@ -75,7 +75,7 @@ def test_cnn_forward_matches_oracle_1e5(rows, dense_path):
     packed = torch.from_numpy(np.stack([pack_obs(obs[s] != 0) for s in range(S)])).to(dev()).contiguous()
     q = torch.zeros((S * rows, 3), device=dev())
     ws = _ws(spec, S, rows)
-    _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), _lib.p(packed), None, rows, _lib.p(q), S, rows,
+    _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), None, _lib.p(packed), None, rows, _lib.p(q), S, rows,
                                            _lib.p(ws), _lib.stream_ptr()))
     q = q.cpu().numpy().reshape(S, rows, 3)
     for s in range(S):
@@ -96,7 +96,7 @@ def test_cnn_forward_other_channel_counts_and_gather(dense_path):
         gather = np.stack([rng.permutation(total)[:rows] for _ in range(S)]).astype(np.int32)
         q = torch.zeros((S * rows, 5), device=dev())
         tg_, ws = torch.from_numpy(gather).to(dev()), _ws(spec, S, rows)
-        _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), _lib.p(packed), _lib.p(tg_), total, _lib.p(q),
+        _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), None, _lib.p(packed), _lib.p(tg_), total, _lib.p(q),
                                                S, rows, _lib.p(ws), _lib.stream_ptr()))
         q = q.cpu().numpy().reshape(S, rows, 5)
         for s in range(S):
@@ -116,7 +116,7 @@ def test_mlp_forward_matches_oracle(D, H, layers, A):
     obs = rng.standard_normal((S, rows, D)).astype(np.float32)
     q = torch.zeros((S * rows, A), device=dev())
     to_, ws = torch.from_numpy(obs).to(dev()), _ws(spec, S, rows)
-    _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), _lib.p(to_), None, rows,
+    _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), None, _lib.p(to_), None, rows,
                                            _lib.p(q), S, rows, _lib.p(ws), _lib.stream_ptr()))
     q = q.cpu().numpy().reshape(S, rows, A)
     for s in range(S):
@@ -131,7 +131,7 @@ def _loss_grad(spec, flat, obs_t, gather, total, act, tgt, S, rows, F):
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev(), dt)
     tg_, ta_, tt_, ws = t(gather, torch.int32), t(act, torch.int32), t(tgt, torch.float32), _ws(spec, S, rows)
     _lib.check(_lib.lib().pqn_qnet_loss_grad(
-        spec.desc, _lib.p(flat), _lib.p(obs_t), _lib.p(tg_), total, _lib.p(ta_),
+        spec.desc, _lib.p(flat), None, _lib.p(obs_t), _lib.p(tg_), total, _lib.p(ta_),
         _lib.p(tt_), total, _lib.p(grads), _lib.p(ls), _lib.p(qs), _lib.p(bn), S, rows,
         _lib.p(ws), _lib.stream_ptr()))
     torch.cuda.synchronize()
