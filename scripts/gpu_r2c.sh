@@ -12,8 +12,9 @@ print("value", d["value"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"]
 for k,v in d["kernel_breakdown"].items(): print(k, v)
 PY
 # ncu --set full: one steady-state instance of each hot kernel (second update of a 2-update run)
-for pat in "tc_gemm_kernel" "conv_fwd_mma_kernel" "conv_bwd_mma_kernel" "row_bwd_kernel"; do
-  timeout 600 ncu --set full --import-source on --clock-control none -k regex:$pat --launch-skip 70 --launch-count 4 \
+for spec in "tc_gemm_kernel:70:3" "conv_fwd_mma_kernel:70:1" "conv_bwd_mma_kernel:10:1" "row_bwd_kernel:10:1"; do
+  pat=${spec%%:*}; rest=${spec#*:}; skip=${rest%%:*}; cnt=${rest#*:}
+  timeout 420 ncu --set full --import-source on --clock-control none -k regex:$pat --launch-skip $skip --launch-count $cnt \
     -o gpurun_out/r2c_ncu_$pat -f python bench.py --steps 1 --warmup 1 --no-cpu --no-env-roofline > gpurun_out/r2c_ncu_$pat.log 2>&1
   ls -la gpurun_out/r2c_ncu_$pat.ncu-rep 2>/dev/null
 done
