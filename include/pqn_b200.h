@@ -212,7 +212,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* desc_host, const float* params, flo
  * (lr, 1-b1^t, 1-b2^t, rect (0 => un-rectified step)); step_counter: int32[1]
  * device counter (grad_steps), incremented by the call. */
 int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu, const float* sched,
-                        int32_t* step_counter, float* gnorm_scratch /*[S]*/, int32_t S, int64_t P,
+                        int32_t* step_counter, float* gnorm_scratch /*[S][64]*/, int32_t S, int64_t P,
                         float max_norm, float b1, float b2, float eps, void* stream);
 
 /* dummy input BatchNorm running statistics (flax nn.BatchNorm momentum 0.99;

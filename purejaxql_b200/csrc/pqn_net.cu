@@ -76,7 +76,7 @@ static int check_desc(const pqn_net_desc_t* d, const char* who) {
   {
     // row_bwd_kernel keeps [A][N] head weights + eight warp-private [A][N] gradient slices in shared memory
     const int Nh = d->kind == PQN_NET_MINATAR_CNN ? 128 : d->hidden;
-    const size_t need = (size_t)(3 * Nh + 9 * d->num_actions * Nh + d->num_actions + 2) * sizeof(float);
+    const size_t need = (size_t)(24 * Nh + 9 * d->num_actions * Nh + 8 * d->num_actions + 16) * sizeof(float);
     if (need > 227u * 1024u)
       return set_error(PQN_E_UNSUPPORTED, "%s: hidden=%d with num_actions=%d needs %zu B of shared memory for the head "
                        "backward (limit 227 KB)", who, Nh, d->num_actions, need);
@@ -458,21 +458,22 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
     const float* __restrict__ params, float* __restrict__ grads, int64_t P,
     int64_t off_scale, int64_t off_dscale, int64_t off_dbias, int64_t off_db, int64_t off_hw, int64_t off_hb, int A,
     const int32_t* __restrict__ gather, const int32_t* __restrict__ action, const float* __restrict__ target,
-    int64_t tr_rows_per_seed, float* __restrict__ loss_sum, float* __restrict__ qsa_sum, int rows) {
+    int64_t tr_rows_per_seed, float* __restrict__ part, int rows) {
+  // Reductions over rows are deterministic: lane-private registers -> warp-private shared-memory slices -> a fixed-order
+  // sum over the 8 warps -> this CTA's partial vector part[seed][cta][3N (+ A*N + A + 2)], which row_bwd_final_kernel
+  // adds over the CTAs in index order (no float atomics anywhere).
   constexpr int F = N / 32;  // features per lane, in float4 chunks at lane*4 + c*128
   extern __shared__ float smem[];
-  float* s_dsc = smem;            // [N]
-  float* s_dbi = smem + N;        // [N]
-  float* s_db = smem + 2 * N;     // [N]
-  float* s_hw = smem + 3 * N;     // [A][N]  head weights, transposed copy (HEAD)
+  float* s_red3 = smem;           // [8 warps][3N]  d scale, d bias, d dense-bias slices
+  float* s_hw = smem + 24 * N;    // [A][N]  head weights, transposed copy (HEAD)
   float* s_dhw = s_hw + (HEAD ? A * N : 0);   // [8 warps][A][N]  warp-private head-weight gradient slices (HEAD);
                                               // 16-byte aligned for the float4 accesses, scalars go last
-  float* s_dhb = s_dhw + (HEAD ? 8 * A * N : 0);  // [A]
-  float* s_ls = s_dhb + (HEAD ? A : 0);           // [2] loss, qsa
+  float* s_dhb = s_dhw + (HEAD ? 8 * A * N : 0);  // [8 warps][A]
+  float* s_ls = s_dhb + (HEAD ? 8 * A : 0);       // [8 warps][2] loss, qsa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int seed = blockIdx.y;
   const float* __restrict__ prm = params + (int64_t)seed * P;
-  const int nsm = 3 * N + (HEAD ? A * N + A + 2 + 8 * A * N : 0);
+  const int nsm = 24 * N + (HEAD ? A * N + 8 * A + 16 + 8 * A * N : 0);
   for (int i = tid; i < nsm; i += 256) smem[i] = 0.f;
   __syncthreads();
   if (HEAD)
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
       if (lane == 0) {
         a_loss += 0.5f * diff * diff * invB;
         a_qsa += q_sa * invB;
-        atomicAdd(s_dhb + act, dq);
+        s_dhb[warp * A + act] += dq;   // warp-private slot, one writer
       }
 #pragma unroll
       for (int c = 0; c < F / 4; ++c) {  // warp-private slice: plain read-modify-write, no atomics
@@ -588,40 +589,62 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
                         tc::tf32_lo(dz[4 * c + 3]));
     }
   }
-  // combine warps in shared memory, then one global atomic per element per CTA
+  // warp-private slices (each lane owns its features: plain stores)
 #pragma unroll
   for (int j = 0; j < F; ++j) {
     const int f = (j >> 2) * 128 + lane * 4 + (j & 3);
-    atomicAdd(s_dsc + f, a_dsc[j]);
-    atomicAdd(s_dbi + f, a_dbi[j]);
-    atomicAdd(s_db + f, a_db[j]);
+    s_red3[warp * 3 * N + f] = a_dsc[j];
+    s_red3[warp * 3 * N + N + f] = a_dbi[j];
+    s_red3[warp * 3 * N + 2 * N + f] = a_db[j];
   }
-  if (HEAD && lane == 0) {
-    atomicAdd(s_ls, a_loss);
-    atomicAdd(s_ls + 1, a_qsa);
-  }
+  if (HEAD && lane == 0) { s_ls[warp * 2] = a_loss; s_ls[warp * 2 + 1] = a_qsa; }
   __syncthreads();
-  float* __restrict__ g = grads + (int64_t)seed * P;
-  for (int i = tid; i < N; i += 256) {
-    atomicAdd(g + off_dscale + i, s_dsc[i]);
-    atomicAdd(g + off_dbias + i, s_dbi[i]);
-    atomicAdd(g + off_db + i, s_db[i]);
+  const int stride = 3 * N + (HEAD ? A * N + A + 2 : 0);
+  float* __restrict__ o = part + ((int64_t)seed * gridDim.x + blockIdx.x) * stride;
+  for (int i = tid; i < 3 * N; i += 256) {
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) v += s_red3[wv * 3 * N + i];
+    o[i] = v;
   }
   if (HEAD) {
-    // s_dhw is [A][N]; the parameter is [N][A]
-    for (int i = tid; i < A * N; i += 256) {
-      const int a = i / N, f = i - a * N;
+    for (int i = tid; i < A * N; i += 256) {   // [A][N]
       float v = 0.f;
 #pragma unroll
       for (int wv = 0; wv < 8; ++wv) v += s_dhw[wv * A * N + i];
-      if (v != 0.f) atomicAdd(g + off_hw + (int64_t)f * A + a, v);
+      o[3 * N + i] = v;
     }
-    if (tid < A) atomicAdd(g + off_hb + tid, s_dhb[tid]);
-    if (tid == 0) {
-      atomicAdd(loss_sum + seed, s_ls[0]);
-      atomicAdd(qsa_sum + seed, s_ls[1]);
+    if (tid < A + 2) {
+      float v = 0.f;
+      for (int wv = 0; wv < 8; ++wv) v += tid < A ? s_dhb[wv * A + tid] : s_ls[wv * 2 + (tid - A)];
+      o[3 * N + A * N + tid] = v;
     }
   }
+}
+
+// Sums the per-CTA partial vectors of row_bwd_kernel in CTA order and writes the gradients (and adds the minibatch's
+// loss / mean q_sa to the running sums).  grid = (ceil(stride / 256), S)
+__global__ void row_bwd_final_kernel(const float* __restrict__ part, int nctas, int N, int A, int head,
+                                     float* __restrict__ grads, int64_t P, int64_t off_dscale, int64_t off_dbias,
+                                     int64_t off_db, int64_t off_hw, int64_t off_hb, float* __restrict__ loss_sum,
+                                     float* __restrict__ qsa_sum) {
+  const int seed = blockIdx.y;
+  const int stride = 3 * N + (head ? A * N + A + 2 : 0);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= stride) return;
+  const float* __restrict__ p = part + (int64_t)seed * nctas * stride + i;
+  float v = 0.f;
+  for (int c = 0; c < nctas; ++c) v += p[(int64_t)c * stride];
+  float* __restrict__ g = grads + (int64_t)seed * P;
+  if (i < N) g[off_dscale + i] = v;
+  else if (i < 2 * N) g[off_dbias + (i - N)] = v;
+  else if (i < 3 * N) g[off_db + (i - 2 * N)] = v;
+  else if (i < 3 * N + A * N) {
+    const int j = i - 3 * N, a = j / N, f = j - a * N;   // partial layout [A][N]; the parameter is [N][A]
+    g[off_hw + (int64_t)f * A + a] = v;
+  } else if (i < 3 * N + A * N + A) g[off_hb + (i - 3 * N - A * N)] = v;
+  else if (i == 3 * N + A * N + A) loss_sum[seed] += v;
+  else qsa_sum[seed] += v;
 }
 
 // ---------------------------------------------------------------------------
@@ -1289,7 +1312,7 @@ template <int C>
 __global__ void __launch_bounds__(ConvBwdSmem<C>::WARPS * 32, 2)
     conv_bwd_mma_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
                         const float* __restrict__ params, int64_t P, pqn_net_layout_t L, const float* __restrict__ DY1,
-                        const float* __restrict__ XH1, const float* __restrict__ RS1, float* __restrict__ grads,
+                        const float* __restrict__ XH1, const float* __restrict__ RS1, float* __restrict__ part,
                         int rows) {
   using Cfg = ConvCfg<C>;
   using M = ConvMma<C>;
@@ -1459,44 +1482,71 @@ __global__ void __launch_bounds__(ConvBwdSmem<C>::WARPS * 32, 2)
         for (int j = 0; j < 4; ++j) wrun[mt][h][j] += wacc[mt][h][j];
   }
   cp_async_wait_all();
-  // ---- reduce and publish: wrun[mt][h][j] is dW[tap = 16mt + g (+8 for j>=2)][o = 8h + 2t + (j&1)]
+  // ---- reduce and publish (deterministic): wrun[mt][h][j] is dW[tap = 16mt + g (+8 for j>=2)][o = 8h + 2t + (j&1)].
+  // The 8 warps add their registers to the block accumulator one after the other, lanes of a warp own distinct
+  // elements; the CTA's partial vector goes to part[seed][cta][TAPS*16 + 48] and conv_bwd_final_kernel sums the CTAs
+  // in index order.
   __syncthreads();  // all warps are done with their slices
-  for (int i = tid; i < M::MT * 16 * CONV_O; i += blockDim.x) s_w[i] = 0.f;
-  __syncthreads();
+  for (int w = 0; w < SM::WARPS; ++w) {
+    if (warp == w) {
 #pragma unroll
-  for (int mt = 0; mt < M::MT; ++mt)
+      for (int mt = 0; mt < M::MT; ++mt)
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int tap = 16 * mt + g + (j >= 2 ? 8 : 0);
-        // x = bit / 255 (pqn_minatar.py:66): the A operand was the raw bit, so scale here
-        if (tap < M::TAPS) atomicAdd(&s_w[tap * CONV_O + 8 * h + 2 * t + (j & 1)], wrun[mt][h][j] * (1.0f / 255.0f));
-      }
+          for (int j = 0; j < 4; ++j) {
+            const int tap = 16 * mt + g + (j >= 2 ? 8 : 0);
+            float* dst = &s_w[tap * CONV_O + 8 * h + 2 * t + (j & 1)];   // tap < 16 * MT: inside the buffer
+            *dst = (w == 0 ? 0.f : *dst) + wrun[mt][h][j];
+          }
+    }
+    __syncthreads();
+  }
+  // per-channel sums: lanes with the same t hold the same columns -> xor-shuffle tree (fixed), then warps in order
 #pragma unroll
   for (int col = 0; col < 4; ++col) {
     float v0 = a_dsc[col], v1 = a_dbi[col], v2 = a_dcb[col];
 #pragma unroll
-    for (int sft = 4; sft <= 16; sft <<= 1) {  // lanes with the same t (same columns)
+    for (int sft = 4; sft <= 16; sft <<= 1) {
       v0 += __shfl_xor_sync(0xffffffffu, v0, sft);
       v1 += __shfl_xor_sync(0xffffffffu, v1, sft);
       v2 += __shfl_xor_sync(0xffffffffu, v2, sft);
     }
-    if (g == 0) {
-      const int o = 8 * (col >> 1) + 2 * t + (col & 1);
-      atomicAdd(&s_red[o], v0);
-      atomicAdd(&s_red[CONV_O + o], v1);
-      atomicAdd(&s_red[2 * CONV_O + o], v2);
+    a_dsc[col] = v0; a_dbi[col] = v1; a_dcb[col] = v2;
+  }
+  for (int w = 0; w < SM::WARPS; ++w) {
+    if (warp == w && g == 0) {
+#pragma unroll
+      for (int col = 0; col < 4; ++col) {
+        const int o = 8 * (col >> 1) + 2 * t + (col & 1);
+        s_red[o] = (w == 0 ? 0.f : s_red[o]) + a_dsc[col];
+        s_red[CONV_O + o] = (w == 0 ? 0.f : s_red[CONV_O + o]) + a_dbi[col];
+        s_red[2 * CONV_O + o] = (w == 0 ? 0.f : s_red[2 * CONV_O + o]) + a_dcb[col];
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
+  float* __restrict__ o = part + ((int64_t)seed * gridDim.x + blockIdx.x) * (M::TAPS * CONV_O + 3 * CONV_O);
+  // x = bit / 255 (pqn_minatar.py:66): the A operand was the raw bit, so scale here
+  for (int i = tid; i < M::TAPS * CONV_O; i += blockDim.x) o[i] = s_w[i] * (1.0f / 255.0f);
+  if (tid < 3 * CONV_O) o[M::TAPS * CONV_O + tid] = s_red[tid];
+}
+
+// Sums conv_bwd_mma_kernel's per-CTA partials in CTA order into the gradients.  grid = (ceil(n / 256), S)
+__global__ void conv_bwd_final_kernel(const float* __restrict__ part, int nctas, int taps16, float* __restrict__ grads,
+                                      int64_t P, pqn_net_layout_t L) {
+  const int seed = blockIdx.y;
+  const int stride = taps16 + 3 * CONV_O;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= stride) return;
+  const float* __restrict__ p = part + (int64_t)seed * nctas * stride + i;
+  float v = 0.f;
+  for (int c = 0; c < nctas; ++c) v += p[(int64_t)c * stride];
   float* __restrict__ gout = grads + (int64_t)seed * P;
-  for (int i = tid; i < M::TAPS * CONV_O; i += blockDim.x) atomicAdd(gout + L.conv_w + i, s_w[i]);
-  if (tid < CONV_O) {
-    atomicAdd(gout + L.ln0_scale + tid, s_red[tid]);
-    atomicAdd(gout + L.ln0_bias + tid, s_red[CONV_O + tid]);
-    atomicAdd(gout + L.conv_b + tid, s_red[2 * CONV_O + tid]);
-  }
+  if (i < taps16) gout[L.conv_w + i] = v;
+  else if (i < taps16 + CONV_O) gout[L.ln0_scale + (i - taps16)] = v;
+  else if (i < taps16 + 2 * CONV_O) gout[L.ln0_bias + (i - taps16 - CONV_O)] = v;
+  else gout[L.conv_b + (i - taps16 - 2 * CONV_O)] = v;
 }
 
 // ---------------------------------------------------------------------------
@@ -1775,9 +1825,14 @@ struct Workspace {
   float *h1_lo, *dz2_lo, *w1_lo;  // 3xTF32 "lo" operands of the tcgen05 path
   float *cxhat, *crstd;           // conv LayerNorm xhat / rstd saved by the training forward (MMA conv path)
   uint32_t* relu_bits;            // packed (h1 > 0) mask, 1024 bits per row (MMA conv path -> tcgen05 dgrad epilogue)
+  float *rb_part, *cb_part;       // per-CTA partial vectors of the deterministic row_bwd / conv_bwd reductions
   // MLP
   float *xg, *h0, *xhat0, *rstd0, *hh1, *xhat1, *rstd1, *dzl, *dh0;
 };
+
+// upper bound of the CTAs (all seeds) of the wave-sized grids of conv_mma_ctas(): <= 6 waves of <= 4 CTAs/SM, + S
+static int64_t part_ctas(int S) { return 6 * 4 * (int64_t)device_sm_count() + 2 * (int64_t)S; }
+static int64_t row_bwd_part_floats(int N, int A);
 
 static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* base, Workspace* w) {
   int64_t off = 0;
@@ -1801,6 +1856,8 @@ static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* bas
     ww->cxhat = take(R * FLAT_CNN);
     ww->crstd = take(R * CONV_PIX);
     ww->relu_bits = reinterpret_cast<uint32_t*>(take(R * (FLAT_CNN / 32)));
+    ww->rb_part = take(part_ctas(S) * row_bwd_part_floats(HID_CNN, d->num_actions));
+    ww->cb_part = take(part_ctas(S) * (int64_t)(9 * d->in_c * CONV_O + 3 * CONV_O));
   } else {
     const int H = d->hidden;
     ww->xg = take(R * d->in_c);
@@ -1812,6 +1869,8 @@ static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* bas
     ww->rstd1 = take(R);
     ww->dzl = take(R * H);
     ww->dh0 = take(R * H);
+    ww->rb_part = take(part_ctas(S) * row_bwd_part_floats(H, d->num_actions));
+    ww->cb_part = nullptr;
   }
   return off;
 }
@@ -1831,20 +1890,23 @@ static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1
 template <int C>
 static int launch_conv_bwd_mma(dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
                                const float* params, int64_t P, const pqn_net_layout_t& L, const float* dy1,
-                               const float* xh1, const float* rs1, float* grads, int rows) {
+                               const float* xh1, const float* rs1, float* grads, float* part, int rows) {
   auto kfn = conv_bwd_mma_kernel<C>;
   if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvBwdSmem<C>::BYTES) != cudaSuccess)
     return check_launch("conv_bwd_mma(cudaFuncSetAttribute)");
   kfn<<<grid, ConvBwdSmem<C>::WARPS * 32, ConvBwdSmem<C>::BYTES, st>>>(obs, orps, gather, params, P, L, dy1, xh1, rs1,
-                                                                       grads, rows);
+                                                                       part, rows);
+  const int n = 9 * C * CONV_O + 3 * CONV_O;
+  conv_bwd_final_kernel<<<dim3(cdiv(n, 256), grid.y), 256, 0, st>>>(part, (int)grid.x, 9 * C * CONV_O, grads, P, L);
   return 0;
 }
 
-// dynamic shared memory of row_bwd_kernel<N, HEAD> (floats: 3N reductions; HEAD: [A][N] weights, A + 2 scalars and
-// eight warp-private [A][N] gradient slices)
+// dynamic shared memory of row_bwd_kernel<N, HEAD> (floats: eight warp-private [3N] reduction slices; HEAD: [A][N]
+// weights, eight warp-private [A][N] gradient slices, [8][A] + [8][2] scalars)
 static size_t row_bwd_smem(int N, int A, bool head) {
-  return (size_t)(3 * N + (head ? A * N + A + 2 + 8 * A * N : 0)) * sizeof(float);
+  return (size_t)(24 * N + (head ? A * N + 8 * A + 16 + 8 * A * N : 0)) * sizeof(float);
 }
+static int64_t row_bwd_part_floats(int N, int A) { return 3 * (int64_t)N + (int64_t)A * N + A + 2; }
 
 template <int N, bool HEAD, typename... Args>
 static int launch_row_bwd(dim3 grid, int A, cudaStream_t st, Args... args) {
@@ -1854,6 +1916,38 @@ static int launch_row_bwd(dim3 grid, int A, cudaStream_t st, Args... args) {
     return check_launch("row_bwd(cudaFuncSetAttribute)");
   LaunchScope _ls(K_ROW_BWD, st);
   row_bwd_kernel<N, HEAD><<<grid, 256, sm, st>>>(args...);
+  return 0;
+}
+static void launch_row_bwd_final(const float* part, dim3 rbg, int N, int A, bool head, float* grads, int64_t P,
+                                 int64_t off_dscale, int64_t off_dbias, int64_t off_db, int64_t off_hw, int64_t off_hb,
+                                 float* loss_sum, float* qsa_sum, cudaStream_t st) {
+  const int stride = 3 * N + (head ? A * N + A + 2 : 0);
+  LaunchScope _ls(K_ROW_BWD, st);
+  row_bwd_final_kernel<<<dim3(cdiv(stride, 256), rbg.y), 256, 0, st>>>(part, (int)rbg.x, N, A, head ? 1 : 0, grads, P,
+                                                                         off_dscale, off_dbias, off_db, off_hw, off_hb,
+                                                                         loss_sum, qsa_sum);
+}
+
+// row_bwd + its fixed-order finalize.  off_scale = LayerNorm scale of this layer (also where d scale goes), off_bias its
+// bias slot, off_db the bias of the dense layer before it.
+static int run_row_bwd(int N, bool head, dim3 rbg, int A, cudaStream_t st, const float* Hh, const float* XHAT,
+                       const float* RSTD, const float* DH, float* DZ, float* DZLO, __half* DZ16H, __half* DZ16L,
+                       float gscale, const float* params, float* grads, int64_t P, int64_t off_scale, int64_t off_bias,
+                       int64_t off_db, int64_t off_hw, int64_t off_hb, const int32_t* gather, const int32_t* action,
+                       const float* target, int64_t trps, float* loss_sum, float* qsa_sum, float* part, int rows) {
+  int rc = 0;
+#define PQN_RB(NN, HH)                                                                                              \
+  rc = launch_row_bwd<NN, HH>(rbg, A, st, Hh, XHAT, RSTD, DH, DZ, DZLO, DZ16H, DZ16L, gscale, params, grads, P,     \
+                              off_scale, off_scale, off_bias, off_db, off_hw, off_hb, A, gather, action, target, trps, \
+                              part, rows)
+  if (N == 128 && head) PQN_RB(128, true);
+  else if (N == 128) PQN_RB(128, false);
+  else if (N == 256 && head) PQN_RB(256, true);
+  else if (N == 256) PQN_RB(256, false);
+  else return set_error(PQN_E_UNSUPPORTED, "row_bwd width %d", N);
+#undef PQN_RB
+  if (rc) return rc;
+  launch_row_bwd_final(part, rbg, N, A, head, grads, P, off_scale, off_bias, off_db, off_hw, off_hb, loss_sum, qsa_sum, st);
   return 0;
 }
 
@@ -2267,10 +2361,10 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
                       L.ln1_scale, L.ln1_bias, 0, 0, A, w.h2, w.xhat2, w.rstd2, nullptr, R, FLAT_CNN);
     }
     const dim3 rbg(conv_mma_ctas(S, R, 4), S);
-    if ((rc = launch_row_bwd<128, true>(rbg, A, st,
-        w.h2, w.xhat2, w.rstd2, nullptr, w.dz2, (use_tc && !f16) ? w.dz2_lo : nullptr, f16 ? pl.dz_hi : nullptr,
-        f16 ? pl.dz_lo : nullptr, gscale, params, grads, P, L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d0_b,
-        L.head_w, L.head_b, A, gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, R))) return rc;
+    if ((rc = run_row_bwd(128, true, rbg, A, st, w.h2, w.xhat2, w.rstd2, nullptr, w.dz2, (use_tc && !f16) ? w.dz2_lo : nullptr,
+                          f16 ? pl.dz_hi : nullptr, f16 ? pl.dz_lo : nullptr, gscale, params, grads, P, L.ln1_scale,
+                          L.ln1_bias, L.d0_b, L.head_w, L.head_b, gather, action, target, tr_rows_per_seed, loss_sum,
+                          qsa_sum, w.rb_part, R))) return rc;
     if (f16) {
       if ((rc = tc16_wgrad(grads, P, L, pl, S, R, gscale, st))) return rc;
       if ((rc = tc16_dgrad(w, pl, S, R, g_conv_mma == 1, gscale, st))) return rc;
@@ -2291,10 +2385,10 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
       const dim3 mg(conv_mma_ctas(S, R, 2), S);
       LaunchScope _ls(K_CONV_BWD, st);
       switch (d->in_c) {
-        case 4: rc = launch_conv_bwd_mma<4>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
-        case 6: rc = launch_conv_bwd_mma<6>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
-        case 7: rc = launch_conv_bwd_mma<7>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
-        case 10: rc = launch_conv_bwd_mma<10>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, R); break;
+        case 4: rc = launch_conv_bwd_mma<4>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, w.cb_part, R); break;
+        case 6: rc = launch_conv_bwd_mma<6>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, w.cb_part, R); break;
+        case 7: rc = launch_conv_bwd_mma<7>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, w.cb_part, R); break;
+        case 10: rc = launch_conv_bwd_mma<10>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, w.cb_part, R); break;
       }
       if (rc) return rc;
     } else
@@ -2315,44 +2409,22 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
     if (d->layers == 2) {
       launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.h0, rows * H, H, params, P, L.d1_w, L.d1_b, L.ln1_scale,
                       L.ln1_bias, 0, 0, A, w.hh1, w.xhat1, w.rstd1, nullptr, R, H);
-      if (H == 128)
-        { launch_row_bwd<128, true>(rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
-                                                        L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
-                                                        L.head_b, A, gather, action, target, tr_rows_per_seed,
-                                                        loss_sum, qsa_sum, R); }
-      else
-        { launch_row_bwd<256, true>(rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
-                                                        L.ln1_scale, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w,
-                                                        L.head_b, A, gather, action, target, tr_rows_per_seed,
-                                                        loss_sum, qsa_sum, R); }
+      if ((rc = run_row_bwd(H, true, rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w, L.head_b,
+                            gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, w.rb_part, R))) return rc;
       const int tiles = (H / 128) * (H / 128);
       const int splits = wgrad_splits(tiles, S, R);
       { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(H / 128, H / 128, S * splits), GT, 0, st>>>(w.h0, rows * H, H, w.dzl, rows * H, H, grads, P,
                                                                       L.d1_w, R, H, splits); }
       { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(w.dzl, rows * H, H, params, P, L.d1_w, w.h0,
                                                                      w.dh0, rows * H, R, H); }
-      if (H == 128)
-        { launch_row_bwd<128, false>(rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
-                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
-                                                         nullptr, nullptr, nullptr, 0, nullptr, nullptr, R); }
-      else
-        { launch_row_bwd<256, false>(rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
-                                                         L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0, A,
-                                                         nullptr, nullptr, nullptr, 0, nullptr, nullptr, R); }
+      if ((rc = run_row_bwd(H, false, rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0,
+                            nullptr, nullptr, nullptr, 0, nullptr, nullptr, w.rb_part, R))) return rc;
       const int sp0 = wgrad_splits(H / 128, S, R);
       { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dh0, rows * H, H, grads,
                                                                         P, L.d0_w, R, D, sp0); }
     } else {
-      if (H == 128)
-        { launch_row_bwd<128, true>(rbg, A, st, w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
-                                                        L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
-                                                        L.head_b, A, gather, action, target, tr_rows_per_seed,
-                                                        loss_sum, qsa_sum, R); }
-      else
-        { launch_row_bwd<256, true>(rbg, A, st, w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P,
-                                                        L.ln0_scale, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w,
-                                                        L.head_b, A, gather, action, target, tr_rows_per_seed,
-                                                        loss_sum, qsa_sum, R); }
+      if ((rc = run_row_bwd(H, true, rbg, A, st, w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w, L.head_b,
+                            gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, w.rb_part, R))) return rc;
       const int sp0 = wgrad_splits(H / 128, S, R);
       { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dzl, rows * H, H, grads,
                                                                         P, L.d0_w, R, D, sp0); }

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += red[w];
-    atomicAdd(gn + seed, t);
+    gn[(int64_t)seed * NORM_BLOCKS + blockIdx.x] = t;   // block partial; radam_kernel adds them in block order
   }
 }
 
@@ -61,7 +61,10 @@ __global__ void __launch_bounds__(256) radam_kernel(float* __restrict__ params, 
   const float bc1 = __ldg(sched + 4 * t + 1);
   const float bc2 = __ldg(sched + 4 * t + 2);
   const float rect = __ldg(sched + 4 * t + 3);
-  const float g_norm = sqrtf(gn[seed]);
+  float gsq = 0.f;
+#pragma unroll 8
+  for (int b = 0; b < NORM_BLOCKS; ++b) gsq += gn[(int64_t)seed * NORM_BLOCKS + b];   // fixed order: deterministic
+  const float g_norm = sqrtf(gsq);
   const bool no_clip = g_norm < max_norm;
   const int64_t off = (int64_t)seed * P + i4 * 4;
   float4 p = *reinterpret_cast<float4*>(params + off);
@@ -162,8 +165,6 @@ int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu,
       S > 65535)
     return set_error(PQN_E_INVALID, "pqn_radam_clip_step: bad argument (P must be a multiple of 4)");
   cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(gnorm_scratch, 0, (size_t)S * sizeof(float), st) != cudaSuccess)
-    return check_launch("pqn_radam_clip_step(memset)");
   { LaunchScope _ls(K_SQNORM, st); sqnorm_kernel<<<dim3(NORM_BLOCKS, S), 256, 0, st>>>(grads, P, gnorm_scratch); }
   const unsigned nb = (unsigned)((P / 4 + 255) / 256);
   { LaunchScope _ls(K_RADAM, st); radam_kernel<<<dim3(nb, S), 256, 0, st>>>(params, grads, mu, nu, sched, step_counter, gnorm_scratch, P, max_norm, b1,

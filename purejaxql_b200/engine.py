@@ -185,7 +185,7 @@ class PQNEngine:
         self._cur_stats = batch_stats                               # read by forward() (train=False => running stats)
         bn_sums = torch.zeros(S, 2 * F, device=dev)
         step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        gnorm = torch.zeros(S, device=dev)
+        gnorm = torch.zeros(S * 64, device=dev)                     # block partials of the squared gradient norm
 
         k = jr.split(K1, 2, mode)
         K2, kT0 = k[:, 0].contiguous(), k[:, 1].contiguous()        # :415

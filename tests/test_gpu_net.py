@@ -202,7 +202,7 @@ def test_radam_clip_matches_oracle():
     p = rng.standard_normal((S, P)).astype(np.float32)
     tab = radam_schedule_table(steps, lambda i: np.float32(1e-3 * (1 - i / 20)))
     tp = torch.from_numpy(p.copy()).to(dev()); mu = torch.zeros_like(tp); nu = torch.zeros_like(tp)
-    cnt = torch.zeros(1, dtype=torch.int32, device=dev()); gn = torch.zeros(S, device=dev())
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev()); gn = torch.zeros(S * 64, device=dev())
     refs = [({"w": p[s].copy()}, R.opt_init({"w": p[s]})) for s in range(S)]
     ttab = torch.from_numpy(tab).to(dev())
     for i in range(steps):

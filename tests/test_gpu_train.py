@@ -240,3 +240,18 @@ def test_wandb_offline_logging_path(tmp_path, monkeypatch):
         wandb.finish()
     assert out["metrics"]["td_loss"].shape == (2, 8)
     assert any(p.name.startswith("offline-run") for p in (tmp_path / "wandb").iterdir())
+
+
+def test_two_identical_runs_give_bit_identical_parameters():
+    """No float atomics on the default path: every cross-row reduction is a fixed-order
+    two-stage sum, so train() is run-to-run deterministic like the reference."""
+    from purejaxql_b200 import pqn_minatar
+    outs = []
+    for _ in range(2):
+        cfg = _cfg("Breakout-MinAtar", NUM_ENVS=256, NUM_STEPS=8, NUM_MINIBATCHES=4, EPS_START=0.5, EPS_FINISH=0.1,
+                   EPS_DECAY=1.0)
+        cfg["TOTAL_TIMESTEPS"] = cfg["TOTAL_TIMESTEPS_DECAY"] = float(4 * cfg["NUM_STEPS"] * cfg["NUM_ENVS"])
+        out = pqn_minatar.make_train(cfg)(jr.split(jr.PRNGKey(4), 3))
+        outs.append((out["runner_state"][0].params_flat.cpu().numpy(), out["metrics"]["td_loss"].cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
