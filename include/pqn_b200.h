@@ -223,14 +223,14 @@ int pqn_radam_clip_step(float* params, const float* grads, float* mu, float* nu,
 int pqn_bn_stats_update(float* batch_stats, float* bn_sums, int32_t S, int32_t F, int64_t stats_seed_stride,
                         float count, float momentum, void* stream);
 
-/* The CNN's dense layer (forward, wgrad, dgrad) runs on the tcgen05 3xTF32 path: 2 (default) derives the "lo"
- * half of the activation operand inside the GEMM kernel, 1 reads it from a tensor the conv forward wrote,
- * 0 selects the fp32 FFMA kernels instead (kept as the A/B reference for parity tests). */
+/* Implementation selectors of the CNN (process-wide; the defaults are the fast paths, the others are kept as A/B
+ * references for the parity tests):
+ *  tensor-core path of the dense layer (forward, wgrad, dgrad): 2 (default) = tcgen05 kind::f16 on fp16-split (hi, lo')
+ *  operand planes; 1 = tcgen05 3xTF32 with the lo operand derived in the kernel; 0 = fp32 FFMA kernels. */
 int pqn_set_tensor_core_path(int on);
-/* The CNN's 3x3 conv (forward, recompute and weight gradient) runs on warp-level tf32 tensor-core MMA built
- * straight from the packed observation bits by default (1); 0 selects the fp32 CUDA-core kernels; 2 runs the
- * forward conv on tcgen05 (im2col rows written by the producer threads directly in the UMMA smem layout;
- * correct, but measured slower than 1 because the per-pixel LayerNorm/store epilogue dominates: DESIGN.md). */
+/*  3x3 conv forward: 1 (default) = fp16 mma.sync (exponent-coded im2col bits, fp16-split weights); 3 = the tf32
+ *  mma.sync kernel of round 1; 2 = tcgen05 (correct, slower: per-pixel epilogue); 0 = fp32 CUDA cores.  The conv
+ *  weight gradient runs on tf32 mma.sync for 1-3. */
 int pqn_set_conv_mma_path(int on);
 
 /* ---- tcgen05 (5th-gen tensor core) path of the dense contractions ----------

@@ -31,7 +31,8 @@ constexpr int FLAT_CNN = CONV_PIX * CONV_O;  // 1024
 // tcgen05 path for the CNN dense layer (pqn_set_tensor_core_path); default on
 static int g_use_tc = 2;  // 0 FFMA, 1 tcgen05 3xTF32 (A_lo derived in the kernel), 2 tcgen05 fp16-split planes (default)
 // warp-level tensor-core (mma.sync tf32) conv kernels (pqn_set_conv_mma_path); default on
-static int g_conv_mma = 1;   // 0: fp32 CUDA cores, 1: mma.sync tf32, 2: tcgen05 forward (+ mma.sync backward)
+static int g_conv_mma = 1;   // 0: fp32 CUDA cores, 1: fp16 mma.sync forward (default), 2: tcgen05 forward, 3: tf32 mma.sync forward
+                             // (1-3: tf32 mma.sync backward)
 
 static inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
 
@@ -981,20 +982,30 @@ struct PatchCfg {
   static constexpr int WORDS = (9 * C + 31) / 32;
 };
 
+// The 9C patch bits of output pixel `pix` as PatchCfg::WORDS words.  The packed observation is pixel-major /
+// channel-minor, so the three taps (dj = 0..2) x C channels of one patch row are 3C CONSECUTIVE bits of the input row:
+// three funnel-shift extracts instead of nine per-pixel ones.
 template <int C>
-__device__ __forceinline__ void build_patch(const uint32_t* __restrict__ so, int pix, uint32_t* __restrict__ out) {
+__device__ __forceinline__ void patch_bits(const uint32_t* __restrict__ so, int pix, uint32_t (&w)[PatchCfg<C>::WORDS]) {
   constexpr int W = PatchCfg<C>::WORDS;
-  uint32_t w[W];
 #pragma unroll
   for (int k = 0; k < W; ++k) w[k] = 0u;
   const int y = pix >> 3, x = pix & 7;
 #pragma unroll
-  for (int r = 0; r < 9; ++r) {
-    const uint32_t nib = pixel_bits<C>(so, (y + r / 3) * 10 + x + r % 3);
-    const int o = r * C;  // compile-time after unrolling
-    w[o >> 5] |= nib << (o & 31);
-    if ((o & 31) + C > 32) w[min((o >> 5) + 1, W - 1)] |= nib >> (32 - (o & 31));
+  for (int di = 0; di < 3; ++di) {
+    const int f0 = ((y + di) * 10 + x) * C;
+    const uint32_t r = __funnelshift_r(so[f0 >> 5], so[(f0 >> 5) + 1], f0 & 31) & ((1u << (3 * C)) - 1u);
+    const int o = 3 * C * di;  // compile-time after unrolling
+    w[o >> 5] |= r << (o & 31);
+    if ((o & 31) + 3 * C > 32) w[min((o >> 5) + 1, W - 1)] |= r >> (32 - (o & 31));
   }
+}
+
+template <int C>
+__device__ __forceinline__ void build_patch(const uint32_t* __restrict__ so, int pix, uint32_t* __restrict__ out) {
+  constexpr int W = PatchCfg<C>::WORDS;
+  uint32_t w[W];
+  patch_bits<C>(so, pix, w);
 #pragma unroll
   for (int k = 0; k < W; ++k) out[k] = w[k];
 }
@@ -1056,16 +1067,7 @@ template <int C>
 __device__ __forceinline__ void build_exp_patch(const uint32_t* __restrict__ so, int pix, uint32_t* __restrict__ out) {
   constexpr int W = PatchCfg<C>::WORDS;
   uint32_t w[W];
-#pragma unroll
-  for (int k = 0; k < W; ++k) w[k] = 0u;
-  const int y = pix >> 3, x = pix & 7;
-#pragma unroll
-  for (int r = 0; r < 9; ++r) {
-    const uint32_t nib = pixel_bits<C>(so, (y + r / 3) * 10 + x + r % 3);
-    const int o = r * C;
-    w[o >> 5] |= nib << (o & 31);
-    if ((o & 31) + C > 32) w[min((o >> 5) + 1, W - 1)] |= nib >> (32 - (o & 31));
-  }
+  patch_bits<C>(so, pix, w);
 #pragma unroll
   for (int ks = 0; ks < ExpPatch<C>::KS; ++ks)  // 8 | 32: a k-step never straddles two words; bits >= 9C are zero
     out[ks] = ((w[(8 * ks) >> 5] >> ((8 * ks) & 31)) & 0xFFu) << 23;
@@ -1258,6 +1260,280 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
         if (t == 0) { brow[16 * mb + g] = (uint16_t)rb0; brow[16 * mb + g + 8] = (uint16_t)rb1; }
       }
      }
+    }
+  }
+  if (TRAIN && bn_sums != nullptr) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      int v = cnt[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v) atomicAdd(&s_cnt[c], (float)v);
+    }
+    __syncthreads();
+    if (tid < C && s_cnt[tid] != 0.f) {
+      atomicAdd(bn_sums + (int64_t)seed * 2 * C + tid, s_cnt[tid]);
+      atomicAdd(bn_sums + (int64_t)seed * 2 * C + C + tid, s_cnt[tid]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv forward on fp16 warp-level MMA (mma.sync.m16n8k16, fp32 accumulate) -- the default conv path of round 2.
+// Same structure as conv_fwd_mma_kernel (one sample per warp, quad-level LayerNorm), but
+//   * the {0,1} im2col operand is fp16 and "exponent coded": per output pixel and k-step of 16 taps two words hold the
+//     tap bits at the exponent bits 10..13 of the low half and 26..29 of the high half; lane t of the fragment masks
+//     bit (10 + t) / (26 + t), which turns a set bit into the fp16 power of two 2^(2^t - 15) (one LOP3 per register
+//     that carries TWO k values) and row k of B is pre-multiplied by the inverse power of two (exact), so every product
+//     equals the plain 0/1 product;
+//   * weights/255 are split into fp16 hi + lo (22 significant bits, like the tf32 hi/lo pair);
+//   * K = 9C taps padded to 16 needs ceil(9C/16) k-steps (3 for C = 4) instead of ceil(9C/8) = 5 tf32 ones: 48 MMAs
+//     and 48 fragment LOP3s per sample instead of 80 / 80 (the tf32 kernel's top stall was the mma.sync pipe).
+// k order inside a k-step (free to choose, B is laid out to match): fragment column 2t <-> tap 16s + t,
+// 2t+1 <-> 16s + 4 + t, 2t+8 <-> 16s + 8 + t, 2t+9 <-> 16s + 12 + t.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_f16_16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int C>
+struct Conv16 {
+  static constexpr int TAPS = 9 * C;
+  static constexpr int KS = (TAPS + 15) / 16;          // k-steps of 16 taps
+  static constexpr int ROW = 2 * KS < 8 ? 8 : 2 * KS;  // padded row: 8 or 12 words keep the 4-row LDS.64 groups apart
+};
+
+// tap of fragment column kk (0..15) of k-step s, see the k order above
+__host__ __device__ constexpr int conv16_tap(int s, int kk) {
+  return 16 * s + (kk < 8 ? 0 : 8) + ((kk & 1) ? 4 : 0) + ((kk & 7) >> 1);
+}
+
+// B fragments of weights/255 as fp16 (hi, lo), pre-scaled by the inverse of the A coding: wb[s][h][lane] = uint4
+// {b0_hi, b1_hi, b0_lo, b1_lo} (b0 = columns k = 2t, 2t+1; b1 = k = 2t+8, 2t+9; n = 8h + g)
+template <int C>
+__device__ __forceinline__ void conv16_load_weights(const float* __restrict__ prm, const pqn_net_layout_t& L, uint4* wb,
+                                                    float* cb, float* sc, float* bi) {
+  using M = Conv16<C>;
+  const float inv255 = 1.0f / 255.0f;
+  for (int i = threadIdx.x; i < M::KS * 2 * 32; i += blockDim.x) {
+    const int ln = i & 31, h = (i >> 5) & 1, s = i >> 6;
+    const int gg = ln >> 2, tt = ln & 3;
+    const int o = h * 8 + gg;
+    const float scale = __uint_as_float((uint32_t)(127 + 15 - (1 << tt)) << 23);   // 2^(15 - 2^t), exact
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {   // q: 0 -> k=2t, 1 -> 2t+1, 2 -> 2t+8, 3 -> 2t+9
+      const int tap = conv16_tap(s, 2 * tt + (q & 1) + (q >> 1) * 8);
+      v[q] = tap < M::TAPS ? __ldg(prm + L.conv_w + tap * CONV_O + o) * inv255 * scale : 0.f;
+      v[q] = fminf(fmaxf(v[q], -65000.f), 65000.f);
+    }
+    const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2half2_rn(v[2] - f1.x, v[3] - f1.y);
+    wb[i] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                       *reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  }
+  if (threadIdx.x < CONV_O) {
+    cb[threadIdx.x] = __ldg(prm + L.conv_b + threadIdx.x);
+    sc[threadIdx.x] = __ldg(prm + L.ln0_scale + threadIdx.x);
+    bi[threadIdx.x] = __ldg(prm + L.ln0_bias + threadIdx.x);
+  }
+}
+
+// exponent-coded fp16 patch words of one output pixel: out[2s], out[2s+1] for k-step s (taps 16s..16s+7, 16s+8..16s+15).
+// Only bits 10..13 and 26..29 are meaningful (the fragment mask picks one of them per half); tap 16s+j, j<4 sits at bit
+// 10+j and tap 16s+4+j at bit 26+j.
+template <int C>
+__device__ __forceinline__ void build_patch16(const uint32_t* __restrict__ so, int pix, uint32_t* __restrict__ out) {
+  constexpr int W = PatchCfg<C>::WORDS;
+  uint32_t w[W];
+  patch_bits<C>(so, pix, w);
+#pragma unroll
+  for (int b = 0; b < 2 * Conv16<C>::KS; ++b) {
+    const int o = 8 * b;                                   // bit offset of this byte in the patch string
+    uint32_t v = (o >> 5) < W ? w[(o >> 5) < W ? (o >> 5) : 0] : 0u;
+    const int sh = o & 31;
+    const uint32_t lo = sh >= 10 ? v >> (sh - 10) : v << (10 - sh);          // bits sh..sh+3   -> 10..13
+    const uint32_t hi = sh + 4 <= 26 ? v << (26 - sh - 4) : v >> (sh + 4 - 26);  // bits sh+4..sh+7 -> 26..29
+    out[b] = __byte_perm(lo, hi, 0x7610);                  // low half from lo, high half from hi
+  }
+}
+
+// patch row of one pixel -> shared memory with 128-bit stores (ROW is 8 or 12 words; pad words are never read)
+template <int C>
+__device__ __forceinline__ void store_patch16(const uint32_t* __restrict__ so, int pix, uint32_t* __restrict__ row) {
+  using M = Conv16<C>;
+  uint32_t w[M::ROW];
+#pragma unroll
+  for (int k = 0; k < M::ROW; ++k) w[k] = 0u;
+  build_patch16<C>(so, pix, w);
+#pragma unroll
+  for (int q = 0; q < M::ROW / 4; ++q)
+    *reinterpret_cast<uint4*>(row + 4 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
+template <int C>
+__device__ __forceinline__ void conv16_block2(const uint32_t* __restrict__ xp, const uint4* __restrict__ wb,
+                                              const float* __restrict__ cb, int mbp, int lane, float (&z)[2][2][4]) {
+  using M = Conv16<C>;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t mask = (1u << (10 + t)) | (1u << (26 + t));
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      z[i][h][0] = z[i][h][2] = cb[8 * h + 2 * t];
+      z[i][h][1] = z[i][h][3] = cb[8 * h + 2 * t + 1];
+    }
+  const uint32_t* r00 = xp + (32 * mbp + g) * M::ROW;
+#pragma unroll
+  for (int s = 0; s < M::KS; ++s) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint2 w0 = *reinterpret_cast<const uint2*>(r00 + (16 * i) * M::ROW + 2 * s);       // pixel row g
+      const uint2 w1 = *reinterpret_cast<const uint2*>(r00 + (16 * i + 8) * M::ROW + 2 * s);   // pixel row g + 8
+      a[i][0] = w0.x & mask; a[i][1] = w1.x & mask; a[i][2] = w0.y & mask; a[i][3] = w1.y & mask;
+    }
+    uint4 b[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) b[h] = wb[(s * 2 + h) * 32 + lane];
+    // lo pass of all four accumulators, then the hi pass: no back-to-back dependent MMAs
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) mma_f16_16n8k16(z[i][h], a[i], b[h].z, b[h].w);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) mma_f16_16n8k16(z[i][h], a[i], b[h].x, b[h].y);
+  }
+}
+
+__device__ __forceinline__ uint32_t cvt_f16x2_satfinite(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <int C, bool TRAIN, bool H16>
+__global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
+    conv_fwd_mma16_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
+                          const float* __restrict__ params, int64_t P, pqn_net_layout_t L, float* __restrict__ H1,
+                          float* __restrict__ H1LO, float* __restrict__ XH1, float* __restrict__ RS1,
+                          uint32_t* __restrict__ RB, float* __restrict__ bn_sums, int rows) {
+  using Cfg = ConvCfg<C>;
+  using M = Conv16<C>;
+  __shared__ __align__(16) uint4 wb[M::KS * 2 * 32];
+  __shared__ float cb[CONV_O], sc[CONV_O], bi[CONV_O];
+  __shared__ uint32_t so[CONV_MMA_WARPS][Cfg::SW];
+  __shared__ __align__(16) uint32_t sxp[CONV_MMA_WARPS][CONV_PIX * M::ROW];
+  __shared__ float s_cnt[C];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int seed = blockIdx.y;
+  conv16_load_weights<C>(params + (int64_t)seed * P, L, wb, cb, sc, bi);
+  if (TRAIN && tid < C) s_cnt[tid] = 0.f;
+  __syncthreads();
+  int cnt[C];
+  uint32_t cmask[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    cnt[c] = 0;
+    cmask[c] = 0u;
+    if (TRAIN) {
+      for (int b = 0; b < 32; ++b) {
+        const int f = lane * 32 + b;
+        if (f < Cfg::OBS_BITS && f % C == c) cmask[c] |= 1u << b;
+      }
+    }
+  }
+  uint32_t* __restrict__ my_so = so[warp];
+  static_assert(Cfg::PW <= 32, "one packed observation word per lane");
+  if (lane == 0) my_so[Cfg::PW] = 0u;
+  const int row_stride = gridDim.x * CONV_MMA_WARPS;
+  auto fetch = [&](int r) -> uint32_t {
+    if (r >= rows || lane >= Cfg::PW) return 0u;
+    const int64_t src = gather ? gather[(int64_t)seed * rows + r] : r;
+    return __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + lane);
+  };
+  uint32_t pre = fetch(blockIdx.x * CONV_MMA_WARPS + warp);
+  for (int row = blockIdx.x * CONV_MMA_WARPS + warp; row < rows; row += row_stride) {
+    __syncwarp();
+    if (lane < Cfg::PW) my_so[lane] = pre;
+    if (TRAIN && bn_sums != nullptr) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) cnt[c] += __popc(pre & cmask[c]);
+    }
+    __syncwarp();
+    pre = fetch(row + row_stride);
+    store_patch16<C>(my_so, lane, sxp[warp] + lane * M::ROW);
+    store_patch16<C>(my_so, lane + 32, sxp[warp] + (lane + 32) * M::ROW);
+    __syncwarp();
+    const int64_t grow = (int64_t)seed * rows + row;
+    float* __restrict__ hrow = H16 ? nullptr : H1 + grow * FLAT_CNN;
+    __half* __restrict__ hrow16 = H16 ? reinterpret_cast<__half*>(H1) + grow * FLAT_CNN : nullptr;
+    __half* __restrict__ lrow16 = H16 ? reinterpret_cast<__half*>(H1LO) + grow * FLAT_CNN : nullptr;
+    float* __restrict__ xrow = (TRAIN && XH1) ? XH1 + grow * FLAT_CNN : nullptr;
+    float* __restrict__ rrow = (TRAIN && RS1) ? RS1 + grow * CONV_PIX : nullptr;
+    uint16_t* __restrict__ brow = (TRAIN && RB) ? reinterpret_cast<uint16_t*>(RB + grow * (FLAT_CNN / 32)) : nullptr;
+#pragma unroll 1
+    for (int mbp = 0; mbp < 2; ++mbp) {
+      float z2[2][2][4];
+      conv16_block2<C>(sxp[warp], wb, cb, mbp, lane, z2);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int mb = 2 * mbp + mi;
+        float (&z)[2][4] = z2[mi];
+        float mean0, rstd0, mean1, rstd1;
+        ln16_quad(z, mean0, rstd0, mean1, rstd1);
+        const float nm0 = -mean0 * rstd0, nm1 = -mean1 * rstd1;   // xhat = z * rstd - mean * rstd: one FFMA
+        uint32_t rb0 = 0u, rb1 = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int o = 8 * h + 2 * t;
+          const float x00 = fmaf(z[h][0], rstd0, nm0), x01 = fmaf(z[h][1], rstd0, nm0);
+          const float x10 = fmaf(z[h][2], rstd1, nm1), x11 = fmaf(z[h][3], rstd1, nm1);
+          float2 v0, v1;
+          v0.x = fmaxf(fmaf(x00, sc[o], bi[o]), 0.f);
+          v0.y = fmaxf(fmaf(x01, sc[o + 1], bi[o + 1]), 0.f);
+          v1.x = fmaxf(fmaf(x10, sc[o], bi[o]), 0.f);
+          v1.y = fmaxf(fmaf(x11, sc[o + 1], bi[o + 1]), 0.f);
+          const int p0 = 16 * mb + g, p1 = p0 + 8;
+          if (H16) {
+            // hi = fp16(h) (saturating: no inf), lo = fp16((h - hi) * 2^11)
+            const uint32_t h0 = cvt_f16x2_satfinite(v0.x, v0.y), h1v = cvt_f16x2_satfinite(v1.x, v1.y);
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1v));
+            const __half2 l0 = __floats2half2_rn((v0.x - f0.x) * tc::TC_LO_SCALE, (v0.y - f0.y) * tc::TC_LO_SCALE);
+            const __half2 l1 = __floats2half2_rn((v1.x - f1.x) * tc::TC_LO_SCALE, (v1.y - f1.y) * tc::TC_LO_SCALE);
+            *reinterpret_cast<uint32_t*>(hrow16 + p0 * CONV_O + o) = h0;
+            *reinterpret_cast<__half2*>(lrow16 + p0 * CONV_O + o) = l0;
+            *reinterpret_cast<uint32_t*>(hrow16 + p1 * CONV_O + o) = h1v;
+            *reinterpret_cast<__half2*>(lrow16 + p1 * CONV_O + o) = l1;
+          } else {
+            *reinterpret_cast<float2*>(hrow + p0 * CONV_O + o) = v0;
+            *reinterpret_cast<float2*>(hrow + p1 * CONV_O + o) = v1;
+          }
+          if (TRAIN) {
+            rb0 |= ((v0.x > 0.f ? 1u : 0u) | (v0.y > 0.f ? 2u : 0u)) << o;
+            rb1 |= ((v1.x > 0.f ? 1u : 0u) | (v1.y > 0.f ? 2u : 0u)) << o;
+          }
+          if (xrow) {
+            *reinterpret_cast<float2*>(xrow + p0 * CONV_O + o) = make_float2(x00, x01);
+            *reinterpret_cast<float2*>(xrow + p1 * CONV_O + o) = make_float2(x10, x11);
+            if (h == 0 && t == 0) { rrow[p0] = rstd0; rrow[p1] = rstd1; }
+          }
+        }
+        if (TRAIN && brow) {
+          rb0 |= __shfl_xor_sync(0xffffffffu, rb0, 1); rb1 |= __shfl_xor_sync(0xffffffffu, rb1, 1);
+          rb0 |= __shfl_xor_sync(0xffffffffu, rb0, 2); rb1 |= __shfl_xor_sync(0xffffffffu, rb1, 2);
+          if (t == 0) { brow[16 * mb + g] = (uint16_t)rb0; brow[16 * mb + g + 8] = (uint16_t)rb1; }
+        }
+      }
     }
   }
   if (TRAIN && bn_sums != nullptr) {
@@ -1986,19 +2262,23 @@ static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* ob
       default: return -1;
     }
   }
-  if (g_conv_mma && h16) {  // h1 / h1lo are the fp16 (hi, lo') planes
+  if (g_conv_mma == 1) {  // fp16 mma.sync conv (default); h16: h1 / h1lo are the fp16 (hi, lo') planes
     const dim3 mg(conv_mma_ctas((int)grid.y, rows, 3), grid.y);
     LaunchScope _ls(TRAIN ? K_CONV_FWD : K_CONV_FWD_INFER, st);
+#define PQN_CONV16(CC)                                                                                              \
+  if (h16) conv_fwd_mma16_kernel<CC, TRAIN, true><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); \
+  else conv_fwd_mma16_kernel<CC, TRAIN, false><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows)
     switch (C) {
-      case 4: conv_fwd_mma_kernel<4, TRAIN, true><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
-      case 6: conv_fwd_mma_kernel<6, TRAIN, true><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
-      case 7: conv_fwd_mma_kernel<7, TRAIN, true><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
-      case 10: conv_fwd_mma_kernel<10, TRAIN, true><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); break;
+      case 4: PQN_CONV16(4); break;
+      case 6: PQN_CONV16(6); break;
+      case 7: PQN_CONV16(7); break;
+      case 10: PQN_CONV16(10); break;
       default: return -1;
     }
+#undef PQN_CONV16
     return 0;
   }
-  if (g_conv_mma) {
+  if (g_conv_mma == 3) {  // the round-1 tf32 mma.sync conv (kept as an A/B reference)
     const dim3 mg(conv_mma_ctas((int)grid.y, rows, 3), grid.y);
     LaunchScope _ls(TRAIN ? K_CONV_FWD : K_CONV_FWD_INFER, st);
     switch (C) {
@@ -2226,7 +2506,7 @@ int64_t pqn_net_stats_floats(const pqn_net_desc_t* d) {
 }
 
 int pqn_set_conv_mma_path(int on) {
-  g_conv_mma = on < 0 ? 0 : (on > 2 ? 2 : on);
+  g_conv_mma = on < 0 ? 0 : (on > 3 ? 3 : on);
   return PQN_OK;
 }
 
@@ -2348,7 +2628,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
     launch_conv_fwd<true>(d->in_c, dim3(cdiv(rows, 4), S), st, ob, obs_rows_per_seed, gather, params, P, L,
                           conv16 ? (float*)pl.h1_hi : w.h1, conv16 ? (float*)pl.h1_lo : nullptr, bn_sums, R,
                           g_conv_mma ? w.cxhat : nullptr, g_conv_mma ? w.crstd : nullptr,
-                          g_conv_mma == 1 ? w.relu_bits : nullptr, conv16);
+                          (g_conv_mma == 1 || g_conv_mma == 3) ? w.relu_bits : nullptr, conv16);
     if (f16) {
       if (!conv16) launch_split16_h1(w.h1, pl, (int64_t)S * rows * FLAT_CNN, st);
       launch_split16_w1(params, P, L.d0_w, pl, S, st);
@@ -2367,10 +2647,10 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
                           qsa_sum, w.rb_part, R))) return rc;
     if (f16) {
       if ((rc = tc16_wgrad(grads, P, L, pl, S, R, gscale, st))) return rc;
-      if ((rc = tc16_dgrad(w, pl, S, R, g_conv_mma == 1, gscale, st))) return rc;
+      if ((rc = tc16_dgrad(w, pl, S, R, g_conv_mma == 1 || g_conv_mma == 3, gscale, st))) return rc;
     } else if (use_tc) {
       if ((rc = tc_wgrad(grads, P, L, w, S, R, st))) return rc;
-      if ((rc = tc_dgrad(params, P, L, w, S, R, g_conv_mma == 1, st))) return rc;
+      if ((rc = tc_dgrad(params, P, L, w, S, R, g_conv_mma == 1 || g_conv_mma == 3, st))) return rc;
     } else {
       const int splits = wgrad_splits(FLAT_CNN / 128, S, R);
       { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(FLAT_CNN / 128, 1, S * splits), GT, 0, st>>>(w.h1, rows * FLAT_CNN, FLAT_CNN, w.dz2,

@@ -52,9 +52,9 @@ def _ws(spec, S, rows):
     return torch.empty(n, dtype=torch.uint8, device=dev())
 
 
-@pytest.fixture(params=[(2, 1), (1, 1), (0, 0), (1, 0), (2, 2)],
-                ids=["tcgen05_f16split+mma_conv", "tcgen05_3xtf32+mma_conv", "ffma", "tcgen05_3xtf32+cuda_conv",
-                     "tcgen05_f16split+tcgen05_conv"])
+@pytest.fixture(params=[(2, 1), (1, 1), (0, 0), (1, 0), (2, 2), (2, 3)],
+                ids=["tcgen05_f16split+f16_mma_conv", "tcgen05_3xtf32+f16_mma_conv", "ffma", "tcgen05_3xtf32+cuda_conv",
+                     "tcgen05_f16split+tcgen05_conv", "tcgen05_f16split+tf32_mma_conv"])
 def dense_path(request):
     """Runs the CNN tests on the implementation variants: dense layer on tcgen05 (fp16-split planes = default,
     or 3xTF32) or fp32 FFMA; conv on warp-level tf32 MMA (default), fp32 CUDA cores or tcgen05."""
