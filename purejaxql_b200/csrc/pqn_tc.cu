@@ -209,9 +209,9 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, float (&acc)[1
 // acc[0..128) (+)= the 128 fp32 columns of this thread's TMEM lane at `row_addr`.  The loads are issued back to
 // back and awaited once (FIRST: all four 32-column loads straight into acc; otherwise two at a time, 64 staging
 // registers) -- the per-load round trip to TMEM was the longest part of the epilogue's dependent chain.
-template <bool FIRST>
-__device__ __forceinline__ void tmem_accumulate_row(uint32_t row_addr, float (&acc)[128], float scale = 1.0f) {
-  if constexpr (FIRST) {
+template <bool FIRST, int NC = 128>
+__device__ __forceinline__ void tmem_accumulate_row(uint32_t row_addr, float (&acc)[NC], float scale = 1.0f) {
+  if constexpr (FIRST && NC == 128) {
     uint32_t v0[32], v1[32], v2[32], v3[32];
     tmem_ld_32x32b_x32(row_addr, v0);
     tmem_ld_32x32b_x32(row_addr + 32, v1);
@@ -225,18 +225,48 @@ __device__ __forceinline__ void tmem_accumulate_row(uint32_t row_addr, float (&a
     }
   } else {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < NC / 64; ++c) {
       uint32_t v0[32], v1[32];
       tmem_ld_32x32b_x32(row_addr + c * 64, v0);
       tmem_ld_32x32b_x32(row_addr + c * 64 + 32, v1);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        acc[c * 64 + j] = fmaf(__uint_as_float(v0[j]), scale, acc[c * 64 + j]);   // scale == 1: exact add
-        acc[c * 64 + 32 + j] = fmaf(__uint_as_float(v1[j]), scale, acc[c * 64 + 32 + j]);
+        if (FIRST) {
+          acc[c * 64 + j] = __uint_as_float(v0[j]);
+          acc[c * 64 + 32 + j] = __uint_as_float(v1[j]);
+        } else {
+          acc[c * 64 + j] = fmaf(__uint_as_float(v0[j]), scale, acc[c * 64 + j]);   // scale == 1: exact add
+          acc[c * 64 + 32 + j] = fmaf(__uint_as_float(v1[j]), scale, acc[c * 64 + 32 + j]);
+        }
       }
     }
   }
+}
+
+// SPLIT epilogue (fp16 kernels with a store epilogue: wgrad, dgrad): EIGHT epilogue warps instead of four -- warps 2-5
+// take columns 0..63 of the tile, warps 6-9 columns 64..127 (a warp may only touch the TMEM lane quadrant warp % 4, and
+// both sets cover the four quadrants).  Half the registers per thread and twice the warps in flight: the dgrad
+// epilogue (K = 128, one tile every ~2500 MMA clocks) was latency-bound with one warp per scheduler (ncu r2c: issue
+// active 20 %, 4468 warp-instructions per tile).  The 32 x 32 staging tile of a warp is XOR-swizzled instead of padded
+// (8 x 4 KB fit next to the three operand stages).
+__device__ __forceinline__ void store_chunk_swz(float* stage, const float (&vals)[32], int lane, float* dst, int64_t ld,
+                                                int m_base, int M) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)   // row = lane, 16-byte chunk j -> physical chunk j ^ (lane & 7)
+    *reinterpret_cast<float4*>(stage + lane * 32 + 4 * (j ^ (lane & 7))) =
+        make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
+  __syncwarp();
+  const int r_in = lane >> 3, c4 = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + r_in;
+    if (m_base + r < M) {
+      const float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + 4 * (c4 ^ (r & 7)));
+      *reinterpret_cast<float4*>(dst + (int64_t)r * ld + 4 * c4) = o;
+    }
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------
@@ -251,8 +281,17 @@ __device__ __forceinline__ void tmem_accumulate_row(uint32_t row_addr, float (&a
 //     buffer with accumulate=0.
 // TMEM columns: main[2] at 0/128, corr[2] at 256/384.
 // ---------------------------------------------------------------------------
+template <int EPI, bool F16>
+struct TcSplit {
+  static constexpr bool value = F16 && (EPI == EPI_STORE || EPI == EPI_RELU_BITS);
+  static constexpr int threads = value ? TC_THREADS + 64 : TC_THREADS;
+  // operand ring + align slack + barriers + staging (split: 8 x [32][32]; else 4 x [32][36] + epilogue parameters)
+  static constexpr int smem = TC_STAGES * TC_STAGE_BYTES + 1024 + 256 +
+                              (value ? 8 * 32 * 32 * 4 : 4 * 32 * 36 * 4 + (384 + 8 * 128 + 8) * 4);
+};
+
 template <int A_MN, int B_MN, int EPI, bool F16 = false>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const GemmShape gs, const EpiParams ep) {
@@ -282,9 +321,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int i = 0; i < TC_STAGES; ++i) {
       mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&lo_full[i], TC_CONV_THREADS);
     }
+    constexpr int EPI_WARPS = TcSplit<EPI, F16>::value ? 8 : 4;
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&main_full[i], 1); mbar_init(&main_empty[i], 4);
-      mbar_init(&corr_full[i], 1); mbar_init(&corr_empty[i], 4);
+      mbar_init(&main_full[i], 1); mbar_init(&main_empty[i], EPI_WARPS);
+      mbar_init(&corr_full[i], 1); mbar_init(&corr_empty[i], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -438,7 +478,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 6 && !TcSplit<EPI, F16>::value) {
     // ===================== converter warps (6..7) =====================
     // The split is elementwise, so it is independent of the (swizzled) tile layout: byte i of the A_hi tile maps
     // to byte i of the A_lo tile.  TMA zero-fills out-of-range rows, whose lo is 0 as well.
@@ -469,9 +509,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..5; split mode: 2..9) =====================
+    constexpr bool SPLIT = TcSplit<EPI, F16>::value;
+    constexpr int NC = SPLIT ? 64 : 128;   // accumulator columns per thread
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access (warp id % 4)
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const int col_off = SPLIT ? (warp >= 6 ? 64 : 0) : 0;
     int mb = 0, cb = 0, ab = 0;
     uint32_t mb_phase = 0, cb_phase = 0, ab_phase = 0;
     const int partials = (gs.k_blocks + TC_PROMOTE - 1) / TC_PROMOTE;
@@ -486,19 +529,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // packed ReLU mask written by the conv forward: 16 bytes per (row, 128-column tile)
         const int m = m0 + quad * 32 + lane;
         if (m < gs.M) {
-          const uint4 b = __ldg(reinterpret_cast<const uint4*>(
-              ep.relu_bits + ((int64_t)seed * ep.rows + m) * (ep.ld_out >> 5) + (n0 >> 5)));
-          mask_bits[0] = b.x; mask_bits[1] = b.y; mask_bits[2] = b.z; mask_bits[3] = b.w;
+          const uint32_t* bp = ep.relu_bits + ((int64_t)seed * ep.rows + m) * (ep.ld_out >> 5) + (n0 >> 5);
+          if constexpr (SPLIT) {
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(bp + (col_off >> 5)));
+            mask_bits[0] = b.x; mask_bits[1] = b.y;
+          } else {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(bp));
+            mask_bits[0] = b.x; mask_bits[1] = b.y; mask_bits[2] = b.z; mask_bits[3] = b.w;
+          }
         }
       }
-      stage_epi_params<EPI>(ep, sp_all, seed, threadIdx.x - 64);
-      float acc[128];
+      if constexpr (!SPLIT) stage_epi_params<EPI>(ep, sp_all, seed, threadIdx.x - 64);
+      float acc[NC];
       if (single_acc) {
         uint64_t* e_bar = ab < 2 ? &main_empty[ab] : &corr_empty[ab - 2];
         uint64_t* f_bar = ab < 2 ? &main_full[ab] : &corr_full[ab - 2];
         mbar_wait(f_bar, ab_phase);
         tcgen05_fence_after();
-        tmem_accumulate_row<true>(tmem_base + ab * 128 + lane_off, acc);
+        tmem_accumulate_row<true, NC>(tmem_base + ab * 128 + col_off + lane_off, acc);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(e_bar);
@@ -507,8 +555,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int pi = 0; pi < partials; ++pi) {
         mbar_wait(&main_full[mb], mb_phase);
         tcgen05_fence_after();
-        if (pi == 0) tmem_accumulate_row<true>(tmem_base + mb * 128 + lane_off, acc);
-        else tmem_accumulate_row<false>(tmem_base + mb * 128 + lane_off, acc);
+        if (pi == 0) tmem_accumulate_row<true, NC>(tmem_base + mb * 128 + col_off + lane_off, acc);
+        else tmem_accumulate_row<false, NC>(tmem_base + mb * 128 + col_off + lane_off, acc);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&main_empty[mb]);
@@ -517,7 +565,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (gs.split3) {
         mbar_wait(&corr_full[cb], cb_phase);
         tcgen05_fence_after();
-        tmem_accumulate_row<false>(tmem_base + 256 + cb * 128 + lane_off, acc, F16 ? TC_LO_INV : 1.0f);
+        tmem_accumulate_row<false, NC>(tmem_base + 256 + cb * 128 + col_off + lane_off, acc, F16 ? TC_LO_INV : 1.0f);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&corr_empty[cb]);
@@ -526,10 +574,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       if (F16 && ep.out_scale != 0.f) {   // undo the power-of-two pre-scaling of an operand (exact)
 #pragma unroll
-        for (int j = 0; j < 128; ++j) acc[j] *= ep.out_scale;
+        for (int j = 0; j < NC; ++j) acc[j] *= ep.out_scale;
       }
-      epilogue_row<EPI>(ep, acc, stage_all + (warp - 2) * 32 * STG_LD, sp_all, lane, seed, m0 + quad * 32, n0, gs.M,
-                        mask_bits);
+      if constexpr (SPLIT) {
+        const int m_base = m0 + quad * 32;
+        float* out = ep.out + (int64_t)seed * ep.out_seed_stride + (int64_t)m_base * ep.ld_out + n0 + col_off;
+        float* stg = stage_all + (warp - 2) * 32 * 32;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = acc[c * 32 + j];
+            if (EPI == EPI_RELU_BITS) v[j] = ((mask_bits[c] >> j) & 1u) ? v[j] : 0.f;
+          }
+          store_chunk_swz(stg, v, lane, out + c * 32, ep.ld_out, m_base, gs.M);
+        }
+      } else {
+        epilogue_row<EPI>(ep, acc, stage_all + (warp - 2) * 32 * STG_LD, sp_all, lane, seed, m0 + quad * 32, n0, gs.M,
+                          mask_bits);
+      }
     }
   }
   tcgen05_fence_before();
@@ -582,13 +646,15 @@ static int num_sms() { return device_sm_count(); }
 template <int A_MN, int B_MN, int EPI, bool F16 = false>
 static int launch_t(const CUtensorMap* t, const GemmShape& gs, const EpiParams& ep, cudaStream_t st, int kid) {
   auto kfn = tc_gemm_kernel<A_MN, B_MN, EPI, F16>;
-  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+  constexpr int SMEM = TcSplit<EPI, F16>::smem, THREADS = TcSplit<EPI, F16>::threads;
+  static_assert(SMEM <= 227 * 1024, "dynamic shared memory of the GEMM kernel exceeds the per-CTA limit");
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
     return check_launch("tc_gemm(cudaFuncSetAttribute)");
   const int tiles = gs.m_tiles * gs.n_tiles * gs.S;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   {
     LaunchScope _ls(kid < 0 ? (int)K_TC_GEMM : kid, st);
-    kfn<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(t[0], t[1], t[2], t[3], gs, ep);
+    kfn<<<grid, THREADS, SMEM, st>>>(t[0], t[1], t[2], t[3], gs, ep);
   }
   return check_launch("tc_gemm");
 }
