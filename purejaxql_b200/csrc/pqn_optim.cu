@@ -55,16 +55,25 @@ __global__ void __launch_bounds__(256) radam_kernel(float* __restrict__ params, 
                                                     float b2, float eps) {
   const int seed = blockIdx.y;
   const int64_t i4 = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i4 * 4 >= P) return;
   const int t = step_counter[0];
   const float lr = __ldg(sched + 4 * t + 0);
   const float bc1 = __ldg(sched + 4 * t + 1);
   const float bc2 = __ldg(sched + 4 * t + 2);
   const float rect = __ldg(sched + 4 * t + 3);
-  float gsq = 0.f;
-#pragma unroll 8
-  for (int b = 0; b < NORM_BLOCKS; ++b) gsq += gn[(int64_t)seed * NORM_BLOCKS + b];   // fixed order: deterministic
-  const float g_norm = sqrtf(gsq);
+  // squared gradient norm = the NORM_BLOCKS (64) block partials of sqnorm_kernel, added in a FIXED order (xor-shuffle
+  // tree inside each of the first two warps, then warp 0 + warp 1) and broadcast through shared memory: deterministic,
+  // and one pass over the 64 partials per block instead of one per thread
+  static_assert(NORM_BLOCKS == 64, "two warps reduce the block partials");
+  __shared__ float s_half[2];
+  if (threadIdx.x < 64) {
+    float v = gn[(int64_t)seed * NORM_BLOCKS + threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_half[threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  const float g_norm = sqrtf(s_half[0] + s_half[1]);
+  if (i4 * 4 >= P) return;   // (after the block-wide barrier above)
   const bool no_clip = g_norm < max_norm;
   const int64_t off = (int64_t)seed * P + i4 * 4;
   float4 p = *reinterpret_cast<float4*>(params + off);

@@ -90,8 +90,10 @@ def test_norm_variant_eval_forward_matches_oracle(kind, norm_type, norm_input):
     obs, dev_obs = _inputs(kind, S, rows)
     A = spec.num_actions
     q = torch.zeros((S * rows, A), device=dev())
+    ws = _ws(spec, S, rows)
     _lib.check(_lib.lib().pqn_qnet_forward(spec.desc, _lib.p(flat), _lib.p(stf), _lib.p(dev_obs), None, rows, _lib.p(q),
-                                           S, rows, _lib.p(_ws(spec, S, rows)), _lib.stream_ptr()), "pqn_qnet_forward")
+                                           S, rows, _lib.p(ws), _lib.stream_ptr()), "pqn_qnet_forward")
+    torch.cuda.synchronize()
     q = q.cpu().numpy().reshape(S, rows, A)
     fwd = RN.cnn_forward if kind == "cnn" else RN.mlp_forward
     for s in range(S):
@@ -117,9 +119,11 @@ def test_norm_variant_loss_grad_matches_fp64_oracle(kind, norm_type, norm_input)
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev(), dt)
     st_dev = stf.clone()
     L = _lib.lib()
-    _lib.check(L.pqn_qnet_loss_grad(spec.desc, _lib.p(flat), _lib.p(st_dev), _lib.p(dev_obs), _lib.p(t(gather, torch.int32)),
-                                    total, _lib.p(t(act, torch.int32)), _lib.p(t(tgt, torch.float32)), total,
-                                    _lib.p(grads), _lib.p(ls), _lib.p(qs), _lib.p(bn), S, rows, _lib.p(_ws(spec, S, rows)),
+    # keep every device buffer referenced until the call has run (a temporary would be recycled by the allocator)
+    tg_, ta_, tt_, ws = t(gather, torch.int32), t(act, torch.int32), t(tgt, torch.float32), _ws(spec, S, rows)
+    _lib.check(L.pqn_qnet_loss_grad(spec.desc, _lib.p(flat), _lib.p(st_dev), _lib.p(dev_obs), _lib.p(tg_),
+                                    total, _lib.p(ta_), _lib.p(tt_), total,
+                                    _lib.p(grads), _lib.p(ls), _lib.p(qs), _lib.p(bn), S, rows, _lib.p(ws),
                                     _lib.stream_ptr()), "pqn_qnet_loss_grad")
     count = float(rows * (100 if kind == "cnn" else 1))
     _lib.check(L.pqn_bn_stats_update(_lib.p(st_dev), _lib.p(bn), S, F, spec.stats_total, count, 0.99, _lib.stream_ptr()))
@@ -218,6 +222,9 @@ def test_norm_variant_update_step_matches_oracle(env_name, kind, module, flatten
             assert abs(got - m["td_loss"]) < tol * max(1.0, abs(m["td_loss"])), (u, got, m["td_loss"])
         if kind == "cnn":
             for p, *_ in eng.spec.entries:
+                if norm_type == "batch_norm" and p[-1] == "bias" and p[-2] in ("Conv_0", "Dense_0") and p[0] == "CNN_0":
+                    continue   # a bias in front of a BatchNorm has an analytically zero gradient: RAdam normalises pure
+                               # rounding noise there, so the two implementations random-walk apart by ~lr per step
                 assert np.abs(leaf(ts.params, p) - params["/".join(p)]).max() < 5e-5, p
             for path, off, n in eng.spec.stats_entries():
                 want = box["stats"]["/".join(path)]
