@@ -145,6 +145,7 @@ int pqn_qlambda(const float* reward, const uint8_t* done, const float* maxq, con
  * blocks are float32[S][P] with the per-seed layout given by pqn_net_layout. */
 #define PQN_NET_MINATAR_CNN 0
 #define PQN_NET_MLP 1
+#define PQN_NET_RNN 2   /* RNNQNetwork (GRU) of pqn_rnn_gymnax.py:57-105: MLP trunk + one-hot last action + scanned GRU + head */
 
 typedef struct pqn_net_desc_t {
   int32_t kind;        /* PQN_NET_* */
@@ -171,6 +172,9 @@ typedef struct pqn_net_layout_t {
   int64_t ln1_scale, ln1_bias;   /* CNN: CNN_0/LayerNorm_1 [128] | MLP: LayerNorm_1 [H] (layers==2) */
   int64_t d1_w, d1_b;            /* MLP only: Dense_1 [H,H]/[H] (layers==2) */
   int64_t head_w, head_b;        /* final Dense [H,A]/[A] */
+  /* PQN_NET_RNN only (-1 otherwise): ScannedRNN_0/GRUCell_0/{ir,iz,in} kernel [H+A,H] + bias [H], {hr,hz} kernel [H,H],
+   * hn kernel [H,H] + bias [H] */
+  int64_t gru_ir_w, gru_ir_b, gru_iz_w, gru_iz_b, gru_in_w, gru_in_b, gru_hr_w, gru_hz_w, gru_hn_w, gru_hn_b;
 } pqn_net_layout_t;
 
 int pqn_net_layout(const pqn_net_desc_t* desc_host, pqn_net_layout_t* out_host);
@@ -206,6 +210,24 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* desc_host, const float* params, flo
                        const int32_t* gather, int64_t obs_rows_per_seed, const int32_t* action,
                        const float* target, int64_t tr_rows_per_seed, float* grads, float* loss_sum,
                        float* qsa_sum, float* bn_sums, int32_t S, int64_t rows, void* workspace, void* stream);
+
+/* ---- recurrent Q-network (PQN_NET_RNN; purejaxql/pqn_rnn_gymnax.py) -------------------------------------------
+ * One time step of network.apply(params, hs, obs[None], done[None], last_action[None], train=False) for S x E envs
+ * (rollout :201-213, evaluation :447-459, memory warm-up :517-529):
+ *   hs float32[S][E][H] carry, updated in place; obs float32 rows (row (s,e) at s*obs_rows_per_seed + e);
+ *   last_done uint8[S][E] resets the carry to zero BEFORE the cell (:41-45); last_action int32[S][E] is appended
+ *   one-hot to the GRU input (:84-85); q float32[S*E][A]. */
+int pqn_rnn_step(const pqn_net_desc_t* desc_host, const float* params, float* hs, const float* obs,
+                 int64_t obs_rows_per_seed, const uint8_t* last_done, const int32_t* last_action, float* q, int32_t S,
+                 int32_t E, void* workspace, void* stream);
+/* _loss_fn + value_and_grad of one minibatch window (:330-366): forward of the whole [T][B] window from the stored
+ * carry hs0[S][B][H] (train=True), in-loss Q(lambda) targets from the stop-gradient q values (:295-323, bootstrap
+ * max_a q[T-1]), loss = 0.5 mean over t < T-1, BPTT through the scanned GRU and the trunk.  All [S][T][B] tensors are
+ * time-major per seed.  grads[S][P] is overwritten; loss_sum[S] += loss, qsa_sum[S] += mean chosen q. */
+int pqn_rnn_loss_grad(const pqn_net_desc_t* desc_host, const float* params, const float* hs0, const float* obs,
+                      const uint8_t* last_done, const int32_t* last_action, const int32_t* action, const float* reward,
+                      const uint8_t* done, float* grads, float* loss_sum, float* qsa_sum, int32_t S, int32_t T, int32_t B,
+                      float gamma, float lambda, void* workspace, void* stream);
 
 /* optax.chain(clip_by_global_norm(max_norm), radam(lr_t)) + apply_updates
  * (pqn_minatar.py:159-162,292).  sched: float32[num_steps][4] per optimizer step

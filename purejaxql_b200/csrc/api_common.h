@@ -15,7 +15,8 @@ enum KernelId : int {
   K_CONV_FWD, K_DENSE_FWD, K_ROW_BWD, K_WGRAD, K_DGRAD, K_CONV_BWD, K_GATHER_ROWS, K_SQNORM, K_RADAM, K_ADVANCE,
   K_BN_UPDATE, K_TC_GEMM, K_TC_SPLIT, K_TC_FWD, K_TC_WGRAD, K_TC_DGRAD, K_NET_INIT,
   K_CONV_FWD_INFER /* rollout / evaluation variant */, K_TC_FWD_HEAD /* forward GEMM with the Q-head epilogue */,
-  K_NORM_FWD, K_NORM_BWD, K_NORM_REDUCE /* modular NORM_TYPE / NORM_INPUT path (pqn_norm.cuh) */, K_COUNT
+  K_NORM_FWD, K_NORM_BWD, K_NORM_REDUCE /* modular NORM_TYPE / NORM_INPUT path (pqn_norm.cuh) */,
+  K_RNN_SCAN, K_RNN_MISC /* GRU network (pqn_rnn.cuh) */, K_COUNT
 };
 
 // SM count of the CURRENT device (cached per device ordinal, not per process)

@@ -40,6 +40,8 @@ static int make_layout(const pqn_net_desc_t* d, pqn_net_layout_t* L) {
   int64_t off = 0;
   auto take = [&](int64_t n) { int64_t o = off; off += align4(n); return o; };
   L->d1_w = L->d1_b = L->ln1_scale = L->ln1_bias = L->conv_w = L->conv_b = -1;
+  L->gru_ir_w = L->gru_ir_b = L->gru_iz_w = L->gru_iz_b = L->gru_in_w = L->gru_in_b = -1;
+  L->gru_hr_w = L->gru_hz_w = L->gru_hn_w = L->gru_hn_b = -1;
   const int A = d->num_actions;
   const bool has_norm = d->norm_type != PQN_NORM_NONE;   // layer_norm and batch_norm have (scale, bias) of the same shape
   if (d->kind == PQN_NET_MINATAR_CNN) {
@@ -51,7 +53,7 @@ static int make_layout(const pqn_net_desc_t* d, pqn_net_layout_t* L) {
     L->d0_w = take((int64_t)FLAT_CNN * HID_CNN); L->d0_b = take(HID_CNN);
     if (has_norm) { L->ln1_scale = take(HID_CNN); L->ln1_bias = take(HID_CNN); }
     L->head_w = take((int64_t)HID_CNN * A); L->head_b = take(A);
-  } else if (d->kind == PQN_NET_MLP) {
+  } else if (d->kind == PQN_NET_MLP || d->kind == PQN_NET_RNN) {
     const int D = d->in_c, H = d->hidden;
     L->bn_scale = take(D); L->bn_bias = take(D);
     L->d0_w = take((int64_t)D * H); L->d0_b = take(H);
@@ -60,6 +62,13 @@ static int make_layout(const pqn_net_desc_t* d, pqn_net_layout_t* L) {
     if (d->layers == 2) {
       L->d1_w = take((int64_t)H * H); L->d1_b = take(H);
       if (has_norm) { L->ln1_scale = take(H); L->ln1_bias = take(H); }
+    }
+    if (d->kind == PQN_NET_RNN) {   // flax GRUCell: input denses with bias, recurrent ones without (except hn)
+      L->gru_ir_w = take((int64_t)(H + A) * H); L->gru_ir_b = take(H);
+      L->gru_iz_w = take((int64_t)(H + A) * H); L->gru_iz_b = take(H);
+      L->gru_in_w = take((int64_t)(H + A) * H); L->gru_in_b = take(H);
+      L->gru_hr_w = take((int64_t)H * H); L->gru_hz_w = take((int64_t)H * H);
+      L->gru_hn_w = take((int64_t)H * H); L->gru_hn_b = take(H);
     }
     L->head_w = take((int64_t)H * A); L->head_b = take(A);
   } else {
@@ -87,7 +96,7 @@ static int check_desc(const pqn_net_desc_t* d, const char* who) {
       return set_error(PQN_E_UNSUPPORTED, "%s: CNN in_c=%d (MinAtar uses 4/6/7/10)", who, d->in_c);
     return PQN_OK;
   }
-  if (d->kind == PQN_NET_MLP) {
+  if (d->kind == PQN_NET_MLP || d->kind == PQN_NET_RNN) {
     if (d->hidden != 128 && d->hidden != 256) return set_error(PQN_E_UNSUPPORTED, "%s: MLP hidden=%d (128 or 256 built)", who, d->hidden);
     if (d->layers != 1 && d->layers != 2) return set_error(PQN_E_UNSUPPORTED, "%s: MLP layers=%d (1 or 2 built)", who, d->layers);
     if (d->in_c < 1 || d->in_c > 4096) return set_error(PQN_E_INVALID, "%s: MLP in dim %d", who, d->in_c);
@@ -215,14 +224,14 @@ __global__ void __launch_bounds__(GT) dense_fwd_kernel(
   }
 
   // ---- epilogue: bias, LayerNorm over the BN columns of each row, ReLU
-  const float* __restrict__ bvec = prm + off_b;
+  const float* __restrict__ bvec = prm + (off_b >= 0 ? off_b : 0);
   const float* __restrict__ sc = prm + off_scale;
   const float* __restrict__ bi = prm + off_bias;
   float colb[TN], cols_[TN], colbi[TN];
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
     const int col = (j >> 2) * 64 + tx * 4 + (j & 3);
-    colb[j] = __ldg(bvec + col); cols_[j] = __ldg(sc + col); colbi[j] = __ldg(bi + col);
+    colb[j] = off_b >= 0 ? __ldg(bvec + col) : 0.f; cols_[j] = __ldg(sc + col); colbi[j] = __ldg(bi + col);
   }
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
@@ -375,7 +384,7 @@ __global__ void __launch_bounds__(GT) wgrad_kernel(const float* __restrict__ X, 
 __global__ void __launch_bounds__(GT) dgrad_kernel(const float* __restrict__ DZ, int64_t dz_seed_stride, int N,
                                                    const float* __restrict__ params, int64_t P, int64_t off_w,
                                                    const float* HPREV, float* OUT, int64_t h_seed_stride, int rows,
-                                                   int Kprev) {
+                                                   int Kprev, int accumulate = 0) {
   constexpr int BM = 128, BN = 128, TM = 8, TN = 8;
   __shared__ __align__(16) float As[2][BK * BM];
   __shared__ __align__(16) float Bs[2][BK * BN];
@@ -424,7 +433,7 @@ __global__ void __launch_bounds__(GT) dgrad_kernel(const float* __restrict__ DZ,
     if (kt + 1 < nk) sstore((kt + 1) & 1);
     __syncthreads();
   }
-  const float* Hs = HPREV + (int64_t)seed * h_seed_stride;
+  const float* Hs = HPREV + (int64_t)seed * h_seed_stride;   // ReLU mask source (the layer output: h > 0)
   float* Os = OUT + (int64_t)seed * h_seed_stride;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
@@ -439,6 +448,10 @@ __global__ void __launch_bounds__(GT) dgrad_kernel(const float* __restrict__ DZ,
       o.y = hv.y > 0.f ? acc[i][4 * c + 1] : 0.f;
       o.z = hv.z > 0.f ? acc[i][4 * c + 2] : 0.f;
       o.w = hv.w > 0.f ? acc[i][4 * c + 3] : 0.f;
+      if (accumulate) {   // OUT += ... (sum of several products, e.g. the three GRU gates; OUT must not alias HPREV)
+        const float4 prev = *reinterpret_cast<const float4*>(Os + (int64_t)row * Kprev + col);
+        o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+      }
       *reinterpret_cast<float4*>(Os + (int64_t)row * Kprev + col) = o;
     }
   }
@@ -1419,8 +1432,14 @@ __device__ __forceinline__ uint32_t cvt_f16x2_satfinite(float lo, float hi) {
   return r;
 }
 
+// 4 warps per CTA, 5 CTAs per SM = 5 warps per scheduler: 96 registers per thread.  (With 8-warp CTAs x 3 the cap is 80
+// registers and the epilogue spilled: ncu r2e, STL = 0.7 % of the instructions but 13 % of the stall samples; the
+// kernel wants ~123 registers unconstrained.)
+constexpr int CONV16_WARPS = 4;
+constexpr int CONV16_CTAS_PER_SM = 5;
+
 template <int C, bool TRAIN, bool H16>
-__global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
+__global__ void __launch_bounds__(CONV16_WARPS * 32, CONV16_CTAS_PER_SM)
     conv_fwd_mma16_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
                           const float* __restrict__ params, int64_t P, pqn_net_layout_t L, float* __restrict__ H1,
                           float* __restrict__ H1LO, float* __restrict__ XH1, float* __restrict__ RS1,
@@ -1429,8 +1448,8 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
   using M = Conv16<C>;
   __shared__ __align__(16) uint4 wb[M::KS * 2 * 32];
   __shared__ float cb[CONV_O], sc[CONV_O], bi[CONV_O];
-  __shared__ uint32_t so[CONV_MMA_WARPS][Cfg::SW];
-  __shared__ __align__(16) uint32_t sxp[CONV_MMA_WARPS][CONV_PIX * M::ROW];
+  __shared__ uint32_t so[CONV16_WARPS][Cfg::SW];
+  __shared__ __align__(16) uint32_t sxp[CONV16_WARPS][CONV_PIX * M::ROW];
   __shared__ float s_cnt[C];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -1454,14 +1473,14 @@ __global__ void __launch_bounds__(CONV_MMA_WARPS * 32, 3)
   uint32_t* __restrict__ my_so = so[warp];
   static_assert(Cfg::PW <= 32, "one packed observation word per lane");
   if (lane == 0) my_so[Cfg::PW] = 0u;
-  const int row_stride = gridDim.x * CONV_MMA_WARPS;
+  const int row_stride = gridDim.x * CONV16_WARPS;
   auto fetch = [&](int r) -> uint32_t {
     if (r >= rows || lane >= Cfg::PW) return 0u;
     const int64_t src = gather ? gather[(int64_t)seed * rows + r] : r;
     return __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + lane);
   };
-  uint32_t pre = fetch(blockIdx.x * CONV_MMA_WARPS + warp);
-  for (int row = blockIdx.x * CONV_MMA_WARPS + warp; row < rows; row += row_stride) {
+  uint32_t pre = fetch(blockIdx.x * CONV16_WARPS + warp);
+  for (int row = blockIdx.x * CONV16_WARPS + warp; row < rows; row += row_stride) {
     __syncwarp();
     if (lane < Cfg::PW) my_so[lane] = pre;
     if (TRAIN && bn_sums != nullptr) {
@@ -2263,11 +2282,11 @@ static int launch_conv_fwd(int C, dim3 grid, cudaStream_t st, const uint32_t* ob
     }
   }
   if (g_conv_mma == 1) {  // fp16 mma.sync conv (default); h16: h1 / h1lo are the fp16 (hi, lo') planes
-    const dim3 mg(conv_mma_ctas((int)grid.y, rows, 3), grid.y);
+    const dim3 mg(conv_mma_ctas((int)grid.y, rows, CONV16_CTAS_PER_SM), grid.y);
     LaunchScope _ls(TRAIN ? K_CONV_FWD : K_CONV_FWD_INFER, st);
 #define PQN_CONV16(CC)                                                                                              \
-  if (h16) conv_fwd_mma16_kernel<CC, TRAIN, true><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); \
-  else conv_fwd_mma16_kernel<CC, TRAIN, false><<<mg, CONV_MMA_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows)
+  if (h16) conv_fwd_mma16_kernel<CC, TRAIN, true><<<mg, CONV16_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows); \
+  else conv_fwd_mma16_kernel<CC, TRAIN, false><<<mg, CONV16_WARPS * 32, 0, st>>>(obs, orps, gather, params, P, L, h1, h1lo, xh1, rs1, rb, bn, rows)
     switch (C) {
       case 4: PQN_CONV16(4); break;
       case 6: PQN_CONV16(6); break;
@@ -2491,6 +2510,7 @@ static int tc_dgrad(const float* params, int64_t P, const pqn_net_layout_t& L, c
 }
 
 #include "pqn_norm.cuh"
+#include "pqn_rnn.cuh"
 
 static inline bool modular_net(const pqn_net_desc_t* d) { return d->norm_type != PQN_NORM_LAYER || d->norm_input != 0; }
 
@@ -2503,6 +2523,114 @@ extern "C" {
 int64_t pqn_net_stats_floats(const pqn_net_desc_t* d) {
   if (check_desc(d, "pqn_net_stats_floats")) return -1;
   return nrm::stats_floats(d);
+}
+
+int pqn_rnn_step(const pqn_net_desc_t* d, const float* params, float* hs, const float* obs, int64_t obs_rows_per_seed,
+                 const uint8_t* last_done, const int32_t* last_action, float* q, int32_t S, int32_t E, void* workspace,
+                 void* stream) {
+  int rc = check_desc(d, "pqn_rnn_step");
+  if (rc) return rc;
+  if ((rc = rnn::check_rnn(d, "pqn_rnn_step"))) return rc;
+  if (!params || !hs || !obs || !last_done || !last_action || !q || !workspace || S <= 0 || E <= 0 || S > 65535)
+    return set_error(PQN_E_INVALID, "pqn_rnn_step: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  pqn_net_layout_t L;
+  make_layout(d, &L);
+  rnn::RnnWs w;
+  rnn::carve_rnn(d, S, E, (char*)workspace, &w);
+  rnn::rnn_trunk(d, L, params, obs, obs_rows_per_seed * d->in_c, S, E, false, w, st);
+  if ((rc = rnn::rnn_scan_fwd<false>(d, L, params, last_action, last_done, hs, hs, S, 1, E, w, st))) return rc;
+  { LaunchScope _ls(K_RNN_MISC, st);
+    nrm::head_fwd_kernel<<<dim3(cdiv(E, 8), S), 256, 0, st>>>(w.y, E, d->hidden, params, L.total, L.head_w, L.head_b,
+                                                               d->num_actions, q); }
+  return check_launch("pqn_rnn_step");
+}
+
+int pqn_rnn_loss_grad(const pqn_net_desc_t* d, const float* params, const float* hs0, const float* obs,
+                      const uint8_t* last_done, const int32_t* last_action, const int32_t* action, const float* reward,
+                      const uint8_t* done, float* grads, float* loss_sum, float* qsa_sum, int32_t S, int32_t T, int32_t B,
+                      float gamma, float lambda, void* workspace, void* stream) {
+  int rc = check_desc(d, "pqn_rnn_loss_grad");
+  if (rc) return rc;
+  if ((rc = rnn::check_rnn(d, "pqn_rnn_loss_grad"))) return rc;
+  if (!params || !hs0 || !obs || !last_done || !last_action || !action || !reward || !done || !grads || !loss_sum ||
+      !qsa_sum || !workspace || S <= 0 || T < 2 || B <= 0 || B > 1024 || S > 65535)
+    return set_error(PQN_E_INVALID, "pqn_rnn_loss_grad: bad argument (T >= 2, B <= 1024)");
+  cudaStream_t st = (cudaStream_t)stream;
+  pqn_net_layout_t L;
+  make_layout(d, &L);
+  const int64_t P = L.total;
+  const int H = d->hidden, A = d->num_actions, D = d->in_c, rows = T * B;
+  rnn::RnnWs w;
+  rnn::carve_rnn(d, S, rows, (char*)workspace, &w);
+  if (cudaMemsetAsync(grads, 0, (size_t)S * P * sizeof(float), st) != cudaSuccess)
+    return check_launch("pqn_rnn_loss_grad(memset)");
+  const int64_t gs = (int64_t)S * rows * H;
+  // ---- forward over the window
+  rnn::rnn_trunk(d, L, params, obs, (int64_t)rows * D, S, rows, true, w, st);
+  if ((rc = rnn::rnn_scan_fwd<true>(d, L, params, last_action, last_done, hs0, w.dhl /*scratch carry out*/, S, T, B, w, st)))
+    return rc;
+  { LaunchScope _ls(K_RNN_MISC, st);
+    nrm::head_fwd_kernel<<<dim3(cdiv(rows, 8), S), 256, 0, st>>>(w.y, rows, H, params, P, L.head_w, L.head_b, A, w.q); }
+  // ---- targets, loss, dq
+  { LaunchScope _ls(K_RNN_MISC, st);
+    const int bt = ((B + 31) / 32) * 32;
+    rnn::rnn_targets_kernel<<<S, bt, 2 * bt * sizeof(float), st>>>(w.q, action, reward, done, T, B, A, gamma, lambda, w.dq,
+                                                                    loss_sum, qsa_sum); }
+  // ---- head backward
+  { LaunchScope _ls(K_RNN_MISC, st);
+    if (H == 128) rnn::rnn_head_bwd_kernel<128><<<dim3(nrm::RED_BLOCKS, S), 128, 0, st>>>(w.y, w.dq, rows, A, params, P, L.head_w, w.dy, w.part);
+    else rnn::rnn_head_bwd_kernel<256><<<dim3(nrm::RED_BLOCKS, S), 256, 0, st>>>(w.y, w.dq, rows, A, params, P, L.head_w, w.dy, w.part); }
+  { LaunchScope _ls(K_RNN_MISC, st);
+    rnn::rnn_head_bwd_final_kernel<<<S, 256, 0, st>>>(w.part, nrm::RED_BLOCKS, H, A, grads, P, L.head_w, L.head_b); }
+  // ---- BPTT through the GRU
+  const int64_t wts = (int64_t)S * H * H;
+  { LaunchScope _ls(K_RNN_MISC, st);
+    rnn::gru_transpose_kernel<<<dim3(32, S, 3), 256, 0, st>>>(params, P, L, H, w.wt, wts); }
+  { LaunchScope _ls(K_RNN_SCAN, st);
+    const dim3 grid(cdiv(B, rnn::RB), S);
+    if (H == 128) rnn::gru_scan_bwd_kernel<128><<<grid, 128, 0, st>>>(w.dy, last_done, w.h0, w.rg, w.zg, w.ng, w.hn, w.wt, wts, w.da, gs, w.dhn, T, B);
+    else rnn::gru_scan_bwd_kernel<256><<<grid, 256, 0, st>>>(w.dy, last_done, w.h0, w.rg, w.zg, w.ng, w.hn, w.wt, wts, w.da, gs, w.dhn, T, B); }
+  // ---- weight gradients of the GRU (batched over the window)
+  const float* xl = w.h[d->layers - 1];   // trunk output = first H columns of the GRU input
+  const int64_t iw[3] = {L.gru_ir_w, L.gru_iz_w, L.gru_in_w}, ib[3] = {L.gru_ir_b, L.gru_iz_b, L.gru_in_b};
+  const int64_t hw[3] = {L.gru_hr_w, L.gru_hz_w, L.gru_hn_w};
+  const int tiles = (H / 128) * (H / 128);
+  const int sp = wgrad_splits(tiles, S, rows);
+  nrm::NormWs nw = {};
+  nw.part = w.part;
+  for (int g = 0; g < 3; ++g) {
+    const float* da = w.da + g * gs;
+    { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(H / 128, H / 128, S * sp), GT, 0, st>>>(xl, (int64_t)rows * H, H, da, (int64_t)rows * H, H, grads, P, iw[g], rows, H, sp); }
+    nrm::colsum2(da, da, S, rows, H, H, nw, w.sums, grads, P, ib[g], -1, st);                         // d b_ig
+    const float* dh = g == 2 ? w.dhn : da;                                                             // hn uses d(hn)
+    { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(H / 128, H / 128, S * sp), GT, 0, st>>>(w.h0, (int64_t)rows * H, H, dh, (int64_t)rows * H, H, grads, P, hw[g], rows, H, sp); }
+    // d x_L (+)= da_g W_ig[:H]^T, masked by the trunk's ReLU
+    { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(da, (int64_t)rows * H, H, params, P, iw[g], xl, w.dx, (int64_t)rows * H, rows, H, g > 0 ? 1 : 0); }
+  }
+  nrm::colsum2(w.dhn, w.dhn, S, rows, H, H, nw, w.sums, grads, P, L.gru_hn_b, -1, st);                 // d b_hn
+  { LaunchScope _ls(K_RNN_MISC, st);
+    if (H == 128) rnn::rnn_onehot_grad_kernel<128><<<dim3(S, 3), 128, 0, st>>>(w.da, gs, last_action, rows, A, grads, P, L);
+    else rnn::rnn_onehot_grad_kernel<256><<<dim3(S, 3), 256, 0, st>>>(w.da, gs, last_action, rows, A, grads, P, L); }
+  // ---- trunk backward (LayerNorm backward -> weight gradient -> input gradient of the layer below)
+  const dim3 rbg(conv_mma_ctas(S, rows, 4), S);
+  const int64_t offw[2] = {L.d0_w, L.d1_w}, offb[2] = {L.d0_b, L.d1_b}, offg[2] = {L.ln0_scale, L.ln1_scale},
+                offbi[2] = {L.ln0_bias, L.ln1_bias};
+  float* dcur = w.dx;
+  for (int l = d->layers - 1; l >= 0; --l) {
+    if ((rc = run_row_bwd(H, false, rbg, A, st, nullptr, w.xh[l], w.rs[l], dcur, dcur, nullptr, nullptr, nullptr, 1.0f, params,
+                          grads, P, offg[l], offbi[l], offb[l], 0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, w.rbp,
+                          rows))) return rc;
+    const float* xprev = l == 0 ? obs : w.h[l - 1];
+    const int kin = l == 0 ? D : H;
+    const int spl = wgrad_splits((kin + 127) / 128 * (H / 128), S, rows);
+    { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(cdiv(kin, 128), H / 128, S * spl), GT, 0, st>>>(xprev, (int64_t)rows * kin, kin, dcur, (int64_t)rows * H, H, grads, P, offw[l], rows, kin, spl); }
+    if (l > 0) {
+      { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(dcur, (int64_t)rows * H, H, params, P, offw[l], w.h[l - 1], w.dhl, (int64_t)rows * H, rows, H, 0); }
+      dcur = w.dhl;
+    }
+  }
+  return check_launch("pqn_rnn_loss_grad");
 }
 
 int pqn_set_conv_mma_path(int on) {
@@ -2525,6 +2653,7 @@ int pqn_net_layout(const pqn_net_desc_t* d, pqn_net_layout_t* out) {
 
 int64_t pqn_net_workspace_bytes(const pqn_net_desc_t* d, int32_t S, int64_t rows) {
   if (check_desc(d, "pqn_net_workspace_bytes")) return -1;
+  if (d->kind == PQN_NET_RNN) return rnn::carve_rnn(d, S, rows, nullptr, nullptr);
   if (modular_net(d)) return nrm::carve_norm(d, S, rows, nullptr, nullptr);
   return carve(d, S, rows, nullptr, nullptr);
 }

@@ -137,8 +137,9 @@ def test_norm_variant_loss_grad_matches_fp64_oracle(kind, norm_type, norm_input)
         x = obs[s][gather[s]].astype(np.float64)
         loss, q_sa, g, new_stats = lg(p64, st64, x, act[s][gather[s]], tgt[s][gather[s]].astype(np.float64), norm_type,
                                       norm_input)
-        assert abs(float(ls[s]) - loss) < 1e-5 * max(1.0, abs(loss)), (float(ls[s]), loss)
-        assert abs(float(qs[s]) - q_sa.mean()) < 1e-5 * max(1.0, abs(q_sa.mean()))
+        # fp32 batch statistics (E[x^2] - E[x]^2 over 16k elements) against the fp64 oracle: a few 1e-5 on q
+        assert abs(float(ls[s]) - loss) < 5e-5 * max(1.0, abs(loss)), (float(ls[s]), loss)
+        assert abs(float(qs[s]) - q_sa.mean()) < 5e-5 * max(1.0, abs(q_sa.mean()))
         scale = max(np.abs(v).max() for v in g.values())
         for path, *_ in spec.entries:
             d = gtree
