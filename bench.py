@@ -216,8 +216,16 @@ def cpu_sample_text(workers, steps, dt):
             f"port (NumPy) -- the reference's JAX-CPU path is not installable here (no jax/gymnax wheels)")
 
 
-def headline_config(seeds_total, world, envs, with_eval=False):
+def headline_config(seeds_total, world, envs, with_eval=False, env_sharded=False):
     per = (seeds_total + world - 1) // world
+    if env_sharded and world > 1:
+        return {"workload": f"Breakout-MinAtar pqn_minatar NUM_ENVS={envs} x {seeds_total} seeds, envs sharded "
+                            f"{envs // world}/GPU (every rank trains every seed), TEST_DURING_TRAINING=False",
+                "num_steps": NUM_STEPS, "num_minibatches": 32, "num_epochs": 2,
+                "l2": "per-step working set exceeds the 126 MB L2" if seeds_total * envs >= 1 << 16 else
+                      "small run: the working set fits the L2; launch/latency bound",
+                "parallelism": f"env-sharded x{world}: one NCCL all-reduce (mean) of the flat [S][P] gradient per "
+                               f"minibatch step (64 per update), per-rank minibatch permutation"}
     return {"workload": f"Breakout-MinAtar pqn_minatar NUM_ENVS={envs} x {seeds_total} seeds "
                         f"(BASELINE configs[1]), seeds sharded {per}/GPU, TEST_DURING_TRAINING="
                         + ("True (greedy eval of 128 envs x 1000 steps every 3 updates inside the timed "
@@ -371,7 +379,7 @@ def env_step_roofline(dev, local_rank, peaks, names=("Breakout-MinAtar",)):
 # --------------------------------------------------------------------------- #
 # GPU arm
 # --------------------------------------------------------------------------- #
-def timed_train(module, cfg, rngs_host, warmup, dev, world, local_rank, profile=False):
+def timed_train(module, cfg, rngs_host, warmup, dev, world, local_rank, profile=False, shard=None):
     """One train() of warmup+K updates; updates warmup.. are bracketed by CUDA events on the launching stream
     (hook called on the host between updates).  Returns (ms, launches in the timed region, clocks, out, per-kernel
     spans or None)."""
@@ -387,6 +395,8 @@ def timed_train(module, cfg, rngs_host, warmup, dev, world, local_rank, profile=
 
     train = module.make_train(cfg)
     eng = train.engine
+    if shard is not None:
+        eng.env_shard = shard
     ev = {"start": torch.cuda.Event(enable_timing=True), "end": torch.cuda.Event(enable_timing=True)}
     sampler = ClockSampler(local_rank)
     state = {"launch0": 0, "replays0": 0}
@@ -420,7 +430,7 @@ def timed_train(module, cfg, rngs_host, warmup, dev, world, local_rank, profile=
     return float(t.item()), int(launches), clocks, out, prof, eng
 
 
-def e2e_train(module, cfg, rngs_host, dev, world):
+def e2e_train(module, cfg, rngs_host, dev, world, shard=None):
     import torch
     import torch.distributed as dist
     if world > 1:
@@ -428,6 +438,8 @@ def e2e_train(module, cfg, rngs_host, dev, world):
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     train2 = module.make_train(cfg)
+    if shard is not None:
+        train2.engine.env_shard = shard
     out2 = train2(rngs_host)                                   # H2D of the keys happens inside
     metrics_host = {k: v.cpu() for k, v in out2["metrics"].items()}
     params_host = out2["runner_state"][0].params_flat.cpu()
@@ -447,11 +459,18 @@ def run_gpu(args, rank, world, local_rank):
     from purejaxql_b200 import jaxrandom as jr, pqn_minatar
 
     seeds_total = args.seeds
-    per = (seeds_total + world - 1) // world
-    lo, hi = min(seeds_total, rank * per), min(seeds_total, (rank + 1) * per)
-    S = hi - lo
+    env_sharded = args.data_parallel == "envs" or (args.data_parallel == "auto" and seeds_total < world)
     all_rngs = jr.to_numpy_u32(jr.split(jr.PRNGKey(0, dev), seeds_total))      # same split as single_run
-    rngs_host = np.ascontiguousarray(all_rngs[lo:hi])
+    if env_sharded:      # every rank trains every seed on its shard of the envs; one gradient all-reduce per minibatch step
+        per, S = seeds_total, seeds_total
+        rngs_host = np.ascontiguousarray(all_rngs)
+        assert args.envs % world == 0
+    else:
+        per = (seeds_total + world - 1) // world
+        lo, hi = min(seeds_total, rank * per), min(seeds_total, (rank + 1) * per)
+        S = hi - lo
+        rngs_host = np.ascontiguousarray(all_rngs[lo:hi])
+    shard = (rank, world) if env_sharded and world > 1 else None
 
     # ---- (1) the timed region: W warm-up + K timed updates of ONE train(), no per-kernel profiling; the update is
     # replayed from a CUDA graph when the engine's "auto" rule applies (S*E*T <= 2^21, e.g. 16 seeds/GPU), exactly
@@ -459,13 +478,14 @@ def run_gpu(args, rank, world, local_rank):
     cfg = base_config(args.warmup + args.steps, num_envs=args.envs, test=args.with_eval)
     if args.with_eval:  # the reference's cadence at this config: a greedy evaluation every 3 updates (int(76 * 0.05))
         cfg["TEST_INTERVAL"] = 3.5 / (args.warmup + args.steps)
-    ms_max, launches, clocks, out, _, eng = timed_train(pqn_minatar, cfg, rngs_host, args.warmup, dev, world, local_rank)
+    ms_max, launches, clocks, out, _, eng = timed_train(pqn_minatar, cfg, rngs_host, args.warmup, dev, world, local_rank,
+                                                        shard=shard)
     graph_used = bool(eng.graph_captured)
     env_steps = seeds_total * args.steps * NUM_STEPS * args.envs
     value = env_steps / (ms_max / 1e3)
 
     # ---- (2) e2e through the public API from host buffers
-    e2e_s, h2d, d2h = e2e_train(pqn_minatar, base_config(args.steps, num_envs=args.envs), rngs_host, dev, world)
+    e2e_s, h2d, d2h = e2e_train(pqn_minatar, base_config(args.steps, num_envs=args.envs), rngs_host, dev, world, shard=shard)
     e2e_val = env_steps / e2e_s
 
     # ---- (3) per-kernel CUDA-event spans from a second, eager pass of the same updates (1 warm-up + 2 profiled):
@@ -473,7 +493,7 @@ def run_gpu(args, rank, world, local_rank):
     # that is why `value` comes from pass (1)
     pcfg = base_config(3, num_envs=args.envs)
     pcfg["CUDA_GRAPH"] = False
-    p_ms, _, _, _, prof, _ = timed_train(pqn_minatar, pcfg, rngs_host, 1, dev, world, local_rank, profile=True)
+    p_ms, _, _, _, prof, _ = timed_train(pqn_minatar, pcfg, rngs_host, 1, dev, world, local_rank, profile=True, shard=shard)
     if rank != 0:
         return
     peaks = load_peaks()
@@ -520,7 +540,7 @@ def run_gpu(args, rank, world, local_rank):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": headline_config(seeds_total, world, args.envs, args.with_eval),
+            "config": headline_config(seeds_total, world, args.envs, args.with_eval, env_sharded),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps,
@@ -627,6 +647,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-env-roofline", action="store_true")
     ap.add_argument("--config", default="headline", choices=["headline", "acrobot65536", "minatar5"])
+    ap.add_argument("--data-parallel", default="auto", choices=["auto", "seeds", "envs"],
+                    help="seeds: shard the independent seeds (no collective); envs: shard NUM_ENVS of every seed and "
+                         "all-reduce the gradient once per minibatch step; auto: envs when --seeds < #GPUs")
     ap.add_argument("--with-eval", action="store_true",
                     help="TEST_DURING_TRAINING=True with the reference's cadence (SURVEY 8(d): report both)")
     args = ap.parse_args()

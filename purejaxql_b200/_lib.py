@@ -31,7 +31,9 @@ NORM_TYPES = {"layer_norm": 0, "batch_norm": 1}          # any other string: no 
 class NetLayout(Structure):
     _fields_ = [(n, c_int64) for n in (
         "total", "bn_scale", "bn_bias", "conv_w", "conv_b", "ln0_scale", "ln0_bias", "d0_w", "d0_b",
-        "ln1_scale", "ln1_bias", "d1_w", "d1_b", "head_w", "head_b")]
+        "ln1_scale", "ln1_bias", "d1_w", "d1_b", "head_w", "head_b",
+        "gru_ir_w", "gru_ir_b", "gru_iz_w", "gru_iz_b", "gru_in_w", "gru_in_b", "gru_hr_w", "gru_hz_w", "gru_hn_w",
+        "gru_hn_b")]
 
 
 class PqnError(RuntimeError):
@@ -71,6 +73,11 @@ _SIGS = {
     "pqn_qnet_loss_grad": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                    c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64,
                                    c_void_p, c_void_p]),
+    "pqn_rnn_step": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                             c_int32, c_int32, c_void_p, c_void_p]),
+    "pqn_rnn_loss_grad": (c_int, [POINTER(NetDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float,
+                                  c_void_p, c_void_p]),
     "pqn_radam_clip_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                     c_int64, c_float, c_float, c_float, c_float, c_void_p]),
     "pqn_bn_stats_update": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_float, c_float, c_void_p]),

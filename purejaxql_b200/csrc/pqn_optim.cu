@@ -213,6 +213,11 @@ int pqn_net_init(const pqn_net_desc_t* d, const uint32_t* keys, float* params, i
       add(L.d1_w, (int64_t)H * H, tn(1.0, H));
       add(L.ln1_scale, H, -1.f);
     }
+    if (d->kind == PQN_NET_RNN) {   // GRUCell input denses: lecun_normal over fan_in = H + A; the orthogonal recurrent
+      add(L.gru_ir_w, (int64_t)(H + A) * H, tn(1.0, H + A));   // kernels are drawn on the host (networks.py)
+      add(L.gru_iz_w, (int64_t)(H + A) * H, tn(1.0, H + A));
+      add(L.gru_in_w, (int64_t)(H + A) * H, tn(1.0, H + A));
+    }
     add(L.head_w, (int64_t)H * A, tn(1.0, H));
   }
   { LaunchScope _ls(K_NET_INIT, st); net_init_kernel<<<dim3(64, S), 256, 0, st>>>(keys, params, L.total, tab); }

@@ -23,6 +23,7 @@ from . import _lib
 
 NET_CNN = 0
 NET_MLP = 1
+NET_RNN = 2     # RNNQNetwork (GRU) of pqn_rnn_gymnax.py:57-105
 
 
 class QNetworkSpec:
@@ -77,6 +78,16 @@ class QNetworkSpec:
                 e += [(("Dense_1", "kernel"), L.d1_w, (H, H), "lecun"),
                       (("Dense_1", "bias"), L.d1_b, (H,), "zeros")]
                 e += norm((), 1, L.ln1_scale, L.ln1_bias, H)
+            if self.kind == NET_RNN:
+                # flax.linen.GRUCell: input denses ir/iz/in (bias, lecun_normal), recurrent hr/hz (no bias) and hn
+                # (bias), orthogonal recurrent kernels
+                g = ("ScannedRNN_0", "GRUCell_0")
+                e += [(g + ("ir", "kernel"), L.gru_ir_w, (H + A, H), "lecun"), (g + ("ir", "bias"), L.gru_ir_b, (H,), "zeros"),
+                      (g + ("iz", "kernel"), L.gru_iz_w, (H + A, H), "lecun"), (g + ("iz", "bias"), L.gru_iz_b, (H,), "zeros"),
+                      (g + ("in", "kernel"), L.gru_in_w, (H + A, H), "lecun"), (g + ("in", "bias"), L.gru_in_b, (H,), "zeros"),
+                      (g + ("hr", "kernel"), L.gru_hr_w, (H, H), "orthogonal"),
+                      (g + ("hz", "kernel"), L.gru_hz_w, (H, H), "orthogonal"),
+                      (g + ("hn", "kernel"), L.gru_hn_w, (H, H), "orthogonal"), (g + ("hn", "bias"), L.gru_hn_b, (H,), "zeros")]
             e += [((f"Dense_{self.layers}", "kernel"), L.head_w, (H, A), "lecun"),
                   ((f"Dense_{self.layers}", "bias"), L.head_b, (A,), "zeros")]
         return e
@@ -162,6 +173,16 @@ class QNetworkSpec:
         flat = torch.empty((S, self.total), dtype=torch.float32, device=keys.device)
         _lib.check(_lib.lib().pqn_net_init(self.desc, _lib.p(keys.contiguous()), _lib.p(flat), S, _lib.stream_ptr()),
                    "pqn_net_init")
+        orth = [(off, shape) for _, off, shape, kind in self.entries if kind == "orthogonal"]
+        if orth:   # flax recurrent_kernel_init = orthogonal(): QR of a normal matrix, per seed, on the host (tiny)
+            ku = keys.detach().cpu().numpy().view(np.uint32)
+            for s in range(S):
+                gen = torch.Generator().manual_seed((int(ku[s, 0]) << 32 | int(ku[s, 1])) & (2 ** 63 - 1))
+                for off, shape in orth:
+                    m = torch.randn(shape, generator=gen, dtype=torch.float64)
+                    qm, rm = torch.linalg.qr(m)
+                    qm = qm * torch.sign(torch.diagonal(rm)).unsqueeze(0)
+                    flat[s, off:off + qm.numel()] = qm.reshape(-1).to(torch.float32).to(flat.device)
         return flat
 
     def init_host(self, keys_u32: np.ndarray, device="cuda") -> torch.Tensor:
