@@ -2123,6 +2123,7 @@ struct Workspace {
   float *rb_part, *cb_part;       // per-CTA partial vectors of the deterministic row_bwd / conv_bwd reductions
   // MLP
   float *xg, *h0, *xhat0, *rstd0, *hh1, *xhat1, *rstd1, *dzl, *dh0;
+  float *m16_h0, *m16_w, *m16_dz;   // fp16 (hi, lo') planes of h0 / Dense_1 kernel / dz1 for the tensor-core hidden layer
 };
 
 // upper bound of the CTAs (all seeds) of the wave-sized grids of conv_mma_ctas(): <= 6 waves of <= 4 CTAs/SM, + S
@@ -2166,6 +2167,9 @@ static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* bas
     ww->dh0 = take(R * H);
     ww->rb_part = take(part_ctas(S) * row_bwd_part_floats(H, d->num_actions));
     ww->cb_part = nullptr;
+    ww->m16_h0 = take(R * H);                       // 2 planes x 2 bytes = 4 bytes per element
+    ww->m16_w = take((int64_t)S * H * H);
+    ww->m16_dz = take(R * H);
   }
   return off;
 }
@@ -2453,6 +2457,60 @@ static int tc16_dgrad(const Workspace& w, const Planes16& pl, int S, int rows, b
   return tc::launch_gemm16(0, 0, have_bits ? tc::EPI_RELU_BITS : tc::EPI_RELU_MASK, t, gs, ep, st, K_TC_DGRAD);
 }
 
+// ---- generic fp16-split GEMMs on planes (hi at p, lo' at p + plane_elems), used by the MLP hidden layer --------------
+// out[S][rows][N] = A[S][rows][K] . B[S][K][N]          (A K-major, B MN-major; raw store, no bias)
+static int tc16_mm_store(const __half* a, int64_t a_plane, const __half* b, int64_t b_plane, float* out, int S, int rows, int K,
+                         int N, cudaStream_t st, int kid) {
+  CUtensorMap t[4];
+  int rc;
+  if ((rc = tc::make_tmap16(&t[0], a, K, rows, S, K, (uint64_t)rows * K, 128))) return rc;
+  if ((rc = tc::make_tmap16(&t[1], a + a_plane, K, rows, S, K, (uint64_t)rows * K, 128))) return rc;
+  if ((rc = tc::make_tmap16(&t[2], b, N, K, S, N, (uint64_t)K * N, 64))) return rc;
+  if ((rc = tc::make_tmap16(&t[3], b + b_plane, N, K, S, N, (uint64_t)K * N, 64))) return rc;
+  tc::GemmShape gs = {};
+  gs.S = S; gs.M = rows; gs.m_tiles = (rows + 127) / 128; gs.n_tiles = N / 128; gs.k_blocks = (K + tc::TC_BK16 - 1) / tc::TC_BK16;
+  gs.split3 = 1;
+  tc::EpiParams ep = {};
+  ep.out = out; ep.ld_out = N; ep.out_seed_stride = (int64_t)rows * N;
+  return tc::launch_gemm16(0, 1, tc::EPI_STORE, t, gs, ep, st, kid);
+}
+// dW[S(P)][M][N] = A[S][rows][M]^T . DZ[S][rows][N] * out_scale      (both operands MN-major, K = rows)
+static int tc16_mm_wgrad(const __half* a, int64_t a_plane, const __half* dz, int64_t dz_plane, float* out, int64_t out_seed_stride,
+                         int S, int rows, int M, int N, float out_scale, cudaStream_t st) {
+  CUtensorMap t[4];
+  int rc;
+  if ((rc = tc::make_tmap16(&t[0], a, M, rows, S, M, (uint64_t)rows * M, 64))) return rc;
+  if ((rc = tc::make_tmap16(&t[1], a + a_plane, M, rows, S, M, (uint64_t)rows * M, 64))) return rc;
+  if ((rc = tc::make_tmap16(&t[2], dz, N, rows, S, N, (uint64_t)rows * N, 64))) return rc;
+  if ((rc = tc::make_tmap16(&t[3], dz + dz_plane, N, rows, S, N, (uint64_t)rows * N, 64))) return rc;
+  tc::GemmShape gs = {};
+  gs.S = S; gs.M = M; gs.m_tiles = M / 128; gs.n_tiles = N / 128; gs.k_blocks = (rows + tc::TC_BK16 - 1) / tc::TC_BK16; gs.split3 = 1;
+  tc::EpiParams ep = {};
+  ep.out = out; ep.ld_out = N; ep.out_seed_stride = out_seed_stride; ep.out_scale = out_scale;
+  return tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD);
+}
+// out[S][rows][Kp] = (mask > 0) * (DZ[S][rows][N] . W[S][Kp][N]^T) * out_scale       (both K-major, K = N)
+static int tc16_mm_dgrad(const __half* dz, int64_t dz_plane, const __half* wgt, int64_t w_plane, const float* mask, float* out,
+                         int S, int rows, int N, int Kp, float out_scale, cudaStream_t st) {
+  CUtensorMap t[4];
+  int rc;
+  if ((rc = tc::make_tmap16(&t[0], dz, N, rows, S, N, (uint64_t)rows * N, 128))) return rc;
+  if ((rc = tc::make_tmap16(&t[1], dz + dz_plane, N, rows, S, N, (uint64_t)rows * N, 128))) return rc;
+  if ((rc = tc::make_tmap16(&t[2], wgt, N, Kp, S, N, (uint64_t)Kp * N, 128))) return rc;
+  if ((rc = tc::make_tmap16(&t[3], wgt + w_plane, N, Kp, S, N, (uint64_t)Kp * N, 128))) return rc;
+  tc::GemmShape gs = {};
+  gs.S = S; gs.M = rows; gs.m_tiles = (rows + 127) / 128; gs.n_tiles = Kp / 128; gs.k_blocks = (N + tc::TC_BK16 - 1) / tc::TC_BK16;
+  gs.split3 = 1;
+  tc::EpiParams ep = {};
+  ep.out = out; ep.mask = mask; ep.ld_out = Kp; ep.out_seed_stride = (int64_t)rows * Kp; ep.rows = rows; ep.out_scale = out_scale;
+  return tc::launch_gemm16(0, 0, tc::EPI_RELU_MASK, t, gs, ep, st, K_TC_DGRAD);
+}
+static void split16_rows(const float* src, int64_t src_seed_stride, int64_t n_per_seed, int S, __half* hi, __half* lo,
+                         cudaStream_t st) {
+  LaunchScope _ls(K_TC_SPLIT, st);
+  split16_strided_kernel<<<dim3(cdiv(n_per_seed / 4, 256), S), 256, 0, st>>>(src, src_seed_stride, hi, lo, n_per_seed);
+}
+
 // Z = H1 . W1 on the tcgen05 path with the LayerNorm/ReLU(/head) epilogue.  epi = EPI_LN_TRAIN or EPI_LN_HEAD.
 static int tc_dense_fwd(int epi, const float* params, int64_t P, const pqn_net_layout_t& L, const Workspace& w, int A,
                         float* q, int S, int rows, cudaStream_t st) {
@@ -2714,6 +2772,21 @@ int pqn_qnet_forward(const pqn_net_desc_t* d, const float* params, const float* 
     } else {
       launch_dense<0>(H, dim3(cdiv(rows, BM), S), st, x, xss, D, params, L.total, L.d0_w, L.d0_b, L.ln0_scale,
                       L.ln0_bias, 0, 0, A, w.h0, nullptr, nullptr, nullptr, (int)rows, D);
+      if (g_use_tc == 2) {
+        // hidden layer (K = N = H) on tcgen05: fp16-split planes of h0 and of the Dense_1 kernel, raw product, then
+        // bias + LayerNorm + ReLU and the Q head in row kernels
+        const int64_t R = (int64_t)S * rows;
+        __half* hp = reinterpret_cast<__half*>(w.m16_h0);
+        __half* wp = reinterpret_cast<__half*>(w.m16_w);
+        split16_rows(w.h0, 0, R * H, 1, hp, hp + R * H, st);
+        split16_rows(params + L.d1_w, L.total, (int64_t)H * H, S, wp, wp + (int64_t)S * H * H, st);
+        if ((rc = tc16_mm_store(hp, R * H, wp, (int64_t)S * H * H, w.hh1, S, (int)rows, H, H, st, K_TC_FWD_HEAD))) return rc;
+        { LaunchScope _ls(K_NORM_FWD, st);
+          if (H == 128) nrm::ln_fwd_kernel<128><<<dim3(cdiv(rows, 8), S), 256, 0, st>>>(w.hh1, rows, params, L.total, L.ln1_scale, L.ln1_bias, nullptr, nullptr, w.hh1, L.d1_b);
+          else nrm::ln_fwd_kernel<256><<<dim3(cdiv(rows, 8), S), 256, 0, st>>>(w.hh1, rows, params, L.total, L.ln1_scale, L.ln1_bias, nullptr, nullptr, w.hh1, L.d1_b); }
+        { LaunchScope _ls(K_NORM_FWD, st);
+          nrm::head_fwd_kernel<<<dim3(cdiv(rows, 8), S), 256, 0, st>>>(w.hh1, (int)rows, H, params, L.total, L.head_w, L.head_b, A, q); }
+      } else
       launch_dense<2>(H, dim3(cdiv(rows, BM), S), st, w.h0, rows * H, H, params, L.total, L.d1_w, L.d1_b, L.ln1_scale,
                       L.ln1_bias, L.head_w, L.head_b, A, nullptr, nullptr, nullptr, q, (int)rows, H);
     }
@@ -2815,7 +2888,29 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
     launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.xg, rows * D, D, params, P, L.d0_w, L.d0_b, L.ln0_scale,
                     L.ln0_bias, 0, 0, A, w.h0, w.xhat0, w.rstd0, nullptr, R, D);
     const dim3 rbg(conv_mma_ctas(S, R, 4), S);
-    if (d->layers == 2) {
+    if (d->layers == 2 && g_use_tc == 2) {
+      // hidden layer on tcgen05 (fp16-split planes): forward product, weight gradient and input gradient
+      const int64_t RR = (int64_t)S * rows;
+      __half* hp = reinterpret_cast<__half*>(w.m16_h0);
+      __half* wp = reinterpret_cast<__half*>(w.m16_w);
+      __half* zp = reinterpret_cast<__half*>(w.m16_dz);
+      const float gscale = grad_scale(rows);
+      split16_rows(w.h0, 0, RR * H, 1, hp, hp + RR * H, st);
+      split16_rows(params + L.d1_w, P, (int64_t)H * H, S, wp, wp + (int64_t)S * H * H, st);
+      if ((rc = tc16_mm_store(hp, RR * H, wp, (int64_t)S * H * H, w.hh1, S, R, H, H, st, K_TC_FWD))) return rc;
+      { LaunchScope _ls(K_NORM_FWD, st);
+        if (H == 128) nrm::ln_fwd_kernel<128><<<dim3(cdiv(rows, 8), S), 256, 0, st>>>(w.hh1, rows, params, P, L.ln1_scale, L.ln1_bias, w.xhat1, w.rstd1, w.hh1, L.d1_b);
+        else nrm::ln_fwd_kernel<256><<<dim3(cdiv(rows, 8), S), 256, 0, st>>>(w.hh1, rows, params, P, L.ln1_scale, L.ln1_bias, w.xhat1, w.rstd1, w.hh1, L.d1_b); }
+      if ((rc = run_row_bwd(H, true, rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, zp, zp + RR * H, gscale, params, grads, P, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w, L.head_b,
+                            gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, w.rb_part, R))) return rc;
+      if ((rc = tc16_mm_wgrad(hp, RR * H, zp, RR * H, grads + L.d1_w, P, S, R, H, H, 1.0f / gscale, st))) return rc;
+      if ((rc = tc16_mm_dgrad(zp, RR * H, wp, (int64_t)S * H * H, w.h0, w.dh0, S, R, H, H, 1.0f / gscale, st))) return rc;
+      if ((rc = run_row_bwd(H, false, rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0,
+                            nullptr, nullptr, nullptr, 0, nullptr, nullptr, w.rb_part, R))) return rc;
+      const int sp0 = wgrad_splits(H / 128, S, R);
+      { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dh0, rows * H, H, grads,
+                                                                        P, L.d0_w, R, D, sp0); }
+    } else if (d->layers == 2) {
       launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.h0, rows * H, H, params, P, L.d1_w, L.d1_b, L.ln1_scale,
                       L.ln1_bias, 0, 0, A, w.hh1, w.xhat1, w.rstd1, nullptr, R, H);
       if ((rc = run_row_bwd(H, true, rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w, L.head_b,

@@ -138,12 +138,15 @@ __global__ void norm_elem_fwd_kernel(const float* __restrict__ Z, int64_t n_per_
 // LayerNorm over groups of G consecutive values + ReLU: one warp per group for G >= 128 (lane-strided), one thread
 // per group for G == 16.  rstd[S][groups]
 template <int G>
-__global__ void ln_fwd_kernel(const float* __restrict__ Z, int64_t groups_per_seed, const float* __restrict__ params,
-                              int64_t P, int64_t off_g, int64_t off_b, float* __restrict__ XH, float* __restrict__ RS,
-                              float* __restrict__ H) {
+__global__ void ln_fwd_kernel(const float* Z, int64_t groups_per_seed, const float* __restrict__ params,
+                              int64_t P, int64_t off_g, int64_t off_b, float* XH, float* RS, float* H,
+                              int64_t off_zbias = -1) {
+  // off_zbias >= 0: Z is a raw product (tensor-core GEMM with a plain store epilogue), the dense bias is added here.
+  // H may alias Z (every thread reads its elements before it writes them).
   const int seed = blockIdx.y;
   const float* __restrict__ gam = params + (int64_t)seed * P + off_g;
   const float* __restrict__ bet = params + (int64_t)seed * P + off_b;
+  const float* __restrict__ zb = off_zbias >= 0 ? params + (int64_t)seed * P + off_zbias : nullptr;
   if constexpr (G == 16) {
     const int64_t grp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= groups_per_seed) return;
@@ -156,14 +159,14 @@ __global__ void ln_fwd_kernel(const float* __restrict__ Z, int64_t groups_per_se
     }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { s1 += z[j]; s2 = fmaf(z[j], z[j], s2); }
+    for (int j = 0; j < 16; ++j) { if (zb) z[j] += zb[j]; s1 += z[j]; s2 = fmaf(z[j], z[j], s2); }
     const float mean = s1 * (1.0f / 16), var = fmaxf(s2 * (1.0f / 16) - mean * mean, 0.f);
     const float rstd = 1.0f / sqrtf(var + LN_EPS);
-    RS[(int64_t)seed * groups_per_seed + grp] = rstd;
+    if (RS) RS[(int64_t)seed * groups_per_seed + grp] = rstd;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float xh = (z[j] - mean) * rstd;
-      XH[base + j] = xh;
+      if (XH) XH[base + j] = xh;
       H[base + j] = fmaxf(xh * gam[j] + bet[j], 0.f);
     }
   } else {
@@ -175,7 +178,7 @@ __global__ void ln_fwd_kernel(const float* __restrict__ Z, int64_t groups_per_se
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < G / 32; ++j) {
-      z[j] = Z[base + j * 32 + lane];
+      z[j] = Z[base + j * 32 + lane] + (zb ? zb[j * 32 + lane] : 0.f);
       s1 += z[j];
       s2 = fmaf(z[j], z[j], s2);
     }
@@ -186,12 +189,12 @@ __global__ void ln_fwd_kernel(const float* __restrict__ Z, int64_t groups_per_se
     }
     const float mean = s1 * (1.0f / G), var = fmaxf(s2 * (1.0f / G) - mean * mean, 0.f);
     const float rstd = 1.0f / sqrtf(var + LN_EPS);
-    if (lane == 0) RS[(int64_t)seed * groups_per_seed + grp] = rstd;
+    if (lane == 0 && RS) RS[(int64_t)seed * groups_per_seed + grp] = rstd;
 #pragma unroll
     for (int j = 0; j < G / 32; ++j) {
       const int c = j * 32 + lane;
       const float xh = (z[j] - mean) * rstd;
-      XH[base + c] = xh;
+      if (XH) XH[base + c] = xh;
       H[base + c] = fmaxf(xh * gam[c] + bet[c], 0.f);
     }
   }

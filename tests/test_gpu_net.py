@@ -104,8 +104,18 @@ def test_cnn_forward_other_channel_counts_and_gather(dense_path):
             assert np.abs(q[s] - ref).max() < 1e-5, (C, np.abs(q[s] - ref).max())
 
 
+@pytest.fixture(params=[2, 0], ids=["hidden_layer_tcgen05_f16split", "ffma"])
+def mlp_path(request):
+    """The MLP's hidden layer (Dense_1: K = N = HIDDEN_SIZE) runs on the tcgen05 fp16-split GEMMs by default (round 2);
+    path 0 keeps everything on the fp32 FFMA kernels."""
+    from purejaxql_b200 import _lib
+    _lib.lib().pqn_set_tensor_core_path(request.param)
+    yield request.param
+    _lib.lib().pqn_set_tensor_core_path(2)
+
+
 @pytest.mark.parametrize("D,H,layers,A", [(4, 256, 2, 2), (6, 256, 2, 3), (4, 128, 1, 2), (6, 128, 2, 3)])
-def test_mlp_forward_matches_oracle(D, H, layers, A):
+def test_mlp_forward_matches_oracle(D, H, layers, A, mlp_path):
     from purejaxql_b200 import _lib
     from purejaxql_b200.networks import NET_MLP, QNetworkSpec
     rng = np.random.default_rng(2)
@@ -173,7 +183,7 @@ def test_cnn_loss_grad_matches_oracle(rows, total, dense_path):
 
 
 @pytest.mark.parametrize("D,H,layers,A,rows", [(4, 256, 2, 2, 32), (6, 256, 2, 3, 515), (4, 128, 1, 2, 100), (6, 128, 2, 3, 256)])
-def test_mlp_loss_grad_matches_oracle(D, H, layers, A, rows):
+def test_mlp_loss_grad_matches_oracle(D, H, layers, A, rows, mlp_path):
     from purejaxql_b200.networks import NET_MLP, QNetworkSpec
     rng = np.random.default_rng(7)
     S, total = 2, 700
