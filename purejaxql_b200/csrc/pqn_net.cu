@@ -2884,7 +2884,14 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
     const int D = d->in_c, H = d->hidden;
     const int BM = (H == 128) ? 128 : 64;
     { LaunchScope _ls(K_GATHER_ROWS, st); gather_rows_kernel<<<dim3(cdiv(rows * D, 256), S), 256, 0, st>>>((const float*)obs, obs_rows_per_seed, gather, w.xg,
-                                                                    bn_sums, R, D); }
+                                                                    nullptr, R, D); }
+    if (bn_sums) {
+      // input BatchNorm statistics (sum x, sum x^2 per feature): deterministic two-stage column sums of the gathered
+      // rows (the per-element float atomics this replaces were 18 % of an Acrobot update at 65,536 envs)
+      nrm::NormWs nw = {};
+      nw.part = w.rb_part;
+      nrm::colsum2(w.xg, w.xg, S, R, D, D, nw, bn_sums, nullptr, 0, -1, -1, st);
+    }
     launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.xg, rows * D, D, params, P, L.d0_w, L.d0_b, L.ln0_scale,
                     L.ln0_bias, 0, 0, A, w.h0, w.xhat0, w.rstd0, nullptr, R, D);
     const dim3 rbg(conv_mma_ctas(S, R, 4), S);

@@ -1,0 +1,8 @@
+#!/bin/bash
+# round-2 GPU session H (2 GPUs): env-sharded mode against a single-rank run, seed-sharded and env-sharded bench lines
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv,noheader
+python -m pytest tests/test_gpu_multi.py -q -m gpu 2>&1 | tail -15 > gpurun_out/r2h_multi.log; tail -8 gpurun_out/r2h_multi.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2h_bench_2gpu.json 2> gpurun_out/r2h_bench_2gpu.err; tail -3 gpurun_out/r2h_bench_2gpu.err; cut -c1-400 gpurun_out/r2h_bench_2gpu.json
+python bench.py --gpus 1 --seeds 1 --steps 20 --warmup 5 --no-cpu --no-env-roofline > gpurun_out/r2h_bench_1seed_1gpu.json 2> gpurun_out/r2h_bench_1seed_1gpu.err; cut -c1-330 gpurun_out/r2h_bench_1seed_1gpu.json
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --seeds 1 --steps 20 --warmup 5 --no-env-roofline > gpurun_out/r2h_bench_1seed_2gpu_envsharded.json 2> gpurun_out/r2h_bench_1seed_2gpu.err; tail -3 gpurun_out/r2h_bench_1seed_2gpu.err; cut -c1-330 gpurun_out/r2h_bench_1seed_2gpu_envsharded.json
