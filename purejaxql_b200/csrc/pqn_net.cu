@@ -2121,10 +2121,33 @@ struct Workspace {
   float *cxhat, *crstd;           // conv LayerNorm xhat / rstd saved by the training forward (MMA conv path)
   uint32_t* relu_bits;            // packed (h1 > 0) mask, 1024 bits per row (MMA conv path -> tcgen05 dgrad epilogue)
   float *rb_part, *cb_part;       // per-CTA partial vectors of the deterministic row_bwd / conv_bwd reductions
+  float* wg_part;                 // split-K partial outputs of the tensor-core weight gradient (small S: few output tiles)
   // MLP
   float *xg, *h0, *xhat0, *rstd0, *hh1, *xhat1, *rstd1, *dzl, *dh0;
   float *m16_h0, *m16_w, *m16_dz;   // fp16 (hi, lo') planes of h0 / Dense_1 kernel / dz1 for the tensor-core hidden layer
 };
+
+// split-K of the tensor-core weight gradient: when S * m_tiles * n_tiles output tiles cannot fill the SMs (one seed of
+// the MLP has 4 tiles, of the CNN 8), the K = rows range is divided so that about 2 x 148 CTAs run; the partial tiles
+// (at most WGRAD_SPLIT_TILES of them) are added in split order by wgrad_split_reduce_kernel (deterministic)
+constexpr int64_t WGRAD_SPLIT_TILES = 2 * 148 + 64;
+static int wgrad_ksplit(int tiles_total, int k_blocks) {
+  if (tiles_total >= 148) return 1;
+  int ks = (2 * 148) / tiles_total;
+  if (ks > k_blocks / 8) ks = k_blocks / 8;          // keep >= 8 k-blocks per CTA
+  if (ks < 1) ks = 1;
+  while (ks > 1 && (int64_t)(ks - 1) * ((k_blocks + ks - 1) / ks) >= k_blocks) --ks;   // no empty split
+  return ks;
+}
+__global__ void wgrad_split_reduce_kernel(const float* __restrict__ part, int ksplit, int64_t split_stride, int64_t n_per_seed,
+                                          float* __restrict__ out, int64_t out_seed_stride) {
+  const int seed = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_per_seed) return;
+  float v = 0.f;
+  for (int k = 0; k < ksplit; ++k) v += part[(int64_t)k * split_stride + (int64_t)seed * n_per_seed + i];
+  out[(int64_t)seed * out_seed_stride + i] = v;
+}
 
 // upper bound of the CTAs (all seeds) of the wave-sized grids of conv_mma_ctas(): <= 6 waves of <= 4 CTAs/SM, + S
 static int64_t part_ctas(int S) { return 6 * 4 * (int64_t)device_sm_count() + 2 * (int64_t)S; }
@@ -2154,6 +2177,7 @@ static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* bas
     ww->relu_bits = reinterpret_cast<uint32_t*>(take(R * (FLAT_CNN / 32)));
     ww->rb_part = take(part_ctas(S) * row_bwd_part_floats(HID_CNN, d->num_actions));
     ww->cb_part = take(part_ctas(S) * (int64_t)(9 * d->in_c * CONV_O + 3 * CONV_O));
+    ww->wg_part = take(WGRAD_SPLIT_TILES * 128 * 128);
   } else {
     const int H = d->hidden;
     ww->xg = take(R * d->in_c);
@@ -2167,6 +2191,7 @@ static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* bas
     ww->dh0 = take(R * H);
     ww->rb_part = take(part_ctas(S) * row_bwd_part_floats(H, d->num_actions));
     ww->cb_part = nullptr;
+    ww->wg_part = take(WGRAD_SPLIT_TILES * 128 * 128);
     ww->m16_h0 = take(R * H);                       // 2 planes x 2 bytes = 4 bytes per element
     ww->m16_w = take((int64_t)S * H * H);
     ww->m16_dz = take(R * H);
@@ -2423,7 +2448,7 @@ static int tc16_dense_fwd(int epi, const float* params, int64_t P, const pqn_net
 }
 
 static int tc16_wgrad(float* grads, int64_t P, const pqn_net_layout_t& L, const Planes16& pl, int S, int rows,
-                      float gscale, cudaStream_t st) {
+                      float gscale, float* wg_part, cudaStream_t st) {
   CUtensorMap t[4];
   int rc;
   if ((rc = tc::make_tmap16(&t[0], pl.h1_hi, FLAT_CNN, rows, S, FLAT_CNN, (uint64_t)rows * FLAT_CNN, 64))) return rc;
@@ -2433,9 +2458,18 @@ static int tc16_wgrad(float* grads, int64_t P, const pqn_net_layout_t& L, const 
   tc::GemmShape gs = {};
   gs.S = S; gs.M = FLAT_CNN; gs.m_tiles = FLAT_CNN / 128; gs.n_tiles = 1;
   gs.k_blocks = (rows + tc::TC_BK16 - 1) / tc::TC_BK16; gs.split3 = 1;
+  gs.k_split = wgrad_ksplit(S * gs.m_tiles * gs.n_tiles, gs.k_blocks);
   tc::EpiParams ep = {};
-  ep.out = grads + L.d0_w; ep.ld_out = HID_CNN; ep.out_seed_stride = P; ep.out_scale = 1.0f / gscale;
-  return tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD);
+  ep.ld_out = HID_CNN; ep.out_scale = 1.0f / gscale;
+  const int64_t n = (int64_t)FLAT_CNN * HID_CNN;
+  if (gs.k_split > 1) { ep.out = wg_part; ep.out_seed_stride = n; ep.split_stride = (int64_t)S * n; }
+  else { ep.out = grads + L.d0_w; ep.out_seed_stride = P; }
+  if ((rc = tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD))) return rc;
+  if (gs.k_split > 1) {
+    LaunchScope _ls(K_TC_WGRAD, st);
+    wgrad_split_reduce_kernel<<<dim3(cdiv(n, 256), S), 256, 0, st>>>(wg_part, gs.k_split, (int64_t)S * n, n, grads + L.d0_w, P);
+  }
+  return 0;
 }
 
 // dY1 = relu_mask * (dZ2 . W1^T) into w.h1 (fp32; the fp16 path has no fp32 h1, so this is not in place unless the
@@ -2476,7 +2510,7 @@ static int tc16_mm_store(const __half* a, int64_t a_plane, const __half* b, int6
 }
 // dW[S(P)][M][N] = A[S][rows][M]^T . DZ[S][rows][N] * out_scale      (both operands MN-major, K = rows)
 static int tc16_mm_wgrad(const __half* a, int64_t a_plane, const __half* dz, int64_t dz_plane, float* out, int64_t out_seed_stride,
-                         int S, int rows, int M, int N, float out_scale, cudaStream_t st) {
+                         int S, int rows, int M, int N, float out_scale, float* wg_part, cudaStream_t st) {
   CUtensorMap t[4];
   int rc;
   if ((rc = tc::make_tmap16(&t[0], a, M, rows, S, M, (uint64_t)rows * M, 64))) return rc;
@@ -2485,9 +2519,18 @@ static int tc16_mm_wgrad(const __half* a, int64_t a_plane, const __half* dz, int
   if ((rc = tc::make_tmap16(&t[3], dz + dz_plane, N, rows, S, N, (uint64_t)rows * N, 64))) return rc;
   tc::GemmShape gs = {};
   gs.S = S; gs.M = M; gs.m_tiles = M / 128; gs.n_tiles = N / 128; gs.k_blocks = (rows + tc::TC_BK16 - 1) / tc::TC_BK16; gs.split3 = 1;
+  gs.k_split = wgrad_ksplit(S * gs.m_tiles * gs.n_tiles, gs.k_blocks);
   tc::EpiParams ep = {};
-  ep.out = out; ep.ld_out = N; ep.out_seed_stride = out_seed_stride; ep.out_scale = out_scale;
-  return tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD);
+  ep.ld_out = N; ep.out_scale = out_scale;
+  const int64_t n = (int64_t)M * N;
+  if (gs.k_split > 1) { ep.out = wg_part; ep.out_seed_stride = n; ep.split_stride = (int64_t)S * n; }
+  else { ep.out = out; ep.out_seed_stride = out_seed_stride; }
+  if ((rc = tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD))) return rc;
+  if (gs.k_split > 1) {
+    LaunchScope _ls(K_TC_WGRAD, st);
+    wgrad_split_reduce_kernel<<<dim3(cdiv(n, 256), S), 256, 0, st>>>(wg_part, gs.k_split, (int64_t)S * n, n, out, out_seed_stride);
+  }
+  return 0;
 }
 // out[S][rows][Kp] = (mask > 0) * (DZ[S][rows][N] . W[S][Kp][N]^T) * out_scale       (both K-major, K = N)
 static int tc16_mm_dgrad(const __half* dz, int64_t dz_plane, const __half* wgt, int64_t w_plane, const float* mask, float* out,
@@ -2848,7 +2891,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
                           L.ln1_bias, L.d0_b, L.head_w, L.head_b, gather, action, target, tr_rows_per_seed, loss_sum,
                           qsa_sum, w.rb_part, R))) return rc;
     if (f16) {
-      if ((rc = tc16_wgrad(grads, P, L, pl, S, R, gscale, st))) return rc;
+      if ((rc = tc16_wgrad(grads, P, L, pl, S, R, gscale, w.wg_part, st))) return rc;
       if ((rc = tc16_dgrad(w, pl, S, R, g_conv_mma == 1 || g_conv_mma == 3, gscale, st))) return rc;
     } else if (use_tc) {
       if ((rc = tc_wgrad(grads, P, L, w, S, R, st))) return rc;
@@ -2910,7 +2953,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
         else nrm::ln_fwd_kernel<256><<<dim3(cdiv(rows, 8), S), 256, 0, st>>>(w.hh1, rows, params, P, L.ln1_scale, L.ln1_bias, w.xhat1, w.rstd1, w.hh1, L.d1_b); }
       if ((rc = run_row_bwd(H, true, rbg, A, st, w.hh1, w.xhat1, w.rstd1, nullptr, w.dzl, nullptr, zp, zp + RR * H, gscale, params, grads, P, L.ln1_scale, L.ln1_bias, L.d1_b, L.head_w, L.head_b,
                             gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, w.rb_part, R))) return rc;
-      if ((rc = tc16_mm_wgrad(hp, RR * H, zp, RR * H, grads + L.d1_w, P, S, R, H, H, 1.0f / gscale, st))) return rc;
+      if ((rc = tc16_mm_wgrad(hp, RR * H, zp, RR * H, grads + L.d1_w, P, S, R, H, H, 1.0f / gscale, w.wg_part, st))) return rc;
       if ((rc = tc16_mm_dgrad(zp, RR * H, wp, (int64_t)S * H * H, w.h0, w.dh0, S, R, H, H, 1.0f / gscale, st))) return rc;
       if ((rc = run_row_bwd(H, false, rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0,
                             nullptr, nullptr, nullptr, 0, nullptr, nullptr, w.rb_part, R))) return rc;

@@ -53,16 +53,38 @@ __global__ void __launch_bounds__(256) colsum2_partial_kernel(const float* __res
       o[t] = v0; o[G + t] = v1;
     }
   } else {
-    // small odd G (MLP input features): thread t < G owns channel t, loops the rows of the chunk
-    if (t < G) {
-      for (int r = r0; r < r1; ++r)
-        for (int c = t; c < ncols; c += G) {
+    // small G that does not divide 256 (MLP input features, ncols == G <= 16): thread = row, G register accumulators,
+    // then a fixed-order tree per channel (warp shuffles, warps in order)
+    float acc0[16], acc1[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = 0.f;
+    for (int r = r0 + t; r < r1; r += 256) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < G) {
           const float x = a[(int64_t)r * ncols + c];
-          s += x;
-          ss = fmaf(x, bb[(int64_t)r * ncols + c], ss);
+          acc0[c] += x;
+          acc1[c] = fmaf(x, bb[(int64_t)r * ncols + c], acc1[c]);
         }
-      float* o = part + (((int64_t)seed * nb + b) * 2) * G;
-      o[t] = s; o[G + t] = ss;
+    }
+    float* o = part + (((int64_t)seed * nb + b) * 2) * G;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (c >= G) break;
+      float v0 = acc0[c], v1 = acc1[c];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, sft);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, sft);
+      }
+      __syncthreads();
+      if ((t & 31) == 0) { sh[0][t >> 5] = v0; sh[1][t >> 5] = v1; }
+      __syncthreads();
+      if (t == 0) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int w = 0; w < 8; ++w) { s0 += sh[0][w]; s1 += sh[1][w]; }
+        o[c] = s0; o[G + c] = s1;
+      }
     }
   }
 }

@@ -337,8 +337,21 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_per_seed = gs.m_tiles * gs.n_tiles;
+  // split-K: tile index -> (seed, m/n tile, k range).  k_split == 1 is the plain case.
+  const int ksplit = gs.k_split > 1 ? gs.k_split : 1;
+  const int kb_per = (gs.k_blocks + ksplit - 1) / ksplit;
+  const int tiles_per_seed = gs.m_tiles * gs.n_tiles * ksplit;
   const int num_tiles = tiles_per_seed * gs.S;
+  auto decode = [&](int tile, int& seed, int& m0, int& n0, int& kb0, int& kbn) {
+    seed = tile / tiles_per_seed;
+    const int rem = tile - seed * tiles_per_seed;
+    const int ks = rem % ksplit, mn = rem / ksplit;
+    m0 = (mn / gs.n_tiles) * 128; n0 = (mn % gs.n_tiles) * 128;
+    kb0 = ks * kb_per;
+    kbn = min(kb_per, gs.k_blocks - kb0);
+    if (kbn < 0) kbn = 0;
+    return ks;
+  };
 
   // F16: fp16 operand planes (hi, lo'), 64-element k-blocks, A_lo' always comes from memory (no converter warps)
   const bool a_lo_tma = gs.split3 && (F16 || !gs.a_lo_inline);
@@ -352,10 +365,9 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int seed = tile / tiles_per_seed;
-        const int rem = tile - seed * tiles_per_seed;
-        const int m0 = (rem / gs.n_tiles) * 128, n0 = (rem % gs.n_tiles) * 128;
-        for (int kb = 0; kb < gs.k_blocks; ++kb) {
+        int seed, m0, n0, kb0, kbn;
+        decode(tile, seed, m0, n0, kb0, kbn);
+        for (int kb = kb0; kb < kb0 + kbn; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
           mbar_expect_tx(&full[stage], gs.split3 ? (a_lo_tma ? TC_STAGE_BYTES : 3 * TC_TILE_BYTES) : TC_STAGE_BYTES / 2);
@@ -412,7 +424,9 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
           tcgen05_fence_after();
           const uint32_t d_acc = tmem_base + ab * 128;
           bool first = true;
-          for (int kb = 0; kb < gs.k_blocks; ++kb) {
+          int seed_, m0_, n0_, kb0_, kbn_;
+          decode(tile, seed_, m0_, n0_, kb0_, kbn_);
+          for (int kb = 0; kb < kbn_; ++kb) {
             mbar_wait(&full[stage], phase);
             if (a_lo_conv) mbar_wait(&lo_full[stage], phase);
             tcgen05_fence_after();
@@ -440,7 +454,9 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
           tcgen05_fence_after();
         }
         bool first_corr = true, first_main = true;
-        for (int kb = 0; kb < gs.k_blocks; ++kb) {
+        int seed_, m0_, n0_, kb0_, kbn_;
+        decode(tile, seed_, m0_, n0_, kb0_, kbn_);
+        for (int kb = 0; kb < kbn_; ++kb) {
           if (kb % TC_PROMOTE == 0) {
             mbar_wait(&main_empty[mb], mb_phase ^ 1u);
             tcgen05_fence_after();
@@ -467,7 +483,7 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
           }
           umma_commit(&empty[stage]);  // smem slot free once these MMAs retire
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
-          if ((kb + 1) % TC_PROMOTE == 0 || kb == gs.k_blocks - 1) {
+          if ((kb + 1) % TC_PROMOTE == 0 || kb == kbn_ - 1) {
             umma_commit(&main_full[mb]);  // main partial ready for promotion
             if (++mb == 2) { mb = 0; mb_phase ^= 1u; }
           }
@@ -487,7 +503,9 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < gs.k_blocks; ++kb) {
+        int seed_, m0_, n0_, kb0_, kbn_;
+        decode(tile, seed_, m0_, n0_, kb0_, kbn_);
+        for (int kb = 0; kb < kbn_; ++kb) {
           mbar_wait(&full[stage], phase);
           const float4* src = reinterpret_cast<const float4*>(smem_al + stage * TC_STAGE_BYTES + TC_A_HI);
           float4* dst = reinterpret_cast<float4*>(smem_al + stage * TC_STAGE_BYTES + TC_A_LO);
@@ -517,12 +535,11 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
     const int col_off = SPLIT ? (warp >= 6 ? 64 : 0) : 0;
     int mb = 0, cb = 0, ab = 0;
     uint32_t mb_phase = 0, cb_phase = 0, ab_phase = 0;
-    const int partials = (gs.k_blocks + TC_PROMOTE - 1) / TC_PROMOTE;
     const bool single_acc = !F16 && gs.split3 && gs.k_blocks <= TC_PROMOTE;  // see the MMA issuer
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int seed = tile / tiles_per_seed;
-      const int rem = tile - seed * tiles_per_seed;
-      const int m0 = (rem / gs.n_tiles) * 128, n0 = (rem % gs.n_tiles) * 128;
+      int seed, m0, n0, kb0, kbn;
+      const int ks = decode(tile, seed, m0, n0, kb0, kbn);
+      const int partials = (kbn + TC_PROMOTE - 1) / TC_PROMOTE;
       uint32_t mask_bits[4] = {0u, 0u, 0u, 0u};
       if constexpr (EPI == EPI_RELU_MASK) prefetch_mask_bits(ep, seed, m0 + quad * 32, n0, lane, gs.M, mask_bits);
       if constexpr (EPI == EPI_RELU_BITS) {
@@ -578,7 +595,8 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
       }
       if constexpr (SPLIT) {
         const int m_base = m0 + quad * 32;
-        float* out = ep.out + (int64_t)seed * ep.out_seed_stride + (int64_t)m_base * ep.ld_out + n0 + col_off;
+        float* out = ep.out + (int64_t)ks * ep.split_stride + (int64_t)seed * ep.out_seed_stride +
+                     (int64_t)m_base * ep.ld_out + n0 + col_off;
         float* stg = stage_all + (warp - 2) * 32 * 32;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {

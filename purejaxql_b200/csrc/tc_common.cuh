@@ -33,11 +33,14 @@ struct GemmShape {
   int M;         // rows of D that exist (rows >= M are not stored)
   int m_tiles, n_tiles, k_blocks;
   int split3;    // 1: split precision (3 tensor-core products per k-step), 0: single pass
+  int k_split;   // >1: the k-blocks of every output tile are divided over k_split CTAs; partial ks goes to
+                 // out + ks * EpiParams::split_stride (EPI_STORE only) and a reduce kernel adds them in order
   int a_lo_inline;  // split3 only: 1 = no A_lo tensor in memory; the converter warps derive A_lo = A - trunc_tf32(A)
                     // from the A tile TMA staged in shared memory (halves the HBM traffic of the A operand)
 };
 
 struct EpiParams {
+  int64_t split_stride;  // elements between the partial outputs of a split-K launch
   float out_scale;  // F16 kernels: result = (main + corr * 2^-11) * out_scale (undoes the operand pre-scaling); 0 => 1
   // EPI_STORE / EPI_RELU_MASK
   float* out;
