@@ -40,7 +40,8 @@ static const char* const kNames[K_COUNT] = {
     "env_reset", "env_step", "env_obs", "eps_greedy", "rollout_act_step", "rollout_keys", "qlambda", "rng",
     "conv_fwd", "dense_fwd", "row_bwd", "wgrad", "dgrad", "conv_bwd", "gather_rows", "sqnorm", "radam", "advance",
     "bn_update", "tc_gemm", "tc_split", "tc_dense_fwd", "tc_wgrad", "tc_dgrad", "net_init",
-    "conv_fwd_infer", "tc_dense_fwd_head", "norm_fwd", "norm_bwd", "norm_reduce", "rnn_scan", "rnn_misc"};
+    "conv_fwd_infer", "tc_dense_fwd_head", "norm_fwd", "norm_bwd", "norm_reduce", "rnn_scan", "rnn_misc",
+    "grad_finalize"};
 
 struct Span { int id; cudaEvent_t a, b; };
 static long long g_launches = 0;

@@ -2128,12 +2128,13 @@ struct Workspace {
 };
 
 // split-K of the tensor-core weight gradient: when S * m_tiles * n_tiles output tiles cannot fill the SMs (one seed of
-// the MLP has 4 tiles, of the CNN 8), the K = rows range is divided so that about 2 x 148 CTAs run; the partial tiles
+// the MLP has 4 tiles, of the CNN 8), the K = rows range is divided so that one CTA per SM runs; the partial tiles
 // (at most WGRAD_SPLIT_TILES of them) are added in split order by wgrad_split_reduce_kernel (deterministic)
 constexpr int64_t WGRAD_SPLIT_TILES = 2 * 148 + 64;
 static int wgrad_ksplit(int tiles_total, int k_blocks) {
-  if (tiles_total >= 148) return 1;
-  int ks = (2 * 148) / tiles_total;
+  const int sms = device_sm_count();                 // persistent kernel, one CTA per SM: one wave of split tiles
+  if (tiles_total >= sms) return 1;
+  int ks = sms / tiles_total;
   if (ks > k_blocks / 8) ks = k_blocks / 8;          // keep >= 8 k-blocks per CTA
   if (ks < 1) ks = 1;
   while (ks > 1 && (int64_t)(ks - 1) * ((k_blocks + ks - 1) / ks) >= k_blocks) --ks;   // no empty split
@@ -2246,7 +2247,7 @@ static void launch_row_bwd_final(const float* part, dim3 rbg, int N, int A, bool
                                  int64_t off_dscale, int64_t off_dbias, int64_t off_db, int64_t off_hw, int64_t off_hb,
                                  float* loss_sum, float* qsa_sum, cudaStream_t st) {
   const int stride = 3 * N + (head ? A * N + A + 2 : 0);
-  LaunchScope _ls(K_ROW_BWD, st);
+  LaunchScope _ls(K_GRAD_FINAL, st);
   row_bwd_final_kernel<<<dim3(cdiv(stride, 256), rbg.y), 256, 0, st>>>(part, (int)rbg.x, N, A, head ? 1 : 0, grads, P,
                                                                          off_dscale, off_dbias, off_db, off_hw, off_hb,
                                                                          loss_sum, qsa_sum);
@@ -2466,7 +2467,7 @@ static int tc16_wgrad(float* grads, int64_t P, const pqn_net_layout_t& L, const 
   else { ep.out = grads + L.d0_w; ep.out_seed_stride = P; }
   if ((rc = tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD))) return rc;
   if (gs.k_split > 1) {
-    LaunchScope _ls(K_TC_WGRAD, st);
+    LaunchScope _ls(K_GRAD_FINAL, st);
     wgrad_split_reduce_kernel<<<dim3(cdiv(n, 256), S), 256, 0, st>>>(wg_part, gs.k_split, (int64_t)S * n, n, grads + L.d0_w, P);
   }
   return 0;
@@ -2527,7 +2528,7 @@ static int tc16_mm_wgrad(const __half* a, int64_t a_plane, const __half* dz, int
   else { ep.out = out; ep.out_seed_stride = out_seed_stride; }
   if ((rc = tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD))) return rc;
   if (gs.k_split > 1) {
-    LaunchScope _ls(K_TC_WGRAD, st);
+    LaunchScope _ls(K_GRAD_FINAL, st);
     wgrad_split_reduce_kernel<<<dim3(cdiv(n, 256), S), 256, 0, st>>>(wg_part, gs.k_split, (int64_t)S * n, n, out, out_seed_stride);
   }
   return 0;

@@ -892,7 +892,7 @@ static int norm_loss_grad(const pqn_net_desc_t* d, const pqn_net_layout_t& L, co
   float* hl = cnn ? w.h2 : w.h[last];
   float* dl = cnn ? w.d2 : w.d[last];
   { LaunchScope _ls(K_ROW_BWD, st); head_bwd_kernel<<<dim3(RED_BLOCKS, S), 256, 0, st>>>(hl, w.q, rows, N, params, P, L.head_w, A, gather, action, target, trps, dl, w.part); }
-  { LaunchScope _ls(K_ROW_BWD, st); head_bwd_final_kernel<<<S, 256, 0, st>>>(w.part, RED_BLOCKS, N, A, grads, P, L.head_w, L.head_b, loss_sum, qsa_sum); }
+  { LaunchScope _ls(K_GRAD_FINAL, st); head_bwd_final_kernel<<<S, 256, 0, st>>>(w.part, RED_BLOCKS, N, A, grads, P, L.head_w, L.head_b, loss_sum, qsa_sum); }
   if (cnn) {
     if ((rc = norm_layer_bwd(norm, w.d2, w.xh2, w.rs2, S, rows, HID_CNN, HID_CNN, params, grads, P, L.ln1_scale, L.ln1_bias,
                              L.d0_b, w, w.mr[1], st))) return rc;

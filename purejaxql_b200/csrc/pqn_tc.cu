@@ -668,7 +668,7 @@ static int launch_t(const CUtensorMap* t, const GemmShape& gs, const EpiParams& 
   static_assert(SMEM <= 227 * 1024, "dynamic shared memory of the GEMM kernel exceeds the per-CTA limit");
   if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
     return check_launch("tc_gemm(cudaFuncSetAttribute)");
-  const int tiles = gs.m_tiles * gs.n_tiles * gs.S;
+  const int tiles = gs.m_tiles * gs.n_tiles * gs.S * (gs.k_split > 1 ? gs.k_split : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   {
     LaunchScope _ls(kid < 0 ? (int)K_TC_GEMM : kid, st);

