@@ -430,6 +430,9 @@ def timed_train(module, cfg, rngs_host, warmup, dev, world, local_rank, profile=
     return float(t.item()), int(launches), clocks, out, prof, eng
 
 
+E2E_PARTS = {}     # wall-clock split of the last e2e_train call (this rank)
+
+
 def e2e_train(module, cfg, rngs_host, dev, world, shard=None):
     import torch
     import torch.distributed as dist
@@ -440,11 +443,14 @@ def e2e_train(module, cfg, rngs_host, dev, world, shard=None):
     train2 = module.make_train(cfg)
     if shard is not None:
         train2.engine.env_shard = shard
-    out2 = train2(rngs_host)                                   # H2D of the keys happens inside
+    t1 = time.perf_counter()
+    out2 = train2(rngs_host)                                   # H2D of the keys happens inside; train() ends synchronised
+    t2 = time.perf_counter()
     metrics_host = {k: v.cpu() for k, v in out2["metrics"].items()}
     params_host = out2["runner_state"][0].params_flat.cpu()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    E2E_PARTS.update(make_train_s=round(t1 - t0, 4), train_s=round(t2 - t1, 4), d2h_s=round(t0 + e2e_s - t2, 4))
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -544,7 +550,8 @@ def run_gpu(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps,
-                    "what": "make_train(config)+train(host rngs): key upload, init, reset, K updates, D2H of metrics+params"},
+                    "what": "make_train(config)+train(host rngs): key upload, init, reset, K updates, D2H of metrics+params",
+                    "wall_split_rank0": dict(E2E_PARTS)},
             "gpu_launches": int(launches), "cuda_graph": graph_used,
             "roofline": roof, "env_step": env_roof, "rollout_engine": rollout_engine, "kernel_breakdown": breakdown,
             "other_rooflines": rooflines,

@@ -636,19 +636,38 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
   }
 }
 
-// Sums the per-CTA partial vectors of row_bwd_kernel in CTA order and writes the gradients (and adds the minibatch's
-// loss / mean q_sa to the running sums).  grid = (ceil(stride / 256), S)
+// Fixed-order column sum of `count` partial vectors (p[c * stride], c = 0..count-1) by a 256-thread block laid out as
+// 32 columns x 8 slices: slice s adds the partials c = s, s+8, ... in order, the eight slice sums are then added in
+// slice order.  Every thread of the block must call it; the result is valid in the threads of slice 0 (threadIdx.x < 32).
+__device__ __forceinline__ float ordered_partial_sum(const float* __restrict__ p, int count, int64_t stride, bool valid) {
+  __shared__ float slice_sum[8][32];
+  const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  float v = 0.f;
+  if (valid) {
+#pragma unroll 4
+    for (int c = sl; c < count; c += 8) v += p[(int64_t)c * stride];
+  }
+  slice_sum[sl][col] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (sl == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += slice_sum[k][col];
+  }
+  return r;
+}
+
+// Sums the per-CTA partial vectors of row_bwd_kernel in a fixed order and writes the gradients (and adds the
+// minibatch's loss / mean q_sa to the running sums).  grid = (ceil(stride / 32), S), block = 256
 __global__ void row_bwd_final_kernel(const float* __restrict__ part, int nctas, int N, int A, int head,
                                      float* __restrict__ grads, int64_t P, int64_t off_dscale, int64_t off_dbias,
                                      int64_t off_db, int64_t off_hw, int64_t off_hb, float* __restrict__ loss_sum,
                                      float* __restrict__ qsa_sum) {
   const int seed = blockIdx.y;
   const int stride = 3 * N + (head ? A * N + A + 2 : 0);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= stride) return;
-  const float* __restrict__ p = part + (int64_t)seed * nctas * stride + i;
-  float v = 0.f;
-  for (int c = 0; c < nctas; ++c) v += p[(int64_t)c * stride];
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const float v = ordered_partial_sum(part + (int64_t)seed * nctas * stride + i, nctas, stride, i < stride);
+  if (i >= stride || threadIdx.x >= 32) return;
   float* __restrict__ g = grads + (int64_t)seed * P;
   if (i < N) g[off_dscale + i] = v;
   else if (i < 2 * N) g[off_dbias + (i - N)] = v;
@@ -2143,16 +2162,95 @@ static int wgrad_ksplit(int tiles_total, int k_blocks) {
 __global__ void wgrad_split_reduce_kernel(const float* __restrict__ part, int ksplit, int64_t split_stride, int64_t n_per_seed,
                                           float* __restrict__ out, int64_t out_seed_stride) {
   const int seed = blockIdx.y;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_per_seed) return;
-  float v = 0.f;
-  for (int k = 0; k < ksplit; ++k) v += part[(int64_t)k * split_stride + (int64_t)seed * n_per_seed + i];
-  out[(int64_t)seed * out_seed_stride + i] = v;
+  const int64_t i = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const float v = ordered_partial_sum(part + (int64_t)seed * n_per_seed + i, ksplit, split_stride, i < n_per_seed);
+  if (i < n_per_seed && threadIdx.x < 32) out[(int64_t)seed * out_seed_stride + i] = v;
+}
+
+// Weight gradient of a layer with a *thin* input (the first MLP layer: Kin = observation features <= 8):
+// dW[k][n] = sum_rows X[row][k] * dZ[row][n].  A 128 x 128 register tile would spend 94 % of its FFMAs on padding, so
+// here every thread owns one output column n (256 / N row groups when N < 256) and Kin accumulators, streams its rows
+// of dZ coalesced and reads the X rows of the CTA's tile from shared memory (broadcast).  Per-CTA partials
+// part[chunk][seed][Kin][N] are then added in chunk order by wgrad_split_reduce_kernel: no float atomics.
+// grid = (chunks, S), block = 256
+constexpr int THIN_KMAX = 8, THIN_ROWS = 128;
+__global__ void __launch_bounds__(256) wgrad_thin_kernel(const float* __restrict__ X, int64_t x_seed_stride, int Kin,
+                                                         const float* __restrict__ DZ, int64_t dz_seed_stride, int N,
+                                                         float* __restrict__ part, int rows, int rows_per_chunk) {
+  __shared__ float xs[THIN_ROWS * THIN_KMAX];
+  __shared__ float red[256 * THIN_KMAX];
+  const int seed = blockIdx.y, S = gridDim.y;
+  const int groups = 256 / N, n = threadIdx.x % N, grp = threadIdx.x / N;     // N in {128, 256}
+  const float* __restrict__ Xs = X + (int64_t)seed * x_seed_stride;
+  const float* __restrict__ Zs = DZ + (int64_t)seed * dz_seed_stride;
+  const int r_begin = blockIdx.x * rows_per_chunk, r_end = min(rows, r_begin + rows_per_chunk);
+  float acc[THIN_KMAX];
+#pragma unroll
+  for (int k = 0; k < THIN_KMAX; ++k) acc[k] = 0.f;
+  for (int r0 = r_begin; r0 < r_end; r0 += THIN_ROWS) {
+    const int nr = min(THIN_ROWS, r_end - r0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr * Kin; i += 256) {
+      const int r = i / Kin, k = i - r * Kin;
+      xs[r * THIN_KMAX + k] = __ldg(Xs + (int64_t)(r0 + r) * Kin + k);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = grp; r < nr; r += groups) {
+      const float z = __ldg(Zs + (int64_t)(r0 + r) * N + n);
+#pragma unroll
+      for (int k = 0; k < THIN_KMAX; ++k)
+        if (k < Kin) acc[k] = fmaf(xs[r * THIN_KMAX + k], z, acc[k]);
+    }
+  }
+  float* __restrict__ out = part + ((int64_t)blockIdx.x * S + seed) * Kin * N;
+  if (groups == 1) {
+#pragma unroll
+    for (int k = 0; k < THIN_KMAX; ++k)
+      if (k < Kin) out[k * N + n] = acc[k];
+  } else {                              // two row groups: add them in group order
+#pragma unroll
+    for (int k = 0; k < THIN_KMAX; ++k) red[threadIdx.x * THIN_KMAX + k] = acc[k];
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+      for (int k = 0; k < THIN_KMAX; ++k)
+        if (k < Kin) out[k * N + n] = acc[k] + red[(threadIdx.x + N) * THIN_KMAX + k];
+    }
+  }
 }
 
 // upper bound of the CTAs (all seeds) of the wave-sized grids of conv_mma_ctas(): <= 6 waves of <= 4 CTAs/SM, + S
 static int64_t part_ctas(int S) { return 6 * 4 * (int64_t)device_sm_count() + 2 * (int64_t)S; }
 static int64_t row_bwd_part_floats(int N, int A);
+static int wgrad_splits(int tiles, int S, int rows);
+static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// first-layer weight gradient dW0[D][H] = X^T . dZ: the thin deterministic kernel when D <= 8 (every shipped classic-control
+// env), the register-tiled FFMA kernel otherwise.  `part` is the row_bwd partial buffer (free again at this point of
+// the stream; chunks * S * D * H floats are far below its size).
+static void run_wgrad_first(const float* X, const float* DZ, float* grads, int64_t P, int64_t off_w, int S, int rows,
+                            int D, int H, float* part, cudaStream_t st) {
+  if (D <= THIN_KMAX && (H == 128 || H == 256)) {
+    int chunks = (2 * device_sm_count()) / S;
+    const int max_chunks = (rows + THIN_ROWS - 1) / THIN_ROWS;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    int per = (rows + chunks - 1) / chunks;
+    per = (per + THIN_ROWS - 1) / THIN_ROWS * THIN_ROWS;
+    chunks = (rows + per - 1) / per;
+    const int64_t n = (int64_t)D * H;
+    { LaunchScope _ls(K_WGRAD, st);
+      wgrad_thin_kernel<<<dim3(chunks, S), 256, 0, st>>>(X, (int64_t)rows * D, D, DZ, (int64_t)rows * H, H, part, rows, per); }
+    { LaunchScope _ls(K_GRAD_FINAL, st);
+      wgrad_split_reduce_kernel<<<dim3(cdiv(n, 32), S), 256, 0, st>>>(part, chunks, (int64_t)S * n, n, grads + off_w, P); }
+    return;
+  }
+  const int sp0 = wgrad_splits(H / 128, S, rows);
+  LaunchScope _ls(K_WGRAD, st);
+  wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(X, (int64_t)rows * D, D, DZ, (int64_t)rows * H, H, grads, P, off_w,
+                                                                   rows, D, sp0);
+}
 
 static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* base, Workspace* w) {
   int64_t off = 0;
@@ -2210,7 +2308,6 @@ static void launch_dense(int BN, dim3 grid, cudaStream_t st, const float* X, int
     { LaunchScope _ls(K_DENSE_FWD, st); dense_fwd_kernel<256, MODE><<<grid, GT, 0, st>>>(X, xss, ldx, params, P, ow, ob, osc, obi, ohw, ohb, A, H, XH, RS, Q, rows, K); }
 }
 
-static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
 template <int C>
 static int launch_conv_bwd_mma(dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
@@ -2248,7 +2345,7 @@ static void launch_row_bwd_final(const float* part, dim3 rbg, int N, int A, bool
                                  float* loss_sum, float* qsa_sum, cudaStream_t st) {
   const int stride = 3 * N + (head ? A * N + A + 2 : 0);
   LaunchScope _ls(K_GRAD_FINAL, st);
-  row_bwd_final_kernel<<<dim3(cdiv(stride, 256), rbg.y), 256, 0, st>>>(part, (int)rbg.x, N, A, head ? 1 : 0, grads, P,
+  row_bwd_final_kernel<<<dim3(cdiv(stride, 32), rbg.y), 256, 0, st>>>(part, (int)rbg.x, N, A, head ? 1 : 0, grads, P,
                                                                          off_dscale, off_dbias, off_db, off_hw, off_hb,
                                                                          loss_sum, qsa_sum);
 }
@@ -2468,7 +2565,7 @@ static int tc16_wgrad(float* grads, int64_t P, const pqn_net_layout_t& L, const 
   if ((rc = tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD))) return rc;
   if (gs.k_split > 1) {
     LaunchScope _ls(K_GRAD_FINAL, st);
-    wgrad_split_reduce_kernel<<<dim3(cdiv(n, 256), S), 256, 0, st>>>(wg_part, gs.k_split, (int64_t)S * n, n, grads + L.d0_w, P);
+    wgrad_split_reduce_kernel<<<dim3(cdiv(n, 32), S), 256, 0, st>>>(wg_part, gs.k_split, (int64_t)S * n, n, grads + L.d0_w, P);
   }
   return 0;
 }
@@ -2529,7 +2626,7 @@ static int tc16_mm_wgrad(const __half* a, int64_t a_plane, const __half* dz, int
   if ((rc = tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD))) return rc;
   if (gs.k_split > 1) {
     LaunchScope _ls(K_GRAD_FINAL, st);
-    wgrad_split_reduce_kernel<<<dim3(cdiv(n, 256), S), 256, 0, st>>>(wg_part, gs.k_split, (int64_t)S * n, n, out, out_seed_stride);
+    wgrad_split_reduce_kernel<<<dim3(cdiv(n, 32), S), 256, 0, st>>>(wg_part, gs.k_split, (int64_t)S * n, n, out, out_seed_stride);
   }
   return 0;
 }
@@ -2958,9 +3055,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
       if ((rc = tc16_mm_dgrad(zp, RR * H, wp, (int64_t)S * H * H, w.h0, w.dh0, S, R, H, H, 1.0f / gscale, st))) return rc;
       if ((rc = run_row_bwd(H, false, rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0,
                             nullptr, nullptr, nullptr, 0, nullptr, nullptr, w.rb_part, R))) return rc;
-      const int sp0 = wgrad_splits(H / 128, S, R);
-      { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dh0, rows * H, H, grads,
-                                                                        P, L.d0_w, R, D, sp0); }
+      run_wgrad_first(w.xg, w.dh0, grads, P, L.d0_w, S, R, D, H, w.rb_part, st);
     } else if (d->layers == 2) {
       launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.h0, rows * H, H, params, P, L.d1_w, L.d1_b, L.ln1_scale,
                       L.ln1_bias, 0, 0, A, w.hh1, w.xhat1, w.rstd1, nullptr, R, H);
@@ -2974,15 +3069,11 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
                                                                      w.dh0, rows * H, R, H); }
       if ((rc = run_row_bwd(H, false, rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0,
                             nullptr, nullptr, nullptr, 0, nullptr, nullptr, w.rb_part, R))) return rc;
-      const int sp0 = wgrad_splits(H / 128, S, R);
-      { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dh0, rows * H, H, grads,
-                                                                        P, L.d0_w, R, D, sp0); }
+      run_wgrad_first(w.xg, w.dh0, grads, P, L.d0_w, S, R, D, H, w.rb_part, st);
     } else {
       if ((rc = run_row_bwd(H, true, rbg, A, st, w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w, L.head_b,
                             gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, w.rb_part, R))) return rc;
-      const int sp0 = wgrad_splits(H / 128, S, R);
-      { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(w.xg, rows * D, D, w.dzl, rows * H, H, grads,
-                                                                        P, L.d0_w, R, D, sp0); }
+      run_wgrad_first(w.xg, w.dzl, grads, P, L.d0_w, S, R, D, H, w.rb_part, st);
     }
   }
   return check_launch("pqn_qnet_loss_grad");
