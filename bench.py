@@ -49,6 +49,15 @@ TOTAL_SEEDS = 128
 NUM_ENVS = 4096
 NUM_STEPS = 32
 METRIC = "MinAtar-Breakout env steps/sec @4096 envs x128 seeds"
+
+
+def metric_name(args):
+    """BASELINE.json's metric; non-default --envs / --seeds runs say so in the name."""
+    if args.envs == NUM_ENVS and args.seeds == TOTAL_SEEDS:
+        return METRIC
+    return f"MinAtar-Breakout env steps/sec @{args.envs} envs x{args.seeds} seeds"
+
+
 UNIT = "env_steps/s"
 # algorithmic work per env-step (SURVEY.md section 8(d); restated in DESIGN.md)
 FLOPS_FWD_PER_SAMPLE = 2 * (64 * 36 * 16 + 1024 * 128 + 128 * 3)        # conv + dense + head MACs x2
@@ -240,7 +249,7 @@ def run_reference(args, rank, world):
         return
     steps, warm = max(1, args.steps), max(0, args.warmup)
     val, dt, workers = cpu_port_parallel(steps, warm)
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(args), "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
@@ -543,7 +552,7 @@ def run_gpu(args, rank, world, local_rank):
                           "what": "rollout phase only (env step + eps-greedy + Q-network forward + Q(lambda) targets): "
                                   "sum of the per-kernel CUDA-event spans of rank 0 in pass (3), x n_gpus"}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+    line = {"metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": headline_config(seeds_total, world, args.envs, args.with_eval, env_sharded),

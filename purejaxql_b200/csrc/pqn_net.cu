@@ -302,12 +302,12 @@ __global__ void __launch_bounds__(GT) dense_fwd_kernel(
 
 // ---------------------------------------------------------------------------
 // wgrad: dW[kin][n] (+)= sum_rows X[row][kin] * dZ[row][n]
-// grid = (ceil(Kin/128), N/128, S*splits); atomicAdd when splits > 1
+// grid = (ceil(Kin/128), N/128, S*splits); splits > 1 writes per-split partials (launch through run_wgrad_ffma)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(GT) wgrad_kernel(const float* __restrict__ X, int64_t x_seed_stride, int ldx,
                                                    const float* __restrict__ DZ, int64_t dz_seed_stride, int N,
                                                    float* __restrict__ grads, int64_t P, int64_t off_w, int rows,
-                                                   int Kin, int splits) {
+                                                   int Kin, int splits, float* __restrict__ part) {
   constexpr int BM = 128, BN = 128, TM = 8, TN = 8;
   __shared__ __align__(16) float As[2][BK * BM];
   __shared__ __align__(16) float Bs[2][BK * BN];
@@ -362,7 +362,10 @@ __global__ void __launch_bounds__(GT) wgrad_kernel(const float* __restrict__ X, 
     if (kt + 1 < nk) sstore((kt + 1) & 1);
     __syncthreads();
   }
-  float* __restrict__ dW = grads + (int64_t)seed * P + off_w;
+  // splits == 1: the gradient itself; otherwise this row range's partial [split][seed][Kin][N], added in split order by
+  // wgrad_split_reduce_kernel (no float atomics)
+  float* __restrict__ dW = splits == 1 ? grads + (int64_t)seed * P + off_w
+                                       : part + ((int64_t)split * (gridDim.z / splits) + seed) * Kin * N;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int kin = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
@@ -370,8 +373,7 @@ __global__ void __launch_bounds__(GT) wgrad_kernel(const float* __restrict__ X, 
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
-      if (splits == 1) dW[(int64_t)kin * N + n] = acc[i][j];
-      else atomicAdd(dW + (int64_t)kin * N + n, acc[i][j]);
+      dW[(int64_t)kin * N + n] = acc[i][j];
     }
   }
 }
@@ -2113,10 +2115,9 @@ static int launch_conv_fwd_tc_t(int S, cudaStream_t st, const uint32_t* obs, int
   return 0;
 }
 
-// MLP input gather (minibatch rows of float obs) + dummy BatchNorm sums.
+// MLP input gather (minibatch rows of float obs); the input BatchNorm sums come from nrm::colsum2 of the result.
 __global__ void gather_rows_kernel(const float* __restrict__ obs, int64_t obs_rows_per_seed,
-                                   const int32_t* __restrict__ gather, float* __restrict__ out,
-                                   float* __restrict__ bn_sums, int rows, int D) {
+                                   const int32_t* __restrict__ gather, float* __restrict__ out, int rows, int D) {
   const int seed = blockIdx.y;
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (int64_t)rows * D) return;
@@ -2124,10 +2125,6 @@ __global__ void gather_rows_kernel(const float* __restrict__ obs, int64_t obs_ro
   const int64_t src = gather ? gather[(int64_t)seed * rows + r] : r;
   const float v = __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * D + j);
   out[((int64_t)seed * rows + r) * D + j] = v;
-  if (bn_sums) {
-    atomicAdd(bn_sums + (int64_t)seed * 2 * D + j, v);
-    atomicAdd(bn_sums + (int64_t)seed * 2 * D + D + j, v * v);
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -2149,7 +2146,7 @@ struct Workspace {
 // split-K of the tensor-core weight gradient: when S * m_tiles * n_tiles output tiles cannot fill the SMs (one seed of
 // the MLP has 4 tiles, of the CNN 8), the K = rows range is divided so that one CTA per SM runs; the partial tiles
 // (at most WGRAD_SPLIT_TILES of them) are added in split order by wgrad_split_reduce_kernel (deterministic)
-constexpr int64_t WGRAD_SPLIT_TILES = 2 * 148 + 64;
+constexpr int64_t WGRAD_SPLIT_TILES = 4 * 148 + 16;   // tensor-core split-K: <= SMs; FFMA row splits: tiles * S * splits < 4 * 148
 static int wgrad_ksplit(int tiles_total, int k_blocks) {
   const int sms = device_sm_count();                 // persistent kernel, one CTA per SM: one wave of split tiles
   if (tiles_total >= sms) return 1;
@@ -2167,10 +2164,25 @@ __global__ void wgrad_split_reduce_kernel(const float* __restrict__ part, int ks
   if (i < n_per_seed && threadIdx.x < 32) out[(int64_t)seed * out_seed_stride + i] = v;
 }
 
+// The register-tiled FFMA weight gradient + (splits > 1) its ordered reduction.  `part` needs splits * S * Kin * N floats
+// (<= WGRAD_SPLIT_TILES tiles of 128 x 128: wgrad_splits keeps tiles * S * splits below 4 * 148).
+static void run_wgrad_ffma(const float* X, int64_t x_seed_stride, int ldx, const float* DZ, int64_t dz_seed_stride, int N,
+                           float* grads, int64_t P, int64_t off_w, int rows, int Kin, int S, int splits, float* part,
+                           cudaStream_t st) {
+  { LaunchScope _ls(K_WGRAD, st);
+    wgrad_kernel<<<dim3((unsigned)((Kin + 127) / 128), (unsigned)(N / 128), (unsigned)(S * splits)), GT, 0, st>>>(
+        X, x_seed_stride, ldx, DZ, dz_seed_stride, N, grads, P, off_w, rows, Kin, splits, part); }
+  if (splits > 1) {
+    const int64_t n = (int64_t)Kin * N;
+    LaunchScope _ls(K_GRAD_FINAL, st);
+    wgrad_split_reduce_kernel<<<dim3((unsigned)((n + 31) / 32), S), 256, 0, st>>>(part, splits, (int64_t)S * n, n, grads + off_w, P);
+  }
+}
+
 // Weight gradient of a layer with a *thin* input (the first MLP layer: Kin = observation features <= 8):
 // dW[k][n] = sum_rows X[row][k] * dZ[row][n].  A 128 x 128 register tile would spend 94 % of its FFMAs on padding, so
-// here every thread owns one output column n (256 / N row groups when N < 256) and Kin accumulators, streams its rows
-// of dZ coalesced and reads the X rows of the CTA's tile from shared memory (broadcast).  Per-CTA partials
+// here every thread owns four output columns (256 / (N/4) row groups) and Kin float4 accumulators, streams its rows
+// of dZ coalesced (16-byte loads) and reads the X rows of the CTA's tile from shared memory (broadcast).  Per-CTA partials
 // part[chunk][seed][Kin][N] are then added in chunk order by wgrad_split_reduce_kernel: no float atomics.
 // grid = (chunks, S), block = 256
 constexpr int THIN_KMAX = 8, THIN_ROWS = 128;
@@ -2178,15 +2190,16 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(const float* __restrict
                                                          const float* __restrict__ DZ, int64_t dz_seed_stride, int N,
                                                          float* __restrict__ part, int rows, int rows_per_chunk) {
   __shared__ float xs[THIN_ROWS * THIN_KMAX];
-  __shared__ float red[256 * THIN_KMAX];
+  __shared__ float4 red[256];
   const int seed = blockIdx.y, S = gridDim.y;
-  const int groups = 256 / N, n = threadIdx.x % N, grp = threadIdx.x / N;     // N in {128, 256}
+  const int cols4 = N >> 2;                                             // threads per row (float4 columns); N in {128, 256}
+  const int groups = 256 / cols4, c4 = threadIdx.x % cols4, grp = threadIdx.x / cols4;
   const float* __restrict__ Xs = X + (int64_t)seed * x_seed_stride;
-  const float* __restrict__ Zs = DZ + (int64_t)seed * dz_seed_stride;
+  const float4* __restrict__ Zs = reinterpret_cast<const float4*>(DZ + (int64_t)seed * dz_seed_stride);
   const int r_begin = blockIdx.x * rows_per_chunk, r_end = min(rows, r_begin + rows_per_chunk);
-  float acc[THIN_KMAX];
+  float4 acc[THIN_KMAX];
 #pragma unroll
-  for (int k = 0; k < THIN_KMAX; ++k) acc[k] = 0.f;
+  for (int k = 0; k < THIN_KMAX; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r0 = r_begin; r0 < r_end; r0 += THIN_ROWS) {
     const int nr = min(THIN_ROWS, r_end - r0);
     __syncthreads();
@@ -2197,25 +2210,31 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(const float* __restrict
     __syncthreads();
 #pragma unroll 4
     for (int r = grp; r < nr; r += groups) {
-      const float z = __ldg(Zs + (int64_t)(r0 + r) * N + n);
+      const float4 z = __ldg(Zs + (int64_t)(r0 + r) * cols4 + c4);
 #pragma unroll
       for (int k = 0; k < THIN_KMAX; ++k)
-        if (k < Kin) acc[k] = fmaf(xs[r * THIN_KMAX + k], z, acc[k]);
+        if (k < Kin) {
+          const float x = xs[r * THIN_KMAX + k];
+          acc[k].x = fmaf(x, z.x, acc[k].x); acc[k].y = fmaf(x, z.y, acc[k].y);
+          acc[k].z = fmaf(x, z.z, acc[k].z); acc[k].w = fmaf(x, z.w, acc[k].w);
+        }
     }
   }
-  float* __restrict__ out = part + ((int64_t)blockIdx.x * S + seed) * Kin * N;
-  if (groups == 1) {
+  // add the row groups in group order (one k at a time through shared memory), then store this CTA's partial
+  float4* __restrict__ out = reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * S + seed) * Kin * N);
 #pragma unroll
-    for (int k = 0; k < THIN_KMAX; ++k)
-      if (k < Kin) out[k * N + n] = acc[k];
-  } else {                              // two row groups: add them in group order
-#pragma unroll
-    for (int k = 0; k < THIN_KMAX; ++k) red[threadIdx.x * THIN_KMAX + k] = acc[k];
+  for (int k = 0; k < THIN_KMAX; ++k) {
+    if (k >= Kin) break;
+    __syncthreads();
+    red[threadIdx.x] = acc[k];
     __syncthreads();
     if (grp == 0) {
-#pragma unroll
-      for (int k = 0; k < THIN_KMAX; ++k)
-        if (k < Kin) out[k * N + n] = acc[k] + red[(threadIdx.x + N) * THIN_KMAX + k];
+      float4 v = red[c4];
+      for (int g = 1; g < groups; ++g) {
+        const float4 o = red[g * cols4 + c4];
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      out[k * cols4 + c4] = v;
     }
   }
 }
@@ -2230,7 +2249,7 @@ static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1
 // env), the register-tiled FFMA kernel otherwise.  `part` is the row_bwd partial buffer (free again at this point of
 // the stream; chunks * S * D * H floats are far below its size).
 static void run_wgrad_first(const float* X, const float* DZ, float* grads, int64_t P, int64_t off_w, int S, int rows,
-                            int D, int H, float* part, cudaStream_t st) {
+                            int D, int H, float* part, float* wg_part, cudaStream_t st) {
   if (D <= THIN_KMAX && (H == 128 || H == 256)) {
     int chunks = (2 * device_sm_count()) / S;
     const int max_chunks = (rows + THIN_ROWS - 1) / THIN_ROWS;
@@ -2246,10 +2265,8 @@ static void run_wgrad_first(const float* X, const float* DZ, float* grads, int64
       wgrad_split_reduce_kernel<<<dim3(cdiv(n, 32), S), 256, 0, st>>>(part, chunks, (int64_t)S * n, n, grads + off_w, P); }
     return;
   }
-  const int sp0 = wgrad_splits(H / 128, S, rows);
-  LaunchScope _ls(K_WGRAD, st);
-  wgrad_kernel<<<dim3(cdiv(D, 128), H / 128, S * sp0), GT, 0, st>>>(X, (int64_t)rows * D, D, DZ, (int64_t)rows * H, H, grads, P, off_w,
-                                                                   rows, D, sp0);
+  run_wgrad_ffma(X, (int64_t)rows * D, D, DZ, (int64_t)rows * H, H, grads, P, off_w, rows, D, S,
+                 wgrad_splits((D + 127) / 128 * (H / 128), S, rows), wg_part, st);
 }
 
 static int64_t carve(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* base, Workspace* w) {
@@ -2800,10 +2817,10 @@ int pqn_rnn_loss_grad(const pqn_net_desc_t* d, const float* params, const float*
   nw.part = w.part;
   for (int g = 0; g < 3; ++g) {
     const float* da = w.da + g * gs;
-    { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(H / 128, H / 128, S * sp), GT, 0, st>>>(xl, (int64_t)rows * H, H, da, (int64_t)rows * H, H, grads, P, iw[g], rows, H, sp); }
+    run_wgrad_ffma(xl, (int64_t)rows * H, H, da, (int64_t)rows * H, H, grads, P, iw[g], rows, H, S, sp, w.wgp, st);
     nrm::colsum2(da, da, S, rows, H, H, nw, w.sums, grads, P, ib[g], -1, st);                         // d b_ig
     const float* dh = g == 2 ? w.dhn : da;                                                             // hn uses d(hn)
-    { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(H / 128, H / 128, S * sp), GT, 0, st>>>(w.h0, (int64_t)rows * H, H, dh, (int64_t)rows * H, H, grads, P, hw[g], rows, H, sp); }
+    run_wgrad_ffma(w.h0, (int64_t)rows * H, H, dh, (int64_t)rows * H, H, grads, P, hw[g], rows, H, S, sp, w.wgp, st);
     // d x_L (+)= da_g W_ig[:H]^T, masked by the trunk's ReLU
     { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(da, (int64_t)rows * H, H, params, P, iw[g], xl, w.dx, (int64_t)rows * H, rows, H, g > 0 ? 1 : 0); }
   }
@@ -2823,7 +2840,7 @@ int pqn_rnn_loss_grad(const pqn_net_desc_t* d, const float* params, const float*
     const float* xprev = l == 0 ? obs : w.h[l - 1];
     const int kin = l == 0 ? D : H;
     const int spl = wgrad_splits((kin + 127) / 128 * (H / 128), S, rows);
-    { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(cdiv(kin, 128), H / 128, S * spl), GT, 0, st>>>(xprev, (int64_t)rows * kin, kin, dcur, (int64_t)rows * H, H, grads, P, offw[l], rows, kin, spl); }
+    run_wgrad_ffma(xprev, (int64_t)rows * kin, kin, dcur, (int64_t)rows * H, H, grads, P, offw[l], rows, kin, S, spl, w.wgp, st);
     if (l > 0) {
       { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(dcur, (int64_t)rows * H, H, params, P, offw[l], w.h[l - 1], w.dhl, (int64_t)rows * H, rows, H, 0); }
       dcur = w.dhl;
@@ -2901,7 +2918,7 @@ int pqn_qnet_forward(const pqn_net_desc_t* d, const float* params, const float* 
     const float* x = (const float*)obs;
     int64_t xss = obs_rows_per_seed * D;
     if (gather) {
-      { LaunchScope _ls(K_GATHER_ROWS, st); gather_rows_kernel<<<dim3(cdiv(rows * D, 256), S), 256, 0, st>>>(x, obs_rows_per_seed, gather, w.xg, nullptr,
+      { LaunchScope _ls(K_GATHER_ROWS, st); gather_rows_kernel<<<dim3(cdiv(rows * D, 256), S), 256, 0, st>>>(x, obs_rows_per_seed, gather, w.xg,
                                                                       (int)rows, D); }
       x = w.xg;
       xss = rows * D;
@@ -2996,9 +3013,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
       if ((rc = tc_dgrad(params, P, L, w, S, R, g_conv_mma == 1 || g_conv_mma == 3, st))) return rc;
     } else {
       const int splits = wgrad_splits(FLAT_CNN / 128, S, R);
-      { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(FLAT_CNN / 128, 1, S * splits), GT, 0, st>>>(w.h1, rows * FLAT_CNN, FLAT_CNN, w.dz2,
-                                                                       rows * HID_CNN, HID_CNN, grads, P, L.d0_w, R,
-                                                                       FLAT_CNN, splits); }
+      run_wgrad_ffma(w.h1, rows * FLAT_CNN, FLAT_CNN, w.dz2, rows * HID_CNN, HID_CNN, grads, P, L.d0_w, R, FLAT_CNN, S, splits, w.wg_part, st);
       { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), FLAT_CNN / 128, S), GT, 0, st>>>(w.dz2, rows * HID_CNN, HID_CNN, params, P,
                                                                             L.d0_w, w.h1, w.h1, rows * FLAT_CNN, R,
                                                                             FLAT_CNN); }
@@ -3024,8 +3039,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
   } else {
     const int D = d->in_c, H = d->hidden;
     const int BM = (H == 128) ? 128 : 64;
-    { LaunchScope _ls(K_GATHER_ROWS, st); gather_rows_kernel<<<dim3(cdiv(rows * D, 256), S), 256, 0, st>>>((const float*)obs, obs_rows_per_seed, gather, w.xg,
-                                                                    nullptr, R, D); }
+    { LaunchScope _ls(K_GATHER_ROWS, st); gather_rows_kernel<<<dim3(cdiv(rows * D, 256), S), 256, 0, st>>>((const float*)obs, obs_rows_per_seed, gather, w.xg, R, D); }
     if (bn_sums) {
       // input BatchNorm statistics (sum x, sum x^2 per feature): deterministic two-stage column sums of the gathered
       // rows (the per-element float atomics this replaces were 18 % of an Acrobot update at 65,536 envs)
@@ -3055,7 +3069,7 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
       if ((rc = tc16_mm_dgrad(zp, RR * H, wp, (int64_t)S * H * H, w.h0, w.dh0, S, R, H, H, 1.0f / gscale, st))) return rc;
       if ((rc = run_row_bwd(H, false, rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0,
                             nullptr, nullptr, nullptr, 0, nullptr, nullptr, w.rb_part, R))) return rc;
-      run_wgrad_first(w.xg, w.dh0, grads, P, L.d0_w, S, R, D, H, w.rb_part, st);
+      run_wgrad_first(w.xg, w.dh0, grads, P, L.d0_w, S, R, D, H, w.rb_part, w.wg_part, st);
     } else if (d->layers == 2) {
       launch_dense<1>(H, dim3(cdiv(rows, BM), S), st, w.h0, rows * H, H, params, P, L.d1_w, L.d1_b, L.ln1_scale,
                       L.ln1_bias, 0, 0, A, w.hh1, w.xhat1, w.rstd1, nullptr, R, H);
@@ -3063,17 +3077,16 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
                             gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, w.rb_part, R))) return rc;
       const int tiles = (H / 128) * (H / 128);
       const int splits = wgrad_splits(tiles, S, R);
-      { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(H / 128, H / 128, S * splits), GT, 0, st>>>(w.h0, rows * H, H, w.dzl, rows * H, H, grads, P,
-                                                                      L.d1_w, R, H, splits); }
+      run_wgrad_ffma(w.h0, rows * H, H, w.dzl, rows * H, H, grads, P, L.d1_w, R, H, S, splits, w.wg_part, st);
       { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(w.dzl, rows * H, H, params, P, L.d1_w, w.h0,
                                                                      w.dh0, rows * H, R, H); }
       if ((rc = run_row_bwd(H, false, rbg, A, st, nullptr, w.xhat0, w.rstd0, w.dh0, w.dh0, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln0_scale, L.ln0_bias, L.d0_b, 0, 0,
                             nullptr, nullptr, nullptr, 0, nullptr, nullptr, w.rb_part, R))) return rc;
-      run_wgrad_first(w.xg, w.dh0, grads, P, L.d0_w, S, R, D, H, w.rb_part, st);
+      run_wgrad_first(w.xg, w.dh0, grads, P, L.d0_w, S, R, D, H, w.rb_part, w.wg_part, st);
     } else {
       if ((rc = run_row_bwd(H, true, rbg, A, st, w.h0, w.xhat0, w.rstd0, nullptr, w.dzl, nullptr, nullptr, nullptr, 1.0f, params, grads, P, L.ln0_scale, L.ln0_bias, L.d0_b, L.head_w, L.head_b,
                             gather, action, target, tr_rows_per_seed, loss_sum, qsa_sum, w.rb_part, R))) return rc;
-      run_wgrad_first(w.xg, w.dzl, grads, P, L.d0_w, S, R, D, H, w.rb_part, st);
+      run_wgrad_first(w.xg, w.dzl, grads, P, L.d0_w, S, R, D, H, w.rb_part, w.wg_part, st);
     }
   }
   return check_launch("pqn_qnet_loss_grad");

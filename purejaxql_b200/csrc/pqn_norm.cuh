@@ -659,6 +659,7 @@ __global__ void in_xhat_kernel(const float* __restrict__ X, int64_t n_per_seed, 
 struct NormWs {
   // shared small buffers
   float *part, *sums, *dg, *mr[3], *aff, *weff, *beff, *cntp, *q;
+  float* wgp;   // per-split partials of the FFMA weight gradient (run_wgrad_ffma)
   // CNN
   float *z1, *xh1, *h1, *rs1, *z2, *xh2, *h2, *rs2, *d2, *d1;
   // MLP
@@ -686,6 +687,7 @@ static int64_t carve_norm(const pqn_net_desc_t* d, int32_t S, int64_t rows, char
   const int64_t R = (int64_t)S * rows;
   const int A = d->num_actions;
   ww->part = take((int64_t)S * part_floats(d));
+  ww->wgp = take(WGRAD_SPLIT_TILES * 128 * 128);
   ww->sums = take((int64_t)S * 2 * 256);
   ww->dg = take((int64_t)S * 2 * 256);
   for (int i = 0; i < 3; ++i) ww->mr[i] = take((int64_t)S * 2 * 256);
@@ -838,12 +840,12 @@ static int norm_forward(const pqn_net_desc_t* d, const pqn_net_layout_t& L, cons
     const float* x = (const float*)obs;
     int64_t xss = orps * D;
     if (gather || train) {   // training also needs the input sums for the (dummy or real) input BatchNorm
-      { LaunchScope _ls(K_GATHER_ROWS, st); gather_rows_kernel<<<dim3(cdiv((int64_t)rows * D, 256), S), 256, 0, st>>>(x, orps, gather, w.xg, nullptr, rows, D); }
+      { LaunchScope _ls(K_GATHER_ROWS, st); gather_rows_kernel<<<dim3(cdiv((int64_t)rows * D, 256), S), 256, 0, st>>>(x, orps, gather, w.xg, rows, D); }
       x = w.xg;
       xss = (int64_t)rows * D;
     }
     if (xss != (int64_t)rows * D) {  // strided rollout rows: make them dense for the elementwise kernels
-      { LaunchScope _ls(K_GATHER_ROWS, st); gather_rows_kernel<<<dim3(cdiv((int64_t)rows * D, 256), S), 256, 0, st>>>(x, orps, nullptr, w.xg, nullptr, rows, D); }
+      { LaunchScope _ls(K_GATHER_ROWS, st); gather_rows_kernel<<<dim3(cdiv((int64_t)rows * D, 256), S), 256, 0, st>>>(x, orps, nullptr, w.xg, rows, D); }
       x = w.xg;
     }
     if (train || d->norm_input) {
@@ -897,7 +899,7 @@ static int norm_loss_grad(const pqn_net_desc_t* d, const pqn_net_layout_t& L, co
     if ((rc = norm_layer_bwd(norm, w.d2, w.xh2, w.rs2, S, rows, HID_CNN, HID_CNN, params, grads, P, L.ln1_scale, L.ln1_bias,
                              L.d0_b, w, w.mr[1], st))) return rc;
     const int splits = wgrad_splits(FLAT_CNN / 128, S, rows);
-    { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(FLAT_CNN / 128, 1, S * splits), GT, 0, st>>>(w.h1, (int64_t)rows * FLAT_CNN, FLAT_CNN, w.d2, (int64_t)rows * HID_CNN, HID_CNN, grads, P, L.d0_w, rows, FLAT_CNN, splits); }
+    run_wgrad_ffma(w.h1, (int64_t)rows * FLAT_CNN, FLAT_CNN, w.d2, (int64_t)rows * HID_CNN, HID_CNN, grads, P, L.d0_w, rows, FLAT_CNN, S, splits, w.wgp, st);
     { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), FLAT_CNN / 128, S), GT, 0, st>>>(w.d2, (int64_t)rows * HID_CNN, HID_CNN, params, P, L.d0_w, w.h1, w.d1, (int64_t)rows * FLAT_CNN, rows, FLAT_CNN); }
     if ((rc = norm_layer_bwd(norm, w.d1, w.xh1, w.rs1, S, rows, FLAT_CNN, CONV_O, params, grads, P, L.ln0_scale, L.ln0_bias,
                              -1, w, w.mr[0], st))) return rc;
@@ -914,7 +916,7 @@ static int norm_loss_grad(const pqn_net_desc_t* d, const pqn_net_layout_t& L, co
       const float* xprev = l == 0 ? xin : w.h[l - 1];
       const int kin = l == 0 ? D : H;
       const int sp = wgrad_splits((kin + 127) / 128 * (H / 128), S, rows);
-      { LaunchScope _ls(K_WGRAD, st); wgrad_kernel<<<dim3(cdiv(kin, 128), H / 128, S * sp), GT, 0, st>>>(xprev, (int64_t)rows * kin, kin, w.d[l], (int64_t)rows * H, H, grads, P, offw[l], rows, kin, sp); }
+      run_wgrad_ffma(xprev, (int64_t)rows * kin, kin, w.d[l], (int64_t)rows * H, H, grads, P, offw[l], rows, kin, S, sp, w.wgp, st);
       if (l > 0) {
         { LaunchScope _ls(K_DGRAD, st); dgrad_kernel<<<dim3(cdiv(rows, 128), H / 128, S), GT, 0, st>>>(w.d[l], (int64_t)rows * H, H, params, P, offw[l], w.h[l - 1], w.d[l - 1], (int64_t)rows * H, rows, H); }
       }

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(H) rnn_onehot_grad_kernel(const float* __restr
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 struct RnnWs {
-  float *h[2], *xh[2], *rs[2], *ai, *y, *h0, *rg, *zg, *ng, *hn, *q, *dq, *dy, *da, *dhn, *dx, *dhl, *wt, *part, *sums, *rbp;
+  float *h[2], *xh[2], *rs[2], *ai, *y, *h0, *rg, *zg, *ng, *hn, *q, *dq, *dy, *da, *dhn, *dx, *dhl, *wt, *part, *sums, *rbp, *wgp;
 };
 
 static int64_t carve_rnn(const pqn_net_desc_t* d, int32_t S, int64_t rows, char* base, RnnWs* w) {
@@ -321,6 +321,7 @@ static int64_t carve_rnn(const pqn_net_desc_t* d, int32_t S, int64_t rows, char*
   ww->wt = take(3 * (int64_t)S * H * H);
   ww->part = take((int64_t)S * nrm::RED_BLOCKS * (2 * 256 > A + H * A ? 2 * 256 : A + H * A));
   ww->sums = take((int64_t)S * 2 * 256);
+  ww->wgp = take(WGRAD_SPLIT_TILES * 128 * 128);   // per-split partials of the FFMA weight gradient
   ww->rbp = take(part_ctas(S) * row_bwd_part_floats(H, A));
   return off;
 }

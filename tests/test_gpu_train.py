@@ -255,3 +255,32 @@ def test_two_identical_runs_give_bit_identical_parameters():
         outs.append((out["runner_state"][0].params_flat.cpu().numpy(), out["metrics"]["td_loss"].cpu().numpy()))
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("variant", ["mlp", "mlp_1seed_big", "cnn_batch_norm", "mlp_norm_input", "gru"])
+def test_other_network_variants_are_run_to_run_deterministic(variant):
+    """The MLP (thin first-layer weight gradient, split-K tensor-core hidden layer at one seed), the modular
+    NORM_TYPE / NORM_INPUT path and the GRU engine: every weight gradient is a fixed-order sum as well."""
+    from purejaxql_b200 import config_loader, pqn_gymnax, pqn_minatar, pqn_rnn_gymnax
+    outs = []
+    for _ in range(2):
+        if variant == "gru":
+            c = config_loader.compose(["+alg=pqn_rnn_cartpole", "NUM_SEEDS=2", "SAVE_PATH=null", "alg.TOTAL_TIMESTEPS=8192",
+                                       "alg.TOTAL_TIMESTEPS_DECAY=8192", "alg.TEST_DURING_TRAINING=False",
+                                       "alg.HIDDEN_SIZE=128"])
+            cfg = {**c, **c["alg"]}
+            out = pqn_rnn_gymnax.make_train(cfg)(jr.split(jr.PRNGKey(1), 2))
+        elif variant == "cnn_batch_norm":
+            cfg = _cfg("Breakout-MinAtar", NUM_ENVS=128, NUM_STEPS=8, NORM_TYPE="batch_norm", NORM_INPUT=False,
+                       EPS_START=0.5, EPS_FINISH=0.1, EPS_DECAY=1.0)
+            cfg["TOTAL_TIMESTEPS"] = cfg["TOTAL_TIMESTEPS_DECAY"] = float(3 * 8 * 128)
+            out = pqn_minatar.make_train(cfg)(jr.split(jr.PRNGKey(2), 2))
+        else:
+            big = variant == "mlp_1seed_big"
+            cfg = _cfg("CartPole-v1", NUM_ENVS=4096 if big else 64, NUM_STEPS=16, HIDDEN_SIZE=128, NUM_LAYERS=2,
+                       NORM_INPUT=variant == "mlp_norm_input", EPS_START=0.5, EPS_FINISH=0.1, EPS_DECAY=1.0)
+            cfg["TOTAL_TIMESTEPS"] = cfg["TOTAL_TIMESTEPS_DECAY"] = float(3 * 16 * cfg["NUM_ENVS"])
+            out = pqn_gymnax.make_train(cfg)(jr.split(jr.PRNGKey(3), 1 if big else 3))
+        outs.append((out["runner_state"][0].params_flat.cpu().numpy(), out["metrics"]["td_loss"].cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
