@@ -36,3 +36,7 @@ print(json.dumps(res[-1]), flush=True)
 res.append(run(pqn_gymnax, "pqn_cartpole", "Acrobot-v1", str(65536 * 64 * 20), seeds=1,
                extra=("alg.NUM_ENVS=65536", "alg.TEST_NUM_ENVS=128")))
 print(json.dumps(res[-1]), flush=True)
+# round 2: the recurrent (GRU) engine with its shipped preset (pqn_rnn_cartpole.yaml, 5e5 steps, 4 seeds)
+from purejaxql_b200 import pqn_rnn_gymnax
+res.append(run(pqn_rnn_gymnax, "pqn_rnn_cartpole", "CartPole-v1", "5e5", seeds=4))
+print(json.dumps(res[-1]), flush=True)

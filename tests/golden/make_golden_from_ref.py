@@ -11,6 +11,9 @@ device logic and -- under -m gpu -- the CUDA kernels against them as soon as the
     <game>_traj_original_ref.npz / <game>_traj_partitionable_ref.npz   for the MinAtar games and classic control
         reset_keys, obs0, step_keys[T], action[T], obs[T], reward[T], done[T], ret[T], len[T], final_time
     jax_prng_ref.json        split / random_bits / uniform / randint / permutation values for both threefry layouts
+    optax_radam_ref.npz      40 steps of chain(clip_by_global_norm(10), radam(linear_schedule)) incl. one clipped step
+    qnetwork_cnn_ref.npz     the reference's own QNetwork (imported from $PUREJAXQL_REF or /root/reference): flax init,
+                             forward (train=False), loss and gradients of the _loss_fn form on 33 binary observations
     ref_versions.json        jax / jaxlib / gymnax versions and which MinAtar ids gymnax.make accepts
                              (records the Seaquest-MinAtar registration finding)
 
@@ -118,6 +121,61 @@ def main():
             print("wrote", short, tag, flush=True)
     jax.config.update("jax_threefry_partitionable", False)
     json.dump(prng, open(os.path.join(args.out, "jax_prng_ref.json"), "w"))
+
+    # ---- optax: chain(clip_by_global_norm, radam(linear_schedule)) over 40 steps on a small parameter tree
+    try:
+        import optax
+        rng = np.random.default_rng(5)
+        p0 = {"a": rng.standard_normal((7, 5)).astype(np.float32), "b": rng.standard_normal(11).astype(np.float32)}
+        gs = [{k: (rng.standard_normal(v.shape) * (30.0 if t == 3 else 1.0)).astype(np.float32) for k, v in p0.items()}
+              for t in range(40)]
+        sched = optax.linear_schedule(init_value=5e-4, end_value=1e-20, transition_steps=64)
+        tx = optax.chain(optax.clip_by_global_norm(10.0), optax.radam(learning_rate=sched))
+        params = {k: jnp.asarray(v) for k, v in p0.items()}
+        state = tx.init(params)
+        traj = []
+        for g in gs:
+            upd, state = tx.update({k: jnp.asarray(v) for k, v in g.items()}, state, params)
+            params = optax.apply_updates(params, upd)
+            traj.append({k: np.asarray(v) for k, v in params.items()})
+        np.savez_compressed(os.path.join(args.out, "optax_radam_ref.npz"),
+                            **{f"p0_{k}": v for k, v in p0.items()},
+                            **{f"g{t}_{k}": v for t, g in enumerate(gs) for k, v in g.items()},
+                            **{f"p{t + 1}_{k}": v for t, tr in enumerate(traj) for k, v in tr.items()})
+        versions["optax"] = optax.__version__
+        print("wrote optax_radam_ref.npz", flush=True)
+    except Exception as e:  # pragma: no cover
+        print(f"optax vectors skipped: {e!r}")
+
+    # ---- the reference's own QNetwork (imported, not restated): init, forward (train=False) and loss gradient
+    try:
+        sys.path.insert(0, os.environ.get("PUREJAXQL_REF", "/root/reference"))
+        from purejaxql.pqn_minatar import QNetwork
+        import flax
+        from flax.traverse_util import flatten_dict
+        net = QNetwork(action_dim=3, norm_type="layer_norm", norm_input=False)
+        rng = np.random.default_rng(9)
+        obs = (rng.random((33, 10, 10, 4)) < 0.1).astype(np.float32)
+        variables = net.init(jax.random.PRNGKey(3), jnp.zeros((1, 10, 10, 4)), train=False)
+        q = net.apply(variables, jnp.asarray(obs), train=False)
+        act = rng.integers(0, 3, 33)
+        tgt = rng.standard_normal(33).astype(np.float32)
+
+        def loss_fn(params):
+            qv, _ = net.apply({"params": params, "batch_stats": variables["batch_stats"]}, jnp.asarray(obs), train=True,
+                              mutable=["batch_stats"])
+            qa = jnp.take_along_axis(qv, jnp.asarray(act)[:, None], axis=-1).squeeze(-1)
+            return 0.5 * jnp.square(qa - jnp.asarray(tgt)).mean()
+        loss, grads = jax.value_and_grad(loss_fn)(variables["params"])
+        np.savez_compressed(os.path.join(args.out, "qnetwork_cnn_ref.npz"), obs=obs, action=act, target=tgt,
+                            q=np.asarray(q), loss=np.asarray(loss),
+                            **{"param/" + "/".join(k): np.asarray(v) for k, v in flatten_dict(variables["params"]).items()},
+                            **{"grad/" + "/".join(k): np.asarray(v) for k, v in flatten_dict(grads).items()})
+        versions["flax"] = flax.__version__
+        print("wrote qnetwork_cnn_ref.npz", flush=True)
+    except Exception as e:  # pragma: no cover
+        print(f"QNetwork vectors skipped: {e!r}")
+    json.dump(versions, open(os.path.join(args.out, "ref_versions.json"), "w"), indent=1)
     print("reference golden vectors written to", args.out)
     return 0
 

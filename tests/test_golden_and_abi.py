@@ -195,6 +195,36 @@ def test_oracle_prng_against_reference_generated_values():
             jr.DEFAULT_PARTITIONABLE = False
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLD, "optax_radam_ref.npz")),
+                    reason="no reference-generated optax trajectory committed")
+def test_oracle_radam_against_reference_generated_trajectory():
+    from oracle import pqn_ref as R
+    z = np.load(os.path.join(GOLD, "optax_radam_ref.npz"))
+    names = sorted(k[3:] for k in z.files if k.startswith("p0_"))
+    p = {k: z[f"p0_{k}"] for k in names}
+    opt = R.opt_init(p)
+    for t in range(40):
+        g = {k: z[f"g{t}_{k}"] for k in names}
+        p, opt, _ = R.radam_clip_step(p, g, opt, R.linear_schedule(5e-4, 1e-20, 64, t), 10.0)
+        for k in names:
+            assert np.abs(p[k] - z[f"p{t + 1}_{k}"]).max() < 2e-7, (t, k)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLD, "qnetwork_cnn_ref.npz")),
+                    reason="no reference-generated QNetwork vectors committed")
+def test_oracle_cnn_against_reference_qnetwork():
+    from oracle import pqn_ref as R
+    z = np.load(os.path.join(GOLD, "qnetwork_cnn_ref.npz"))
+    p = {k[len("param/"):]: z[k] for k in z.files if k.startswith("param/")}
+    q = R.cnn_forward(p, z["obs"])
+    assert np.abs(q - z["q"]).max() < 1e-5 * max(1.0, np.abs(z["q"]).max())
+    loss, _, g = R.cnn_loss_and_grads(p, z["obs"], z["action"], z["target"])[:3]
+    assert abs(loss - float(z["loss"])) < 1e-5 * max(1.0, abs(float(z["loss"])))
+    scale = max(np.abs(z[k]).max() for k in z.files if k.startswith("grad/"))
+    for k in p:
+        assert np.abs(g[k] - z["grad/" + k]).max() < 2e-5 * scale, k
+
+
 def test_bench_gpu_arm_does_not_import_oracle():
     """bench.py may execute oracle/ only in its CPU legs (cpu_baseline / --impl reference): every `oracle` import must
     sit inside cpu_port_steps, never at module level or in the GPU arm."""
