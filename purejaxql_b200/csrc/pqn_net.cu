@@ -639,37 +639,44 @@ __global__ void __launch_bounds__(256) row_bwd_kernel(
 }
 
 // Fixed-order column sum of `count` partial vectors (p[c * stride], c = 0..count-1) by a 256-thread block laid out as
-// 32 columns x 8 slices: slice s adds the partials c = s, s+8, ... in order, the eight slice sums are then added in
-// slice order.  Every thread of the block must call it; the result is valid in the threads of slice 0 (threadIdx.x < 32).
+// (256 / SL) columns x SL slices: slice s adds the partials c = s, s+SL, ... in order, the SL slice sums are then added
+// in slice order.  Every thread of the block must call it; the result is valid in the threads of slice 0
+// (threadIdx.x < 256 / SL).  SL = 8 for a few partials per seed (many seeds), 32 for hundreds (one seed): the chain of
+// dependent-latency loads per thread stays short either way.
+template <int SL>
 __device__ __forceinline__ float ordered_partial_sum(const float* __restrict__ p, int count, int64_t stride, bool valid) {
-  __shared__ float slice_sum[8][32];
-  const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  constexpr int COLS = 256 / SL;
+  __shared__ float slice_sum[SL][COLS];
+  const int col = threadIdx.x % COLS, sl = threadIdx.x / COLS;
   float v = 0.f;
   if (valid) {
 #pragma unroll 4
-    for (int c = sl; c < count; c += 8) v += p[(int64_t)c * stride];
+    for (int c = sl; c < count; c += SL) v += p[(int64_t)c * stride];
   }
   slice_sum[sl][col] = v;
   __syncthreads();
   float r = 0.f;
   if (sl == 0) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r += slice_sum[k][col];
+    for (int k = 0; k < SL; ++k) r += slice_sum[k][col];
   }
   return r;
 }
+// slices for `count` partials per output element
+static inline int final_slices(int count) { return count > 48 ? 32 : 8; }
 
 // Sums the per-CTA partial vectors of row_bwd_kernel in a fixed order and writes the gradients (and adds the
-// minibatch's loss / mean q_sa to the running sums).  grid = (ceil(stride / 32), S), block = 256
+// minibatch's loss / mean q_sa to the running sums).  grid = (ceil(stride / (256 / SL)), S), block = 256
+template <int SL>
 __global__ void row_bwd_final_kernel(const float* __restrict__ part, int nctas, int N, int A, int head,
                                      float* __restrict__ grads, int64_t P, int64_t off_dscale, int64_t off_dbias,
                                      int64_t off_db, int64_t off_hw, int64_t off_hb, float* __restrict__ loss_sum,
                                      float* __restrict__ qsa_sum) {
   const int seed = blockIdx.y;
   const int stride = 3 * N + (head ? A * N + A + 2 : 0);
-  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
-  const float v = ordered_partial_sum(part + (int64_t)seed * nctas * stride + i, nctas, stride, i < stride);
-  if (i >= stride || threadIdx.x >= 32) return;
+  const int i = blockIdx.x * (256 / SL) + threadIdx.x % (256 / SL);
+  const float v = ordered_partial_sum<SL>(part + (int64_t)seed * nctas * stride + i, nctas, stride, i < stride);
+  if (i >= stride || threadIdx.x >= 256 / SL) return;
   float* __restrict__ g = grads + (int64_t)seed * P;
   if (i < N) g[off_dscale + i] = v;
   else if (i < 2 * N) g[off_dbias + (i - N)] = v;
@@ -1495,13 +1502,20 @@ __global__ void __launch_bounds__(CONV16_WARPS * 32, CONV16_CTAS_PER_SM)
   static_assert(Cfg::PW <= 32, "one packed observation word per lane");
   if (lane == 0) my_so[Cfg::PW] = 0u;
   const int row_stride = gridDim.x * CONV16_WARPS;
-  auto fetch = [&](int r) -> uint32_t {
-    if (r >= rows || lane >= Cfg::PW) return 0u;
-    const int64_t src = gather ? gather[(int64_t)seed * rows + r] : r;
+  // two-deep prefetch: the gather index of row + 2 strides and the packed observation of row + 1 stride are in flight
+  // while this row is computed, so the index -> observation load chain never stalls the in-order issue
+  auto fetch_index = [&](int r) -> int {
+    if (r >= rows) return -1;
+    return gather ? __ldg(gather + (int64_t)seed * rows + r) : r;
+  };
+  auto fetch_obs = [&](int src) -> uint32_t {
+    if (src < 0 || lane >= Cfg::PW) return 0u;
     return __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + lane);
   };
-  uint32_t pre = fetch(blockIdx.x * CONV16_WARPS + warp);
-  for (int row = blockIdx.x * CONV16_WARPS + warp; row < rows; row += row_stride) {
+  const int row0 = blockIdx.x * CONV16_WARPS + warp;
+  uint32_t pre = fetch_obs(fetch_index(row0));
+  int src_next = fetch_index(row0 + row_stride);
+  for (int row = row0; row < rows; row += row_stride) {
     __syncwarp();
     if (lane < Cfg::PW) my_so[lane] = pre;
     if (TRAIN && bn_sums != nullptr) {
@@ -1509,7 +1523,8 @@ __global__ void __launch_bounds__(CONV16_WARPS * 32, CONV16_CTAS_PER_SM)
       for (int c = 0; c < C; ++c) cnt[c] += __popc(pre & cmask[c]);
     }
     __syncwarp();
-    pre = fetch(row + row_stride);
+    pre = fetch_obs(src_next);
+    src_next = fetch_index(row + 2 * row_stride);
     store_patch16<C>(my_so, lane, sxp[warp] + lane * M::ROW);
     store_patch16<C>(my_so, lane + 32, sxp[warp] + (lane + 32) * M::ROW);
     __syncwarp();
@@ -1848,16 +1863,16 @@ __global__ void __launch_bounds__(ConvBwdSmem<C>::WARPS * 32, 2)
   if (tid < 3 * CONV_O) o[M::TAPS * CONV_O + tid] = s_red[tid];
 }
 
-// Sums conv_bwd_mma_kernel's per-CTA partials in CTA order into the gradients.  grid = (ceil(n / 256), S)
+// Sums conv_bwd_mma_kernel's per-CTA partials in a fixed order into the gradients.
+// grid = (ceil(n / (256 / SL)), S), block = 256
+template <int SL>
 __global__ void conv_bwd_final_kernel(const float* __restrict__ part, int nctas, int taps16, float* __restrict__ grads,
                                       int64_t P, pqn_net_layout_t L) {
   const int seed = blockIdx.y;
   const int stride = taps16 + 3 * CONV_O;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= stride) return;
-  const float* __restrict__ p = part + (int64_t)seed * nctas * stride + i;
-  float v = 0.f;
-  for (int c = 0; c < nctas; ++c) v += p[(int64_t)c * stride];
+  const int i = blockIdx.x * (256 / SL) + threadIdx.x % (256 / SL);
+  const float v = ordered_partial_sum<SL>(part + (int64_t)seed * nctas * stride + i, nctas, stride, i < stride);
+  if (i >= stride || threadIdx.x >= 256 / SL) return;
   float* __restrict__ gout = grads + (int64_t)seed * P;
   if (i < taps16) gout[L.conv_w + i] = v;
   else if (i < taps16 + CONV_O) gout[L.ln0_scale + (i - taps16)] = v;
@@ -2156,12 +2171,22 @@ static int wgrad_ksplit(int tiles_total, int k_blocks) {
   while (ks > 1 && (int64_t)(ks - 1) * ((k_blocks + ks - 1) / ks) >= k_blocks) --ks;   // no empty split
   return ks;
 }
+template <int SL>
 __global__ void wgrad_split_reduce_kernel(const float* __restrict__ part, int ksplit, int64_t split_stride, int64_t n_per_seed,
                                           float* __restrict__ out, int64_t out_seed_stride) {
   const int seed = blockIdx.y;
-  const int64_t i = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
-  const float v = ordered_partial_sum(part + (int64_t)seed * n_per_seed + i, ksplit, split_stride, i < n_per_seed);
-  if (i < n_per_seed && threadIdx.x < 32) out[(int64_t)seed * out_seed_stride + i] = v;
+  const int64_t i = (int64_t)blockIdx.x * (256 / SL) + threadIdx.x % (256 / SL);
+  const float v = ordered_partial_sum<SL>(part + (int64_t)seed * n_per_seed + i, ksplit, split_stride, i < n_per_seed);
+  if (i < n_per_seed && threadIdx.x < 256 / SL) out[(int64_t)seed * out_seed_stride + i] = v;
+}
+// out[seed][i] = sum over k < ksplit of part[k * split_stride + seed * n + i], in k-slice order
+static void launch_split_reduce(const float* part, int ksplit, int64_t split_stride, int64_t n, int S, float* out,
+                                int64_t out_seed_stride, cudaStream_t st) {
+  LaunchScope _ls(K_GRAD_FINAL, st);
+  if (final_slices(ksplit) == 32)
+    wgrad_split_reduce_kernel<32><<<dim3((unsigned)((n + 7) / 8), S), 256, 0, st>>>(part, ksplit, split_stride, n, out, out_seed_stride);
+  else
+    wgrad_split_reduce_kernel<8><<<dim3((unsigned)((n + 31) / 32), S), 256, 0, st>>>(part, ksplit, split_stride, n, out, out_seed_stride);
 }
 
 // The register-tiled FFMA weight gradient + (splits > 1) its ordered reduction.  `part` needs splits * S * Kin * N floats
@@ -2174,8 +2199,7 @@ static void run_wgrad_ffma(const float* X, int64_t x_seed_stride, int ldx, const
         X, x_seed_stride, ldx, DZ, dz_seed_stride, N, grads, P, off_w, rows, Kin, splits, part); }
   if (splits > 1) {
     const int64_t n = (int64_t)Kin * N;
-    LaunchScope _ls(K_GRAD_FINAL, st);
-    wgrad_split_reduce_kernel<<<dim3((unsigned)((n + 31) / 32), S), 256, 0, st>>>(part, splits, (int64_t)S * n, n, grads + off_w, P);
+    launch_split_reduce(part, splits, (int64_t)S * n, n, S, grads + off_w, P, st);
   }
 }
 
@@ -2261,8 +2285,7 @@ static void run_wgrad_first(const float* X, const float* DZ, float* grads, int64
     const int64_t n = (int64_t)D * H;
     { LaunchScope _ls(K_WGRAD, st);
       wgrad_thin_kernel<<<dim3(chunks, S), 256, 0, st>>>(X, (int64_t)rows * D, D, DZ, (int64_t)rows * H, H, part, rows, per); }
-    { LaunchScope _ls(K_GRAD_FINAL, st);
-      wgrad_split_reduce_kernel<<<dim3(cdiv(n, 32), S), 256, 0, st>>>(part, chunks, (int64_t)S * n, n, grads + off_w, P); }
+    launch_split_reduce(part, chunks, (int64_t)S * n, n, S, grads + off_w, P, st);
     return;
   }
   run_wgrad_ffma(X, (int64_t)rows * D, D, DZ, (int64_t)rows * H, H, grads, P, off_w, rows, D, S,
@@ -2336,7 +2359,10 @@ static int launch_conv_bwd_mma(dim3 grid, cudaStream_t st, const uint32_t* obs, 
   kfn<<<grid, ConvBwdSmem<C>::WARPS * 32, ConvBwdSmem<C>::BYTES, st>>>(obs, orps, gather, params, P, L, dy1, xh1, rs1,
                                                                        part, rows);
   const int n = 9 * C * CONV_O + 3 * CONV_O;
-  conv_bwd_final_kernel<<<dim3(cdiv(n, 256), grid.y), 256, 0, st>>>(part, (int)grid.x, 9 * C * CONV_O, grads, P, L);
+  if (final_slices((int)grid.x) == 32)
+    conv_bwd_final_kernel<32><<<dim3(cdiv(n, 8), grid.y), 256, 0, st>>>(part, (int)grid.x, 9 * C * CONV_O, grads, P, L);
+  else
+    conv_bwd_final_kernel<8><<<dim3(cdiv(n, 32), grid.y), 256, 0, st>>>(part, (int)grid.x, 9 * C * CONV_O, grads, P, L);
   return 0;
 }
 
@@ -2362,9 +2388,12 @@ static void launch_row_bwd_final(const float* part, dim3 rbg, int N, int A, bool
                                  float* loss_sum, float* qsa_sum, cudaStream_t st) {
   const int stride = 3 * N + (head ? A * N + A + 2 : 0);
   LaunchScope _ls(K_GRAD_FINAL, st);
-  row_bwd_final_kernel<<<dim3(cdiv(stride, 32), rbg.y), 256, 0, st>>>(part, (int)rbg.x, N, A, head ? 1 : 0, grads, P,
-                                                                         off_dscale, off_dbias, off_db, off_hw, off_hb,
-                                                                         loss_sum, qsa_sum);
+  if (final_slices((int)rbg.x) == 32)
+    row_bwd_final_kernel<32><<<dim3(cdiv(stride, 8), rbg.y), 256, 0, st>>>(part, (int)rbg.x, N, A, head ? 1 : 0, grads, P, off_dscale,
+                                                                           off_dbias, off_db, off_hw, off_hb, loss_sum, qsa_sum);
+  else
+    row_bwd_final_kernel<8><<<dim3(cdiv(stride, 32), rbg.y), 256, 0, st>>>(part, (int)rbg.x, N, A, head ? 1 : 0, grads, P, off_dscale,
+                                                                           off_dbias, off_db, off_hw, off_hb, loss_sum, qsa_sum);
 }
 
 // row_bwd + its fixed-order finalize.  off_scale = LayerNorm scale of this layer (also where d scale goes), off_bias its
@@ -2581,8 +2610,7 @@ static int tc16_wgrad(float* grads, int64_t P, const pqn_net_layout_t& L, const 
   else { ep.out = grads + L.d0_w; ep.out_seed_stride = P; }
   if ((rc = tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD))) return rc;
   if (gs.k_split > 1) {
-    LaunchScope _ls(K_GRAD_FINAL, st);
-    wgrad_split_reduce_kernel<<<dim3(cdiv(n, 32), S), 256, 0, st>>>(wg_part, gs.k_split, (int64_t)S * n, n, grads + L.d0_w, P);
+    launch_split_reduce(wg_part, gs.k_split, (int64_t)S * n, n, S, grads + L.d0_w, P, st);
   }
   return 0;
 }
@@ -2642,8 +2670,7 @@ static int tc16_mm_wgrad(const __half* a, int64_t a_plane, const __half* dz, int
   else { ep.out = out; ep.out_seed_stride = out_seed_stride; }
   if ((rc = tc::launch_gemm16(1, 1, tc::EPI_STORE, t, gs, ep, st, K_TC_WGRAD))) return rc;
   if (gs.k_split > 1) {
-    LaunchScope _ls(K_GRAD_FINAL, st);
-    wgrad_split_reduce_kernel<<<dim3(cdiv(n, 32), S), 256, 0, st>>>(wg_part, gs.k_split, (int64_t)S * n, n, out, out_seed_stride);
+    launch_split_reduce(wg_part, gs.k_split, (int64_t)S * n, n, S, out, out_seed_stride, st);
   }
   return 0;
 }
