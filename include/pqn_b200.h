@@ -79,6 +79,17 @@ int pqn_threefry2x32(const uint32_t* key_pairs, const uint32_t* ctr_pairs, uint3
                      void* stream);
 /* out[n][len] = jax.random.random_bits(keys[n], 32, (len,)) — sort keys of jax.random.permutation (:303) */
 int pqn_rng_bits(const uint32_t* keys, int64_t n, int64_t len, uint32_t* out, int rng_mode, void* stream);
+/* out[S][n] (int32) = jax.random.permutation(keys[s], n) as an index permutation, i.e. the shuffle that
+ * `jax.random.permutation(rng, x)` applies to every leaf of the flattened rollout (pqn_minatar.py:299-315): jax's
+ * rounds of a stable sort by fresh 32-bit keys, done as an exact bucket + rank sort (csrc/pqn_perm.cu).
+ * out_chunk > 0 (must divide n) writes the minibatch layout out[n / out_chunk][S][out_chunk] instead of out[S][n]
+ * (:316-321: minibatch i of seed s = positions [i * chunk, (i+1) * chunk)).  workspace: pqn_permutation_workspace_bytes. */
+/* test hook: target bucket size 2^log2_elems of the bucket sort (default 6; > 8 forces the global-memory rank path);
+ * returns the previous value.  Set it before pqn_permutation_workspace_bytes. */
+int pqn_set_permutation_bucket_log2(int log2_elems);
+int64_t pqn_permutation_workspace_bytes(int64_t n, int32_t S);
+int pqn_permutation(const uint32_t* keys, int64_t n, int32_t S, int rng_mode, int32_t* out, int64_t out_chunk,
+                    void* workspace, void* stream);
 
 /* ---- the environment operator: vmapped LogWrapper(env).reset / .step ------
  * replaces vmap_reset / vmap_step, pqn_minatar.py:107-112 (gymnax protocol:

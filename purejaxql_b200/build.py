@@ -24,6 +24,7 @@ UNITS = [
     ("pqn_env.cu", ["-fmad=false"]),
     ("pqn_net.cu", []),
     ("pqn_optim.cu", []),
+    ("pqn_perm.cu", []),
     ("pqn_tc.cu", []),
 ]
 

@@ -17,7 +17,8 @@ enum KernelId : int {
   K_CONV_FWD_INFER /* rollout / evaluation variant */, K_TC_FWD_HEAD /* forward GEMM with the Q-head epilogue */,
   K_NORM_FWD, K_NORM_BWD, K_NORM_REDUCE /* modular NORM_TYPE / NORM_INPUT path (pqn_norm.cuh) */,
   K_RNN_SCAN, K_RNN_MISC /* GRU network (pqn_rnn.cuh) */,
-  K_GRAD_FINAL /* fixed-order second stage of the deterministic gradient reductions */, K_COUNT
+  K_GRAD_FINAL /* fixed-order second stage of the deterministic gradient reductions */,
+  K_PERM /* jax.random.permutation bucket + rank sort (pqn_perm.cu) */, K_COUNT
 };
 
 // SM count of the CURRENT device (cached per device ordinal, not per process)

@@ -234,6 +234,7 @@ class PQNEngine:
         upd_idx = torch.zeros(1, dtype=torch.int64, device=dev)      # n_updates on the device
         m_cur = torch.zeros((S, 7), dtype=torch.float64, device=dev)  # td_loss, qvals, 5 info means
         ws = self._workspace(S, max(mb, E))
+        perm_ws = jr.permutation_workspace(T * E, S, dev)
         denom = float(self.epochs * self.nmb)
         bn_count = float(mb * world * (100 if self.binary else 1))
 
@@ -275,8 +276,7 @@ class PQNEngine:
                 r, kperm = k[:, 0].contiguous(), k[:, 1].contiguous()
                 if world > 1:                                        # a different local permutation on every rank
                     kperm = jr.split(kperm, world, mode)[:, rank].contiguous()
-                perm = jr.permutation_indices(kperm, T * E, mode)    # :299-315 same perm for every leaf
-                perm_view = perm.view(S, self.nmb, mb).transpose(0, 1).contiguous()
+                perm_view = jr.permutation_indices(kperm, T * E, mode, chunk=mb, workspace=perm_ws)   # :299-321  [nmb][S][mb]
                 r = jr.split(r, 2, mode)[:, 0].contiguous()          # :317
                 for mbi in range(self.nmb):
                     _lib.check(L.pqn_qnet_loss_grad(

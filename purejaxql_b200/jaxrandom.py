@@ -59,22 +59,22 @@ def random_bits(keys: torch.Tensor, length: int, rng_mode: int = 0) -> torch.Ten
     return out
 
 
-def permutation_indices(keys: torch.Tensor, n: int, rng_mode: int = 0) -> torch.Tensor:
-    """Index permutation of ``jax.random.permutation(key, x)`` for ``len(x)==n``,
-    batched over keys [S,2] -> int32[S,n].  jax's ``_shuffle``: ceil(3 ln n /
-    ln(2^32-1)) rounds of a *stable* sort by fresh uint32 keys.  The random sort
-    keys come from our kernel; the stable key sort itself uses torch.sort
-    (a cub radix sort) as plumbing."""
-    rounds = int(np.ceil(3 * np.log(max(1, n)) / np.log(np.iinfo(np.uint32).max)))
+def permutation_workspace(n: int, S: int, device) -> torch.Tensor:
+    """Scratch buffer of ``pqn_permutation`` for S keys and n elements (callers that permute every update keep one)."""
+    nbytes = int(_lib.lib().pqn_permutation_workspace_bytes(int(n), int(S)))
+    return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+
+
+def permutation_indices(keys: torch.Tensor, n: int, rng_mode: int = 0, chunk: int = 0, workspace=None) -> torch.Tensor:
+    """Index permutation of ``jax.random.permutation(key, x)`` for ``len(x)==n``, batched over keys [S,2] ->
+    int32[S,n]: jax's ``_shuffle`` (ceil(3 ln n / ln(2^32-1)) rounds of a *stable* sort by fresh uint32 keys) in
+    ``pqn_permutation`` (exact bucket + rank sort, csrc/pqn_perm.cu).  ``chunk > 0`` returns the minibatch layout
+    int32[n // chunk, S, chunk] (minibatch i of seed s = positions [i*chunk, (i+1)*chunk) of its permutation)."""
+    keys = keys.contiguous()
     S = keys.shape[0]
-    idx = torch.arange(n, device=keys.device, dtype=torch.int64).unsqueeze(0).expand(S, n).contiguous()
-    key = keys
-    for _ in range(rounds):
-        ks = split(key, 2, rng_mode)
-        key, sub = ks[:, 0].contiguous(), ks[:, 1].contiguous()
-        # uint32 sort keys as int32 with the sign bit flipped: signed order == unsigned order, and the radix sort runs
-        # over 32 key bits instead of the 64 of an int64 view
-        bits = random_bits(sub, n, rng_mode).bitwise_xor_(-0x80000000)
-        order = torch.sort(bits, dim=1, stable=True).indices
-        idx = torch.gather(idx, 1, order)
-    return idx.to(torch.int32)
+    ws = workspace if workspace is not None else permutation_workspace(n, S, keys.device)
+    shape = (n // chunk, S, chunk) if chunk else (S, n)
+    out = torch.empty(shape, dtype=torch.int32, device=keys.device)
+    _lib.check(_lib.lib().pqn_permutation(_lib.p(keys), int(n), int(S), rng_mode, _lib.p(out), int(chunk), _lib.p(ws),
+                                          _lib.stream_ptr()), "pqn_permutation")
+    return out
