@@ -1863,6 +1863,302 @@ __global__ void __launch_bounds__(ConvBwdSmem<C>::WARPS * 32, 2)
   if (tid < 3 * CONV_O) o[M::TAPS * CONV_O + tid] = s_red[tid];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// conv backward with the weight gradient on fp16 warp-level MMA (mma.sync.m16n8k16, fp32 accumulate) -- the default
+// backward of the fp16 conv path.  Same phases as conv_bwd_mma_kernel; what changes is phase B,
+// dW[tap][o] = sum_pixels x[pixel, tap] dz[pixel][o] with M = taps, N = 16 channels, K = 64 pixels in 4 k-steps of 16:
+//   * A (the {0,1} im2col bits, tap-major) is "exponent coded" like the forward: for every PAIR of pixels (2j, 2j+1)
+//     and group q of four taps one word holds the tap bits of pixel 2j at bits 10..13 and of pixel 2j+1 at bits 26..29;
+//     a fragment register (row = tap, its two k values = the two pixels of a pair) is that word AND the lane's mask
+//     (1 << (10 + g%4)) | (1 << (26 + g%4)): a set bit becomes the fp16 power of two 2^(2^(g%4) - 15).  The factor
+//     depends only on the accumulator ROW, which is fixed per thread, so it is undone by one exact multiplication
+//     when the accumulators are published -- 48 LOP3 per sample instead of 288 shift / and / select.
+//   * B = dz * gs as fp16 hi + lo (lo = fp16(v - hi): 22 significant bits where it matters; gs is a power of two that
+//     lifts the gradient-sized values out of the fp16 subnormals), written by phase A directly in fragment order:
+//     dzT[plane][channel][pixel pair], the pairs (t, t + 4) of a k-step adjacent so that (b0, b1) is one LDS.64; the
+//     k-step block of a channel row is XOR-swizzled so that the phase-A stores and the fragment loads are conflict free.
+//   * 48 MMAs per sample (3 m-tiles x 2 n-tiles x 4 k-steps x {hi, lo}) instead of 96 tf32 ones.
+// Phase A works on the pixel pair (16 mb + 2g, + 1) per thread (it was (g, g + 8)): a thread's two dz values of one
+// channel are exactly one B word.  The DY / xhat stage has a row + column swizzle for that access pattern.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+struct ConvBwd16 {
+  static constexpr int MT = ConvMma<C>::MT;
+  static constexpr int NG = 4 * MT;                             // tap groups of 4 per pixel pair
+  static constexpr int NGP = (NG % 8 == 4) ? NG : NG + 4;       // pair stride in words: the 4 t-lanes hit distinct banks
+  static constexpr int DY = 0;                                  // [64][16] upstream gradient (swizzled)
+  static constexpr int XH = DY + FLAT_CNN;                      // [64][16] saved xhat (swizzled)
+  static constexpr int RS = XH + FLAT_CNN;                      // [64] saved rstd
+  static constexpr int DZT = RS + CONV_PIX;                     // 2 planes x [16 ch][32 pair words]; aliases the obs row
+  static constexpr int PW = DZT + 2 * CONV_O * 32;              // [32 pairs][NGP] exponent-coded pair words
+  static constexpr int WARP_FLOATS = (PW + 32 * NGP + 3) / 4 * 4;
+  static constexpr int WARPS = (C == 4) ? 8 : 6;                // keeps two CTAs per SM for the wider observations
+  static constexpr int BYTES = (WARPS * WARP_FLOATS + 4 * CONV_O) * 4;  // + sc[16] + s_red[48]
+};
+
+// float offset of (pixel row p, channel column col) in the swizzled [64][16] DY / xhat stage: the rows 2g of one
+// fragment group would all start on bank 0, so odd (p / 4) swaps the two rows of a pair and odd (p / 2) swaps the
+// column halves -- the four g of a half-warp then cover the 32 banks once
+__device__ __forceinline__ int cswz16(int p, int col) {
+  return ((p ^ ((p >> 2) & 1)) << 4) + (col ^ (((p >> 1) & 1) << 3));
+}
+// word offset of (channel ch, k-step ks, position pos) in a dzT plane [16][32]
+__device__ __forceinline__ int dzt_word(int ch, int ks, int pos) {
+  const int c7 = ch & 7;
+  return (ch << 5) + ((ks ^ ((c7 + (c7 >> 2)) & 3)) << 3) + pos;
+}
+
+template <int C>
+__global__ void __launch_bounds__(ConvBwd16<C>::WARPS * 32, 2)
+    conv_bwd_mma16_kernel(const uint32_t* __restrict__ obs, int64_t obs_rows_per_seed, const int32_t* __restrict__ gather,
+                          const float* __restrict__ params, int64_t P, pqn_net_layout_t L, const float* __restrict__ DY1,
+                          const float* __restrict__ XH1, const float* __restrict__ RS1, float* __restrict__ part,
+                          int rows, float gs) {
+  using Cfg = ConvCfg<C>;
+  using M = ConvMma<C>;
+  using SM = ConvBwd16<C>;
+  constexpr int PWD = PatchCfg<C>::WORDS;
+  extern __shared__ __align__(16) float smem_bwd[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int seed = blockIdx.y;
+  float* my = smem_bwd + warp * SM::WARP_FLOATS;
+  float* my_dy = my + SM::DY;
+  float* my_xh = my + SM::XH;
+  float* my_rs = my + SM::RS;
+  uint32_t* my_dzt = reinterpret_cast<uint32_t*>(my + SM::DZT);   // plane 0 = hi, plane 1 = lo: 512 words each
+  uint32_t* my_so = reinterpret_cast<uint32_t*>(my + SM::DZT);    // packed obs row: only needed until the pair words exist
+  uint32_t* my_pw = reinterpret_cast<uint32_t*>(my + SM::PW);
+  float* sc = smem_bwd + SM::WARPS * SM::WARP_FLOATS;
+  float* s_red = sc + CONV_O;
+  float* s_w = smem_bwd;  // block-level dW reduction buffer, aliases warp 0's slice; only used after the row loop
+  static_assert(Cfg::SW <= 2 * CONV_O * 32, "obs staging aliases the dz planes");
+  static_assert(M::MT * 16 * CONV_O <= SM::WARP_FLOATS * SM::WARPS, "dW reduction buffer aliases the warp slices");
+  static_assert(Cfg::PW <= 32, "one packed observation word per lane");
+  if (tid < CONV_O) sc[tid] = __ldg(params + (int64_t)seed * P + L.ln0_scale + tid);
+  if (tid < 3 * CONV_O) s_red[tid] = 0.f;
+  __syncthreads();
+  float a_dsc[4] = {0.f, 0.f, 0.f, 0.f}, a_dbi[4] = {0.f, 0.f, 0.f, 0.f}, a_dcb[4] = {0.f, 0.f, 0.f, 0.f};
+  float wrun[M::MT][2][4];
+#pragma unroll
+  for (int mt = 0; mt < M::MT; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wrun[mt][h][j] = 0.f;
+  const uint32_t amask = (1u << (10 + (g & 3))) | (1u << (26 + (g & 3)));
+  const int pos_g = g < 4 ? 2 * g : 2 * (g - 4) + 1;   // pair g of a k-step sits next to pair g + 4
+
+  const int row_stride = gridDim.x * SM::WARPS;
+  auto fetch_index = [&](int r) -> int {
+    if (r >= rows) return -1;
+    return gather ? __ldg(gather + (int64_t)seed * rows + r) : r;
+  };
+  auto fetch_obs = [&](int src) -> uint32_t {
+    if (src < 0 || lane >= Cfg::PW) return 0u;
+    return __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + lane);
+  };
+  auto fetch_rows = [&](int r) {  // async copy of the sample's dy / xhat / rstd rows into this warp's slice
+    if (r < rows) {
+      const int64_t gr = (int64_t)seed * rows + r;
+      const float* dsrc = DY1 + gr * FLAT_CNN;
+      const float* xsrc = XH1 + gr * FLAT_CNN;
+#pragma unroll
+      for (int i = 0; i < FLAT_CNN / 4 / 32; ++i) {
+        const int q = i * 32 + lane, prow = q >> 2;              // 16-byte chunk q = (pixel row, column quad)
+        const int dst = cswz16(prow, (q & 3) * 4);               // the swizzles move whole chunks
+        cp_async16(my_dy + dst, dsrc + q * 4);
+        cp_async16(my_xh + dst, xsrc + q * 4);
+      }
+      if (lane < CONV_PIX / 4) cp_async16(my_rs + lane * 4, RS1 + gr * CONV_PIX + lane * 4);
+    }
+    cp_async_commit();
+  };
+  int row = blockIdx.x * SM::WARPS + warp;
+  uint32_t pre = fetch_obs(fetch_index(row));
+  int src_next = fetch_index(row + row_stride);
+  fetch_rows(row);
+  for (; row < rows; row += row_stride) {
+    __syncwarp();
+    if (lane < Cfg::PW) my_so[lane] = pre;
+    if (lane == 0) my_so[Cfg::PW] = 0u;  // pad word read by the funnel shift of the last pixel
+    __syncwarp();
+    pre = fetch_obs(src_next);
+    src_next = fetch_index(row + 2 * row_stride);
+    {  // exponent-coded pair words of pixel pair `lane`
+      uint32_t w0[PWD], w1[PWD];
+      patch_bits<C>(my_so, 2 * lane, w0);
+      patch_bits<C>(my_so, 2 * lane + 1, w1);
+      uint32_t pw[SM::NGP];
+#pragma unroll
+      for (int k = 0; k < SM::NGP; ++k) pw[k] = 0u;
+#pragma unroll
+      for (int q = 0; q < SM::NG; ++q) {
+        // memory order inside an m-tile: groups (0, 2, 1, 3), so the words of fragment rows g and g + 8 are adjacent
+        const int ql = q & 3, slot = (q & ~3) + (ql == 1 ? 2 : (ql == 2 ? 1 : ql));
+        const int bit = 4 * q, wi = bit >> 5, sh = bit & 31;
+        if (wi < PWD) {
+          const uint32_t v0 = w0[wi < PWD ? wi : 0], v1 = w1[wi < PWD ? wi : 0];
+          const uint32_t lo = sh >= 10 ? v0 >> (sh >= 10 ? sh - 10 : 0) : v0 << (sh < 10 ? 10 - sh : 0);
+          const uint32_t hi = sh <= 26 ? v1 << (sh <= 26 ? 26 - sh : 0) : v1 >> (sh > 26 ? sh - 26 : 0);
+          pw[slot] = __byte_perm(lo, hi, 0x7610);
+        }
+      }
+      uint32_t* dstw = my_pw + lane * SM::NGP;
+#pragma unroll
+      for (int k = 0; k < SM::NGP / 4; ++k)
+        *reinterpret_cast<uint4*>(dstw + 4 * k) = make_uint4(pw[4 * k], pw[4 * k + 1], pw[4 * k + 2], pw[4 * k + 3]);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    // ---- phase A: LayerNorm backward of the pixel pair (16 mb + 2g, + 1); dz * gs -> fp16 (hi, lo) planes
+#pragma unroll 1
+    for (int mb = 0; mb < 4; ++mb) {
+      const int p0 = 16 * mb + 2 * g, p1 = p0 + 1;
+      float z[2][4];
+      float2 dyv[2][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        dyv[h][0] = *reinterpret_cast<const float2*>(my_dy + cswz16(p0, 8 * h + 2 * t));
+        dyv[h][1] = *reinterpret_cast<const float2*>(my_dy + cswz16(p1, 8 * h + 2 * t));
+        const float2 a0 = *reinterpret_cast<const float2*>(my_xh + cswz16(p0, 8 * h + 2 * t));
+        const float2 a1 = *reinterpret_cast<const float2*>(my_xh + cswz16(p1, 8 * h + 2 * t));
+        z[h][0] = a0.x; z[h][1] = a0.y; z[h][2] = a1.x; z[h][3] = a1.y;
+      }
+      const float rstd0 = my_rs[p0], rstd1 = my_rs[p1];
+      float dxh[2][4];
+      float m1a = 0.f, m2a = 0.f, m1b = 0.f, m2b = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int o = 8 * h + 2 * t;
+        const float dy4[4] = {dyv[h][0].x, dyv[h][0].y, dyv[h][1].x, dyv[h][1].y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = 2 * h + (j & 1);
+          a_dsc[col] = fmaf(dy4[j], z[h][j], a_dsc[col]);
+          a_dbi[col] += dy4[j];
+          dxh[h][j] = dy4[j] * sc[o + (j & 1)];
+          if (j < 2) { m1a += dxh[h][j]; m2a = fmaf(dxh[h][j], z[h][j], m2a); }
+          else { m1b += dxh[h][j]; m2b = fmaf(dxh[h][j], z[h][j], m2b); }
+        }
+      }
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        m1a += __shfl_xor_sync(0xffffffffu, m1a, o); m2a += __shfl_xor_sync(0xffffffffu, m2a, o);
+        m1b += __shfl_xor_sync(0xffffffffu, m1b, o); m2b += __shfl_xor_sync(0xffffffffu, m2b, o);
+      }
+      m1a *= (1.0f / CONV_O); m2a *= (1.0f / CONV_O); m1b *= (1.0f / CONV_O); m2b *= (1.0f / CONV_O);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float dzv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float rstd = j < 2 ? rstd0 : rstd1, m1 = j < 2 ? m1a : m1b, m2 = j < 2 ? m2a : m2b;
+          dzv[j] = rstd * (dxh[h][j] - m1 - z[h][j] * m2);
+          a_dcb[2 * h + (j & 1)] += dzv[j];
+        }
+        // B words: (pixel p0, pixel p1) of channel o (j = 0, 2) and of channel o + 1 (j = 1, 3); k-step mb, pair g
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float v0 = dzv[c] * gs, v1 = dzv[2 + c] * gs;
+          const uint32_t hw = cvt_f16x2_satfinite(v0, v1);
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+          const __half2 lw = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+          const int wd = dzt_word(8 * h + 2 * t + c, mb, pos_g);
+          my_dzt[wd] = hw;
+          my_dzt[CONV_O * 32 + wd] = *reinterpret_cast<const uint32_t*>(&lw);
+        }
+      }
+    }
+    __syncwarp();
+    fetch_rows(row + row_stride);  // overlaps phase B
+    // ---- phase B: dW[tap][o] += sum_pixels x[pixel, tap] * dz[pixel][o]   (fresh accumulators per sample)
+    float wacc[M::MT][2][4];
+#pragma unroll
+    for (int mt = 0; mt < M::MT; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wacc[mt][h][j] = 0.f;
+#pragma unroll 1
+    for (int ks = 0; ks < 4; ++ks) {
+      // B fragments: b0 = dz[pixels 16ks + 2t, + 1][o = 8h + g], b1 = the same of pixels + 8: one LDS.64 per plane
+      uint2 bhi[2], blo[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int wd = dzt_word(8 * h + g, ks, 2 * t);
+        bhi[h] = *reinterpret_cast<const uint2*>(my_dzt + wd);
+        blo[h] = *reinterpret_cast<const uint2*>(my_dzt + CONV_O * 32 + wd);
+      }
+      const uint32_t* pa = my_pw + (8 * ks + t) * SM::NGP + 2 * (g >> 2);   // pixel pair 8ks + t: rows (g, g + 8)
+      const uint32_t* pb = pa + 4 * SM::NGP;                               // pixel pair 8ks + t + 4
+#pragma unroll
+      for (int mt = 0; mt < M::MT; ++mt) {
+        const uint2 wa = *reinterpret_cast<const uint2*>(pa + 4 * mt), wb = *reinterpret_cast<const uint2*>(pb + 4 * mt);
+        uint32_t a[4];
+        a[0] = wa.x & amask; a[1] = wa.y & amask; a[2] = wb.x & amask; a[3] = wb.y & amask;
+        // lo pass of both column halves, then the hi pass: no back-to-back MMAs on one accumulator
+        mma_f16_16n8k16(wacc[mt][0], a, blo[0].x, blo[0].y);
+        mma_f16_16n8k16(wacc[mt][1], a, blo[1].x, blo[1].y);
+        mma_f16_16n8k16(wacc[mt][0], a, bhi[0].x, bhi[0].y);
+        mma_f16_16n8k16(wacc[mt][1], a, bhi[1].x, bhi[1].y);
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < M::MT; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wrun[mt][h][j] += wacc[mt][h][j];
+  }
+  cp_async_wait_all();
+  // ---- reduce and publish (deterministic), as in conv_bwd_mma_kernel; the A coding 2^(2^(g%4) - 15) of this thread's
+  // accumulator rows and the dz scale gs are undone here (exact powers of two)
+  const float unscale = __uint_as_float((uint32_t)(127 + 15 - (1 << (g & 3))) << 23) / gs;
+  __syncthreads();  // all warps are done with their slices
+  for (int w = 0; w < SM::WARPS; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int mt = 0; mt < M::MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int tap = 16 * mt + g + (j >= 2 ? 8 : 0);
+            float* dst = &s_w[tap * CONV_O + 8 * h + 2 * t + (j & 1)];   // tap < 16 * MT: inside the buffer
+            *dst = (w == 0 ? 0.f : *dst) + wrun[mt][h][j] * unscale;
+          }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int col = 0; col < 4; ++col) {
+    float v0 = a_dsc[col], v1 = a_dbi[col], v2 = a_dcb[col];
+#pragma unroll
+    for (int sft = 4; sft <= 16; sft <<= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, sft);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, sft);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, sft);
+    }
+    a_dsc[col] = v0; a_dbi[col] = v1; a_dcb[col] = v2;
+  }
+  for (int w = 0; w < SM::WARPS; ++w) {
+    if (warp == w && g == 0) {
+#pragma unroll
+      for (int col = 0; col < 4; ++col) {
+        const int o = 8 * (col >> 1) + 2 * t + (col & 1);
+        s_red[o] = (w == 0 ? 0.f : s_red[o]) + a_dsc[col];
+        s_red[CONV_O + o] = (w == 0 ? 0.f : s_red[CONV_O + o]) + a_dbi[col];
+        s_red[2 * CONV_O + o] = (w == 0 ? 0.f : s_red[2 * CONV_O + o]) + a_dcb[col];
+      }
+    }
+    __syncthreads();
+  }
+  float* __restrict__ o = part + ((int64_t)seed * gridDim.x + blockIdx.x) * (M::TAPS * CONV_O + 3 * CONV_O);
+  for (int i = tid; i < M::TAPS * CONV_O; i += blockDim.x) o[i] = s_w[i] * (1.0f / 255.0f);
+  if (tid < 3 * CONV_O) o[M::TAPS * CONV_O + tid] = s_red[tid];
+}
+
 // Sums conv_bwd_mma_kernel's per-CTA partials in a fixed order into the gradients.
 // grid = (ceil(n / (256 / SL)), S), block = 256
 template <int SL>
@@ -2358,6 +2654,24 @@ static int launch_conv_bwd_mma(dim3 grid, cudaStream_t st, const uint32_t* obs, 
     return check_launch("conv_bwd_mma(cudaFuncSetAttribute)");
   kfn<<<grid, ConvBwdSmem<C>::WARPS * 32, ConvBwdSmem<C>::BYTES, st>>>(obs, orps, gather, params, P, L, dy1, xh1, rs1,
                                                                        part, rows);
+  const int n = 9 * C * CONV_O + 3 * CONV_O;
+  if (final_slices((int)grid.x) == 32)
+    conv_bwd_final_kernel<32><<<dim3(cdiv(n, 8), grid.y), 256, 0, st>>>(part, (int)grid.x, 9 * C * CONV_O, grads, P, L);
+  else
+    conv_bwd_final_kernel<8><<<dim3(cdiv(n, 32), grid.y), 256, 0, st>>>(part, (int)grid.x, 9 * C * CONV_O, grads, P, L);
+  return 0;
+}
+
+// the fp16 variant (conv path 1); gs = power-of-two scale of dz before the fp16 split
+template <int C>
+static int launch_conv_bwd_mma16(dim3 grid, cudaStream_t st, const uint32_t* obs, int64_t orps, const int32_t* gather,
+                                 const float* params, int64_t P, const pqn_net_layout_t& L, const float* dy1,
+                                 const float* xh1, const float* rs1, float* grads, float* part, int rows, float gs) {
+  auto kfn = conv_bwd_mma16_kernel<C>;
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvBwd16<C>::BYTES) != cudaSuccess)
+    return check_launch("conv_bwd_mma16(cudaFuncSetAttribute)");
+  kfn<<<grid, ConvBwd16<C>::WARPS * 32, ConvBwd16<C>::BYTES, st>>>(obs, orps, gather, params, P, L, dy1, xh1, rs1, part,
+                                                                   rows, gs);
   const int n = 9 * C * CONV_O + 3 * CONV_O;
   if (final_slices((int)grid.x) == 32)
     conv_bwd_final_kernel<32><<<dim3(cdiv(n, 8), grid.y), 256, 0, st>>>(part, (int)grid.x, 9 * C * CONV_O, grads, P, L);
@@ -3049,6 +3363,17 @@ int pqn_qnet_loss_grad(const pqn_net_desc_t* d, const float* params, float* batc
     if (g_conv_mma) {
       const dim3 mg(conv_mma_ctas(S, R, 2), S);
       LaunchScope _ls(K_CONV_BWD, st);
+      // dz of the conv is rstd (<= 316) times a dense-layer-sized gradient: one sixteenth of the dense gradient scale
+      // keeps it a factor ~200 below the fp16 maximum (conversions saturate) and far above the subnormals
+      const float gs16 = grad_scale((int)rows) * (1.0f / 16.0f);
+      if (g_conv_mma == 1) {
+        switch (d->in_c) {
+          case 4: rc = launch_conv_bwd_mma16<4>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, w.cb_part, R, gs16); break;
+          case 6: rc = launch_conv_bwd_mma16<6>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, w.cb_part, R, gs16); break;
+          case 7: rc = launch_conv_bwd_mma16<7>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, w.cb_part, R, gs16); break;
+          case 10: rc = launch_conv_bwd_mma16<10>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, w.cb_part, R, gs16); break;
+        }
+      } else
       switch (d->in_c) {
         case 4: rc = launch_conv_bwd_mma<4>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, w.cb_part, R); break;
         case 6: rc = launch_conv_bwd_mma<6>(mg, st, ob, obs_rows_per_seed, gather, params, P, L, w.h1, w.cxhat, w.crstd, grads, w.cb_part, R); break;
