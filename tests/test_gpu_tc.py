@@ -123,3 +123,14 @@ def test_tc_gemm16_small_gradients_with_prescale(a_mn, b_mn):
     d, ref, *_ = _run16(2, 256, 128, 512, a_mn, b_mn, seed=3, a_scale=float(2 ** 16), a_mag=1e-6)
     scale = np.abs(ref).max()
     assert np.abs(d - ref).max() < 4e-6 * scale, (np.abs(d - ref).max(), scale)
+
+
+@pytest.mark.parametrize("S,M,N", [(5, 4096, 1024), (3, 6536, 256), (160, 128, 384)])
+def test_tc_gemm16_a_stationary_mode(S, M, N):
+    """K = 128 (two k-blocks), K-major operands, several n-tiles and >= 148 (seed, m-tile) groups: the kernel keeps the
+    A tiles of a group resident and walks the n-tiles (the dense dgrad's shape); ragged M covers the row clipping."""
+    d, ref, *_ = _run16(S, M, N, 128, 0, 0, seed=S + N)
+    assert np.isfinite(d).all()
+    scale = np.abs(ref).max()
+    err = np.abs(d - ref).max()
+    assert err < 4e-6 * scale, (err, scale)
