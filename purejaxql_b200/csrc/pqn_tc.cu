@@ -353,23 +353,6 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
     return ks;
   };
 
-  // A-stationary mode (fp16 K-major operands with K = 2 k-blocks and several n-tiles: the dense dgrad, K = 128): a CTA
-  // takes whole (seed, m-tile) groups and walks their n-tiles, the operand ring is cut to two stages so that stage kb
-  // always holds k-block kb, and the A tiles are only loaded for the first n-tile of a group -- the TMA fill per output
-  // tile drops from 128 KB to 64 KB + 64 KB / n_tiles (the kernel sat at 67 % of the shared-memory pipe, ncu r2c).
-  const int groups = gs.S * gs.m_tiles;
-  const bool a_stat = F16 && !A_MN && !B_MN && ksplit == 1 && gs.k_blocks == 2 && gs.n_tiles > 1 && gs.split3 &&
-                      groups >= (int)gridDim.x;
-  const int nstages = a_stat ? 2 : TC_STAGES;
-  auto tile_at = [&](int it) -> int {   // it-th tile of this CTA, -1 when it has none left
-    if (!a_stat) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      return tile < num_tiles ? tile : -1;
-    }
-    const int grp = blockIdx.x + (it / gs.n_tiles) * gridDim.x;
-    return grp < groups ? grp * gs.n_tiles + it % gs.n_tiles : -1;
-  };
-
   // F16: fp16 operand planes (hi, lo'), 64-element k-blocks, A_lo' always comes from memory (no converter warps)
   const bool a_lo_tma = gs.split3 && (F16 || !gs.a_lo_inline);
   const bool a_lo_conv = !F16 && gs.split3 && gs.a_lo_inline;
@@ -381,18 +364,15 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int seed, m0, n0, kb0, kbn;
         decode(tile, seed, m0, n0, kb0, kbn);
         for (int kb = kb0; kb < kb0 + kbn; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
-          const bool load_a = !a_stat || it % gs.n_tiles == 0;   // A-stationary: stage kb keeps A k-block kb of the group
-          mbar_expect_tx(&full[stage], !load_a ? 2 * TC_TILE_BYTES
-                                               : gs.split3 ? (a_lo_tma ? TC_STAGE_BYTES : 3 * TC_TILE_BYTES) : TC_STAGE_BYTES / 2);
+          mbar_expect_tx(&full[stage], gs.split3 ? (a_lo_tma ? TC_STAGE_BYTES : 3 * TC_TILE_BYTES) : TC_STAGE_BYTES / 2);
           const int k0 = kb * BKE;
-          if (!load_a) {
-          } else if (A_MN) {
+          if (A_MN) {
 #pragma unroll
             for (int j = 0; j < MNB; ++j) {
               tma_load_3d(sb + TC_A_HI + j * MNB_BYTES, &tm_a_hi, &full[stage], m0 + MNB_ELEMS * j, k0, seed);
@@ -412,7 +392,7 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
             tma_load_3d(sb + TC_B_HI, &tm_b_hi, &full[stage], k0, n0, seed);
             if (gs.split3) tma_load_3d(sb + TC_B_LO, &tm_b_lo, &full[stage], k0, n0, seed);
           }
-          if (++stage == nstages) { stage = 0; phase ^= 1u; }
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -437,7 +417,7 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
       if (single_acc) {
         int ab = 0;
         uint32_t ab_phase = 0;
-        for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
           uint64_t* e_bar = ab < 2 ? &main_empty[ab] : &corr_empty[ab - 2];
           uint64_t* f_bar = ab < 2 ? &main_full[ab] : &corr_full[ab - 2];
           mbar_wait(e_bar, ab_phase ^ 1u);
@@ -461,13 +441,13 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
               first = false;
             }
             umma_commit(&empty[stage]);
-            if (++stage == nstages) { stage = 0; phase ^= 1u; }
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
           }
           umma_commit(f_bar);
           if (++ab == 4) { ab = 0; ab_phase ^= 1u; }
         }
       } else
-      for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const uint32_t d_corr = tmem_base + 256 + cb * 128;
         if (gs.split3) {
           mbar_wait(&corr_empty[cb], cb_phase ^ 1u);
@@ -502,7 +482,7 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
             first_main = false;
           }
           umma_commit(&empty[stage]);  // smem slot free once these MMAs retire
-          if (++stage == nstages) { stage = 0; phase ^= 1u; }
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
           if ((kb + 1) % TC_PROMOTE == 0 || kb == kbn_ - 1) {
             umma_commit(&main_full[mb]);  // main partial ready for promotion
             if (++mb == 2) { mb = 0; mb_phase ^= 1u; }
@@ -522,7 +502,7 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
       const int ct = threadIdx.x - 6 * 32;
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int seed_, m0_, n0_, kb0_, kbn_;
         decode(tile, seed_, m0_, n0_, kb0_, kbn_);
         for (int kb = 0; kb < kbn_; ++kb) {
@@ -542,7 +522,7 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
           }
           fence_proxy_async_smem();
           mbar_arrive(&lo_full[stage]);
-          if (++stage == nstages) { stage = 0; phase ^= 1u; }
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -556,7 +536,7 @@ __global__ void __launch_bounds__((TcSplit<EPI, F16>::threads), 1)
     int mb = 0, cb = 0, ab = 0;
     uint32_t mb_phase = 0, cb_phase = 0, ab_phase = 0;
     const bool single_acc = !F16 && gs.split3 && gs.k_blocks <= TC_PROMOTE;  // see the MMA issuer
-    for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int seed, m0, n0, kb0, kbn;
       const int ks = decode(tile, seed, m0, n0, kb0, kbn);
       const int partials = (kbn + TC_PROMOTE - 1) / TC_PROMOTE;

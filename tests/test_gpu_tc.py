@@ -126,9 +126,10 @@ def test_tc_gemm16_small_gradients_with_prescale(a_mn, b_mn):
 
 
 @pytest.mark.parametrize("S,M,N", [(5, 4096, 1024), (3, 6536, 256), (160, 128, 384)])
-def test_tc_gemm16_a_stationary_mode(S, M, N):
-    """K = 128 (two k-blocks), K-major operands, several n-tiles and >= 148 (seed, m-tile) groups: the kernel keeps the
-    A tiles of a group resident and walks the n-tiles (the dense dgrad's shape); ragged M covers the row clipping."""
+def test_tc_gemm16_dgrad_shapes(S, M, N):
+    """K = 128 (two k-blocks), K-major operands, several n-tiles and more (seed, m-tile) groups than SMs -- the dense
+    dgrad's shape at full size; ragged M covers the row clipping.  (An A-stationary variant of the kernel for this shape
+    -- A tiles loaded once per group, two-stage ring -- measured no faster in round 2 and was dropped: DESIGN.md 3.2.)"""
     d, ref, *_ = _run16(S, M, N, 128, 0, 0, seed=S + N)
     assert np.isfinite(d).all()
     scale = np.abs(ref).max()
