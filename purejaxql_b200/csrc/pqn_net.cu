@@ -1504,13 +1504,16 @@ __global__ void __launch_bounds__(CONV16_WARPS * 32, CONV16_CTAS_PER_SM)
   const int row_stride = gridDim.x * CONV16_WARPS;
   // two-deep prefetch: the gather index of row + 2 strides and the packed observation of row + 1 stride are in flight
   // while this row is computed, so the index -> observation load chain never stalls the in-order issue
+  // unconditional loads from clamped addresses (rows past the end re-read the last row, lanes past the packed width
+  // re-read word 0; neither is ever used): a predicated load with a default value made ptxas copy the result into the
+  // loop-carried register ~125 instructions after the LDG, which stalled every warp on the load it had just issued
+  // (13 % of all stall samples of the forward kernel, ncu r2m)
   auto fetch_index = [&](int r) -> int {
-    if (r >= rows) return -1;
-    return gather ? __ldg(gather + (int64_t)seed * rows + r) : r;
+    const int rc = r < rows ? r : rows - 1;
+    return gather ? __ldg(gather + (int64_t)seed * rows + rc) : rc;
   };
   auto fetch_obs = [&](int src) -> uint32_t {
-    if (src < 0 || lane >= Cfg::PW) return 0u;
-    return __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + lane);
+    return __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + (lane < Cfg::PW ? lane : 0));
   };
   const int row0 = blockIdx.x * CONV16_WARPS + warp;
   uint32_t pre = fetch_obs(fetch_index(row0));
@@ -1950,13 +1953,16 @@ __global__ void __launch_bounds__(ConvBwd16<C>::WARPS * 32, 2)
   const int pos_g = g < 4 ? 2 * g : 2 * (g - 4) + 1;   // pair g of a k-step sits next to pair g + 4
 
   const int row_stride = gridDim.x * SM::WARPS;
+  // unconditional loads from clamped addresses (rows past the end re-read the last row, lanes past the packed width
+  // re-read word 0; neither is ever used): a predicated load with a default value made ptxas copy the result into the
+  // loop-carried register ~125 instructions after the LDG, which stalled every warp on the load it had just issued
+  // (13 % of all stall samples of the forward kernel, ncu r2m)
   auto fetch_index = [&](int r) -> int {
-    if (r >= rows) return -1;
-    return gather ? __ldg(gather + (int64_t)seed * rows + r) : r;
+    const int rc = r < rows ? r : rows - 1;
+    return gather ? __ldg(gather + (int64_t)seed * rows + rc) : rc;
   };
   auto fetch_obs = [&](int src) -> uint32_t {
-    if (src < 0 || lane >= Cfg::PW) return 0u;
-    return __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + lane);
+    return __ldg(obs + ((int64_t)seed * obs_rows_per_seed + src) * Cfg::PW + (lane < Cfg::PW ? lane : 0));
   };
   auto fetch_rows = [&](int r) {  // async copy of the sample's dy / xhat / rstd rows into this warp's slice
     if (r < rows) {
