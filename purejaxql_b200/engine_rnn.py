@@ -126,10 +126,14 @@ class PQNRnnEngine:
         eps_one = torch.ones(1, device=dev)
         eps_dev = torch.zeros(1, device=dev)
 
+        act_t = torch.empty((S, E), dtype=torch.int32, device=dev)
+        rew_t = torch.empty((S, E), device=dev)
+        done_t = torch.empty((S, E), dtype=torch.uint8, device=dev)
+
         def rollout(carry_key, n_steps, slot0, eps):
             """n_steps x _step_env / _random_step starting from the expl_state above; transitions go to memory slots
-            slot0..; returns the scan's final carry key (the reference re-binds `rng` to it)."""
-            nonlocal last_obs, new_obs
+            slot0..; returns the scan's final carry key (the reference re-binds `rng` to it).  Only static buffers are
+            touched, so the update's rollout can be replayed from a CUDA graph."""
             step_keys = torch.zeros((n_steps, S, 2, 2), dtype=torch.int32, device=dev)
             carry = carry_key.clone()
             _lib.check(L.pqn_rollout_keys(_lib.p(carry), _lib.p(step_keys), S, n_steps, mode, _lib.stream_ptr()),
@@ -139,13 +143,10 @@ class PQNRnnEngine:
                 mem.hs[:, s].copy_(hs); mem.obs[:, s].copy_(last_obs)
                 mem.last_done[:, s].copy_(last_done); mem.last_action[:, s].copy_(last_action)
                 self.step(params, hs, last_obs, last_done, last_action, q, S, E)
-                act_t = torch.empty((S, E), dtype=torch.int32, device=dev)
-                rew_t = torch.empty((S, E), device=dev)
-                done_t = torch.empty((S, E), dtype=torch.uint8, device=dev)
                 self._act_step(S, E, step_keys[t], q, eps, state, new_obs, act_t, rew_t, done_t, maxq, info_sums, 0,
                                self.rew_scale)
                 mem.action[:, s].copy_(act_t); mem.reward[:, s].copy_(rew_t); mem.done[:, s].copy_(done_t)
-                last_obs, new_obs = new_obs, last_obs
+                last_obs.copy_(new_obs)
                 last_done.copy_(done_t); last_action.copy_(act_t)
             return carry
 
@@ -161,19 +162,25 @@ class PQNRnnEngine:
         test_every = int(NU * c["TEST_INTERVAL"]) if self.test else None
         loss_sum, qsa_sum = torch.zeros(S, device=dev), torch.zeros(S, device=dev)
         ws = self._workspace(S, max(Tm * Bm, E))
+        perm_ws = jr.permutation_workspace(E, S, dev)
         timesteps = grad_steps = 0
         denom = float(self.epochs * self.nmb)
         on_update_end = getattr(self, "on_update_end", None)
-        for n_updates in range(NU):
+        # static buffers of the update step (graph capturable, like engine.PQNEngine)
+        rng_buf = rng.clone()
+        kT_buf = torch.zeros((S, 2), dtype=torch.int32, device=dev)
+        upd_idx = torch.zeros(1, dtype=torch.int64, device=dev)
+        m_cur = torch.zeros((S, 7), dtype=torch.float64, device=dev)
+
+        def update_body():
             # ================= SAMPLE PHASE (:190-236)
-            eps_dev.copy_(eps_table[n_updates:n_updates + 1])
-            k = jr.split(rng, 2, mode)                               # :222
+            eps_dev.copy_(eps_table.index_select(0, upd_idx))
+            k = jr.split(rng_buf, 2, mode)                           # :222
             info_sums.zero_()
             for name in ("hs", "obs", "action", "reward", "done", "last_done", "last_action"):   # :239-243 shift the memory
                 buf = getattr(mem, name)
                 buf[:, :W].copy_(buf[:, T:T + W].clone())
             rng = rollout(k[:, 1].contiguous(), T, W, eps_dev)       # rng := final carry of the scan (:223-228)
-            timesteps += T * E
             # ================= NETWORKS UPDATE (:246-386)
             loss_sum.zero_(); qsa_sum.zero_()
             k = jr.split(rng, 2, mode)                               # :381  (the scan carry starts at `rng`)
@@ -181,7 +188,7 @@ class PQNRnnEngine:
             for _ in range(self.epochs):
                 k = jr.split(r, 2, mode)                             # :368
                 r, kperm = k[:, 0].contiguous(), k[:, 1].contiguous()
-                perm = jr.permutation_indices(kperm, E, mode).to(torch.int64)          # permutation of the ENV axis
+                perm = jr.permutation_indices(kperm, E, mode, workspace=perm_ws).to(torch.int64)   # permutation of the ENV axis
                 r = jr.split(r, 2, mode)[:, 0].contiguous()          # :375
                 for mbi in range(self.nmb):
                     idx = perm[:, mbi * Bm:(mbi + 1) * Bm]                             # [S, Bm]
@@ -199,25 +206,58 @@ class PQNRnnEngine:
                     _lib.check(L.pqn_radam_clip_step(_lib.p(params), _lib.p(grads), _lib.p(mu), _lib.p(nu), _lib.p(sched),
                                                      _lib.p(step_counter), _lib.p(gnorm), S, P, float(c["MAX_GRAD_NORM"]),
                                                      0.9, 0.999, 1e-8, _lib.stream_ptr()), "pqn_radam_clip_step")
-                    grad_steps += 1
-            rng = r
+            if self.test:                                            # :398  rng, _rng = split(rng)
+                k = jr.split(r, 2, mode)
+                r = k[:, 0].contiguous()
+                kT_buf.copy_(k[:, 1])
+            rng_buf.copy_(r)
+            m_cur[:, 0] = loss_sum.double() / denom
+            m_cur[:, 1] = qsa_sum.double() / denom
+            m_cur[:, 2:7] = info_sums / float(T * E)
+            upd_idx.add_(1)
+
+        # CUDA graph: these runs are launch-bound (32 envs x 64 steps: thousands of small launches per update), so the
+        # update is captured after the first eager one and replayed unless CUDA_GRAPH is false
+        want_graph = c.get("CUDA_GRAPH", "auto")
+        use_graph = (True if want_graph == "auto" else bool(want_graph)) and NU > 2
+        graph = None
+        self.graph_captured = False
+        for n_updates in range(NU):
+            if graph is not None:
+                graph.replay()
+            else:
+                update_body()
+                if use_graph and n_updates == 0:
+                    try:
+                        torch.cuda.synchronize(dev)
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            update_body()
+                        graph = g
+                        self.graph_captured = True
+                    except Exception as e:                            # capture is an optimisation only
+                        import warnings
+                        warnings.warn(f"CUDA graph capture of the recurrent update failed ({e!r}); running eagerly")
+                        graph, use_graph = None, False
+                        torch.cuda.synchronize(dev)
+            timesteps += T * E
+            grad_steps += self.nmb * self.epochs
             col = n_updates
             metrics["env_step"][:, col] = timesteps
             metrics["update_steps"][:, col] = n_updates + 1
             metrics["grad_steps"][:, col] = grad_steps
-            metrics["td_loss"][:, col] = loss_sum.double() / denom
-            metrics["qvals"][:, col] = qsa_sum.double() / denom
+            metrics["td_loss"][:, col] = m_cur[:, 0]
+            metrics["qvals"][:, col] = m_cur[:, 1]
             for j, kk in enumerate(INFO_KEYS):
-                metrics[kk][:, col] = info_sums[:, j] / float(T * E)
+                metrics[kk][:, col] = m_cur[:, 2 + j]
             if on_update_end is not None:
-                on_update_end(n_updates, dict(mem=mem, params=params, rng=rng))
+                on_update_end(n_updates, dict(mem=mem, params=params, rng=rng_buf))
             if self.test:                                            # :398-408
-                k = jr.split(rng, 2, mode)
-                rng, kT = k[:, 0].contiguous(), k[:, 1].contiguous()
                 if test_every > 0 and (n_updates + 1) % test_every == 0:
-                    test_metrics = self.get_test_metrics(params, kT)
+                    test_metrics = self.get_test_metrics(params, kT_buf.clone())
                 for kk in INFO_KEYS:
                     test_hist[kk][:, col] = test_metrics[kk]
+        rng = rng_buf
         torch.cuda.synchronize(dev)
         out_metrics = {m: v[:, :NU].float() if m in ("td_loss", "qvals", *INFO_KEYS) else v[:, :NU].to(torch.int64)
                        for m, v in metrics.items()}

@@ -200,3 +200,25 @@ def test_rnn_cartpole_smoke_with_eval():
     assert m["td_loss"].shape == (2, 8) and torch.isfinite(m["td_loss"]).all()
     assert "test/returned_episode_returns" in m and "env_frame" not in m
     assert m["env_step"][0, -1].item() == 16384
+
+
+def test_rnn_cuda_graph_replay_equals_eager():
+    """The recurrent update is captured into a CUDA graph after the first eager update (these runs are launch-bound);
+    replayed updates must reproduce the eager run bit for bit (everything is deterministic)."""
+    from purejaxql_b200 import pqn_rnn_gymnax
+    outs = []
+    for graph in (False, True):
+        cfg = dict(ENV_NAME="CartPole-v1", NUM_ENVS=8, NUM_STEPS=12, MEMORY_WINDOW=3, NUM_MINIBATCHES=4, NUM_EPOCHS=2,
+                   EPS_START=1.0, EPS_FINISH=0.1, EPS_DECAY=0.5, LR=1e-4, MAX_GRAD_NORM=10, GAMMA=0.99, LAMBDA=0.95,
+                   NORM_TYPE="layer_norm", NORM_INPUT=False, HIDDEN_SIZE=128, NUM_LAYERS=2, LR_LINEAR_DECAY=True,
+                   REW_SCALE=0.1, WANDB_MODE="disabled", TEST_DURING_TRAINING=True, TEST_INTERVAL=0.4, TEST_NUM_ENVS=8,
+                   EPS_TEST=0.0, CUDA_GRAPH=graph)
+        cfg["TOTAL_TIMESTEPS"] = cfg["TOTAL_TIMESTEPS_DECAY"] = float(5 * cfg["NUM_STEPS"] * cfg["NUM_ENVS"])
+        train = pqn_rnn_gymnax.make_train(cfg)
+        out = train(jr.split(jr.PRNGKey(5), 2))
+        assert train.engine.graph_captured == graph
+        outs.append((out["runner_state"][0].params_flat.cpu().numpy(), out["metrics"]["td_loss"].cpu().numpy(),
+                     out["metrics"]["test/returned_episode_returns"].cpu().numpy(),
+                     out["runner_state"][4].cpu().numpy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b, equal_nan=True)
