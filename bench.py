@@ -452,6 +452,14 @@ def e2e_train(module, cfg, rngs_host, dev, world, shard=None):
     train2 = module.make_train(cfg)
     if shard is not None:
         train2.engine.env_shard = shard
+    marks = [torch.cuda.Event(enable_timing=True)]           # per-update GPU time of this run (diagnostic, no sync)
+    marks[0].record()
+
+    def _mark(n, dbg):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append(ev)
+    train2.engine.on_update_end = _mark
     t1 = time.perf_counter()
     out2 = train2(rngs_host)                                   # H2D of the keys happens inside; train() ends synchronised
     t2 = time.perf_counter()
@@ -460,6 +468,7 @@ def e2e_train(module, cfg, rngs_host, dev, world, shard=None):
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     E2E_PARTS.update(make_train_s=round(t1 - t0, 4), train_s=round(t2 - t1, 4), d2h_s=round(t0 + e2e_s - t2, 4))
+    E2E_PARTS["gpu_ms_init_then_per_update"] = [round(marks[i].elapsed_time(marks[i + 1]), 1) for i in range(len(marks) - 1)]
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
