@@ -445,6 +445,9 @@ E2E_PARTS = {}     # wall-clock split of the last e2e_train call (this rank)
 def e2e_train(module, cfg, rngs_host, dev, world, shard=None):
     import torch
     import torch.distributed as dist
+    import gc
+    gc.collect()                          # the previous engine's buffers go back to the caching allocator now, not
+    gc.disable()                          # in the middle of the timed call (a collection pause is host time)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -467,6 +470,7 @@ def e2e_train(module, cfg, rngs_host, dev, world, shard=None):
     params_host = out2["runner_state"][0].params_flat.cpu()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    gc.enable()
     E2E_PARTS.update(make_train_s=round(t1 - t0, 4), train_s=round(t2 - t1, 4), d2h_s=round(t0 + e2e_s - t2, 4))
     E2E_PARTS["gpu_ms_init_then_per_update"] = [round(marks[i].elapsed_time(marks[i + 1]), 1) for i in range(len(marks) - 1)]
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
