@@ -1550,6 +1550,7 @@ __global__ void __launch_bounds__(CONV16_WARPS * 32, CONV16_CTAS_PER_SM)
         ln16_quad(z, mean0, rstd0, mean1, rstd1);
         const float nm0 = -mean0 * rstd0, nm1 = -mean1 * rstd1;   // xhat = z * rstd - mean * rstd: one FFMA
         uint32_t rb0 = 0u, rb1 = 0u;
+        uint32_t wh[2][2], wl[2][2];   // packed (hi, lo') words [n-tile h][pixel row g / g+8] of the training variant
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int o = 8 * h + 2 * t;
@@ -1568,10 +1569,15 @@ __global__ void __launch_bounds__(CONV16_WARPS * 32, CONV16_CTAS_PER_SM)
             const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1v));
             const __half2 l0 = __floats2half2_rn((v0.x - f0.x) * tc::TC_LO_SCALE, (v0.y - f0.y) * tc::TC_LO_SCALE);
             const __half2 l1 = __floats2half2_rn((v1.x - f1.x) * tc::TC_LO_SCALE, (v1.y - f1.y) * tc::TC_LO_SCALE);
-            *reinterpret_cast<uint32_t*>(hrow16 + p0 * CONV_O + o) = h0;
-            *reinterpret_cast<__half2*>(lrow16 + p0 * CONV_O + o) = l0;
-            *reinterpret_cast<uint32_t*>(hrow16 + p1 * CONV_O + o) = h1v;
-            *reinterpret_cast<__half2*>(lrow16 + p1 * CONV_O + o) = l1;
+            if (TRAIN) {   // stored after the h loop, two lanes' pairs per 8-byte store
+              wh[h][0] = h0; wh[h][1] = h1v;
+              wl[h][0] = *reinterpret_cast<const uint32_t*>(&l0); wl[h][1] = *reinterpret_cast<const uint32_t*>(&l1);
+            } else {
+              *reinterpret_cast<uint32_t*>(hrow16 + p0 * CONV_O + o) = h0;
+              *reinterpret_cast<__half2*>(lrow16 + p0 * CONV_O + o) = l0;
+              *reinterpret_cast<uint32_t*>(hrow16 + p1 * CONV_O + o) = h1v;
+              *reinterpret_cast<__half2*>(lrow16 + p1 * CONV_O + o) = l1;
+            }
           } else {
             *reinterpret_cast<float2*>(hrow + p0 * CONV_O + o) = v0;
             *reinterpret_cast<float2*>(hrow + p1 * CONV_O + o) = v1;
@@ -1584,6 +1590,22 @@ __global__ void __launch_bounds__(CONV16_WARPS * 32, CONV16_CTAS_PER_SM)
             *reinterpret_cast<float2*>(xrow + p0 * CONV_O + o) = make_float2(x00, x01);
             *reinterpret_cast<float2*>(xrow + p1 * CONV_O + o) = make_float2(x10, x11);
             if (h == 0 && t == 0) { rrow[p0] = rstd0; rrow[p1] = rstd1; }
+          }
+        }
+        if (H16 && TRAIN) {
+          // Lanes t and t^1 hold adjacent channel pairs.  The even lane stores the four channels 4(t/2).. of the low
+          // n-tile (its own pair + the partner's), the odd lane those of the high n-tile: 16 eight-byte plane stores per
+          // m-block instead of 32 four-byte ones.  The kernel's time follows its store instructions (loads queue
+          // behind them): -11 % in the same-box A/B, while widening the xhat stores the same way spilled and lost.
+          const bool odd = t & 1;
+          const int q4 = 4 * (t >> 1) + (odd ? 8 : 0);
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp) {
+            const int px = 16 * mb + g + 8 * pp;
+            const uint32_t rh = __shfl_xor_sync(0xffffffffu, odd ? wh[0][pp] : wh[1][pp], 1);
+            const uint32_t rl = __shfl_xor_sync(0xffffffffu, odd ? wl[0][pp] : wl[1][pp], 1);
+            *reinterpret_cast<uint2*>(hrow16 + px * CONV_O + q4) = odd ? make_uint2(rh, wh[1][pp]) : make_uint2(wh[0][pp], rh);
+            *reinterpret_cast<uint2*>(lrow16 + px * CONV_O + q4) = odd ? make_uint2(rl, wl[1][pp]) : make_uint2(wl[0][pp], rl);
           }
         }
         if (TRAIN && brow) {
