@@ -1347,6 +1347,12 @@ struct Conv16 {
   static constexpr int ROW = 2 * KS < 8 ? 8 : 2 * KS;  // padded row: 8 or 12 words keep the 4-row LDS.64 groups apart
 };
 
+// Output channel of column n (0..7) of n-tile h.  NOT the natural 8h + n: with 4 (n / 2) + 2h + (n % 2) the accumulator
+// columns (2t, 2t+1) of the two n-tiles are the four CONSECUTIVE channels 4t .. 4t+3 of a pixel, so a thread stores 16
+// bytes of xhat / 8 bytes of each fp16 plane per pixel with one instruction and no lane exchange (the kernel's time
+// follows its store instructions: same-box A/B in profiles/r2_conv_fwd_sensitivity.json).
+__host__ __device__ constexpr int conv16_channel(int h, int n) { return 4 * (n >> 1) + 2 * h + (n & 1); }
+
 // tap of fragment column kk (0..15) of k-step s, see the k order above
 __host__ __device__ constexpr int conv16_tap(int s, int kk) {
   return 16 * s + (kk < 8 ? 0 : 8) + ((kk & 1) ? 4 : 0) + ((kk & 7) >> 1);
@@ -1362,7 +1368,7 @@ __device__ __forceinline__ void conv16_load_weights(const float* __restrict__ pr
   for (int i = threadIdx.x; i < M::KS * 2 * 32; i += blockDim.x) {
     const int ln = i & 31, h = (i >> 5) & 1, s = i >> 6;
     const int gg = ln >> 2, tt = ln & 3;
-    const int o = h * 8 + gg;
+    const int o = conv16_channel(h, gg);
     const float scale = __uint_as_float((uint32_t)(127 + 15 - (1 << tt)) << 23);   // 2^(15 - 2^t), exact
     float v[4];
 #pragma unroll
@@ -1426,8 +1432,8 @@ __device__ __forceinline__ void conv16_block2(const uint32_t* __restrict__ xp, c
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      z[i][h][0] = z[i][h][2] = cb[8 * h + 2 * t];
-      z[i][h][1] = z[i][h][3] = cb[8 * h + 2 * t + 1];
+      z[i][h][0] = z[i][h][2] = cb[4 * t + 2 * h];       // conv16_channel(h, 2t), (h, 2t + 1)
+      z[i][h][1] = z[i][h][3] = cb[4 * t + 2 * h + 1];
     }
   const uint32_t* r00 = xp + (32 * mbp + g) * M::ROW;
 #pragma unroll
@@ -1538,6 +1544,10 @@ __global__ void __launch_bounds__(CONV16_WARPS * 32, CONV16_CTAS_PER_SM)
     float* __restrict__ xrow = (TRAIN && XH1) ? XH1 + grow * FLAT_CNN : nullptr;
     float* __restrict__ rrow = (TRAIN && RS1) ? RS1 + grow * CONV_PIX : nullptr;
     uint16_t* __restrict__ brow = (TRAIN && RB) ? reinterpret_cast<uint16_t*>(RB + grow * (FLAT_CNN / 32)) : nullptr;
+    // rstd and the ReLU masks of m-block t are kept by lane t of every quad and stored once per sample (2 + 2 store
+    // instructions instead of 8 + 8 predicated ones)
+    float keep_rs0 = 0.f, keep_rs1 = 0.f;
+    uint32_t keep_rb = 0u;
 #pragma unroll 1
     for (int mbp = 0; mbp < 2; ++mbp) {
       float z2[2][2][4];
@@ -1550,70 +1560,64 @@ __global__ void __launch_bounds__(CONV16_WARPS * 32, CONV16_CTAS_PER_SM)
         ln16_quad(z, mean0, rstd0, mean1, rstd1);
         const float nm0 = -mean0 * rstd0, nm1 = -mean1 * rstd1;   // xhat = z * rstd - mean * rstd: one FFMA
         uint32_t rb0 = 0u, rb1 = 0u;
-        uint32_t wh[2][2], wl[2][2];   // packed (hi, lo') words [n-tile h][pixel row g / g+8] of the training variant
+        // the thread's channels of pixel rows p0 = 16 mb + g and p1 = p0 + 8: 4t .. 4t+3 (n-tile h -> 4t + 2h, + 1)
+        const int p0 = 16 * mb + g, p1 = p0 + 8, o4 = 4 * t;
+        float x0[4], x1[4], v0[4], v1[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int o = 8 * h + 2 * t;
-          const float x00 = fmaf(z[h][0], rstd0, nm0), x01 = fmaf(z[h][1], rstd0, nm0);
-          const float x10 = fmaf(z[h][2], rstd1, nm1), x11 = fmaf(z[h][3], rstd1, nm1);
-          float2 v0, v1;
-          v0.x = fmaxf(fmaf(x00, sc[o], bi[o]), 0.f);
-          v0.y = fmaxf(fmaf(x01, sc[o + 1], bi[o + 1]), 0.f);
-          v1.x = fmaxf(fmaf(x10, sc[o], bi[o]), 0.f);
-          v1.y = fmaxf(fmaf(x11, sc[o + 1], bi[o + 1]), 0.f);
-          const int p0 = 16 * mb + g, p1 = p0 + 8;
-          if (H16) {
-            // hi = fp16(h) (saturating: no inf), lo = fp16((h - hi) * 2^11)
-            const uint32_t h0 = cvt_f16x2_satfinite(v0.x, v0.y), h1v = cvt_f16x2_satfinite(v1.x, v1.y);
-            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
-            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1v));
-            const __half2 l0 = __floats2half2_rn((v0.x - f0.x) * tc::TC_LO_SCALE, (v0.y - f0.y) * tc::TC_LO_SCALE);
-            const __half2 l1 = __floats2half2_rn((v1.x - f1.x) * tc::TC_LO_SCALE, (v1.y - f1.y) * tc::TC_LO_SCALE);
-            if (TRAIN) {   // stored after the h loop, two lanes' pairs per 8-byte store
-              wh[h][0] = h0; wh[h][1] = h1v;
-              wl[h][0] = *reinterpret_cast<const uint32_t*>(&l0); wl[h][1] = *reinterpret_cast<const uint32_t*>(&l1);
-            } else {
-              *reinterpret_cast<uint32_t*>(hrow16 + p0 * CONV_O + o) = h0;
-              *reinterpret_cast<__half2*>(lrow16 + p0 * CONV_O + o) = l0;
-              *reinterpret_cast<uint32_t*>(hrow16 + p1 * CONV_O + o) = h1v;
-              *reinterpret_cast<__half2*>(lrow16 + p1 * CONV_O + o) = l1;
-            }
-          } else {
-            *reinterpret_cast<float2*>(hrow + p0 * CONV_O + o) = v0;
-            *reinterpret_cast<float2*>(hrow + p1 * CONV_O + o) = v1;
-          }
-          if (TRAIN) {
-            rb0 |= ((v0.x > 0.f ? 1u : 0u) | (v0.y > 0.f ? 2u : 0u)) << o;
-            rb1 |= ((v1.x > 0.f ? 1u : 0u) | (v1.y > 0.f ? 2u : 0u)) << o;
-          }
-          if (xrow) {
-            *reinterpret_cast<float2*>(xrow + p0 * CONV_O + o) = make_float2(x00, x01);
-            *reinterpret_cast<float2*>(xrow + p1 * CONV_O + o) = make_float2(x10, x11);
-            if (h == 0 && t == 0) { rrow[p0] = rstd0; rrow[p1] = rstd1; }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int o = o4 + 2 * h + c;
+            x0[2 * h + c] = fmaf(z[h][c], rstd0, nm0);
+            x1[2 * h + c] = fmaf(z[h][2 + c], rstd1, nm1);
+            v0[2 * h + c] = fmaxf(fmaf(x0[2 * h + c], sc[o], bi[o]), 0.f);
+            v1[2 * h + c] = fmaxf(fmaf(x1[2 * h + c], sc[o], bi[o]), 0.f);
           }
         }
-        if (H16 && TRAIN) {
-          // Lanes t and t^1 hold adjacent channel pairs.  The even lane stores the four channels 4(t/2).. of the low
-          // n-tile (its own pair + the partner's), the odd lane those of the high n-tile: 16 eight-byte plane stores per
-          // m-block instead of 32 four-byte ones.  The kernel's time follows its store instructions (loads queue
-          // behind them): -11 % in the same-box A/B, while widening the xhat stores the same way spilled and lost.
-          const bool odd = t & 1;
-          const int q4 = 4 * (t >> 1) + (odd ? 8 : 0);
+        if (H16) {
+          // hi = fp16(h) (saturating: no inf), lo = fp16((h - hi) * 2^11); 8-byte stores
+          uint32_t hw0[2], hw1[2], lw0[2], lw1[2];
 #pragma unroll
-          for (int pp = 0; pp < 2; ++pp) {
-            const int px = 16 * mb + g + 8 * pp;
-            const uint32_t rh = __shfl_xor_sync(0xffffffffu, odd ? wh[0][pp] : wh[1][pp], 1);
-            const uint32_t rl = __shfl_xor_sync(0xffffffffu, odd ? wl[0][pp] : wl[1][pp], 1);
-            *reinterpret_cast<uint2*>(hrow16 + px * CONV_O + q4) = odd ? make_uint2(rh, wh[1][pp]) : make_uint2(wh[0][pp], rh);
-            *reinterpret_cast<uint2*>(lrow16 + px * CONV_O + q4) = odd ? make_uint2(rl, wl[1][pp]) : make_uint2(wl[0][pp], rl);
+          for (int h = 0; h < 2; ++h) {
+            hw0[h] = cvt_f16x2_satfinite(v0[2 * h], v0[2 * h + 1]);
+            hw1[h] = cvt_f16x2_satfinite(v1[2 * h], v1[2 * h + 1]);
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&hw0[h]));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&hw1[h]));
+            const __half2 l0 = __floats2half2_rn((v0[2 * h] - f0.x) * tc::TC_LO_SCALE, (v0[2 * h + 1] - f0.y) * tc::TC_LO_SCALE);
+            const __half2 l1 = __floats2half2_rn((v1[2 * h] - f1.x) * tc::TC_LO_SCALE, (v1[2 * h + 1] - f1.y) * tc::TC_LO_SCALE);
+            lw0[h] = *reinterpret_cast<const uint32_t*>(&l0); lw1[h] = *reinterpret_cast<const uint32_t*>(&l1);
           }
+          *reinterpret_cast<uint2*>(hrow16 + p0 * CONV_O + o4) = make_uint2(hw0[0], hw0[1]);
+          *reinterpret_cast<uint2*>(lrow16 + p0 * CONV_O + o4) = make_uint2(lw0[0], lw0[1]);
+          *reinterpret_cast<uint2*>(hrow16 + p1 * CONV_O + o4) = make_uint2(hw1[0], hw1[1]);
+          *reinterpret_cast<uint2*>(lrow16 + p1 * CONV_O + o4) = make_uint2(lw1[0], lw1[1]);
+        } else {
+          *reinterpret_cast<float4*>(hrow + p0 * CONV_O + o4) = make_float4(v0[0], v0[1], v0[2], v0[3]);
+          *reinterpret_cast<float4*>(hrow + p1 * CONV_O + o4) = make_float4(v1[0], v1[1], v1[2], v1[3]);
+        }
+        if (TRAIN) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            rb0 |= (v0[c] > 0.f ? 1u : 0u) << (o4 + c);
+            rb1 |= (v1[c] > 0.f ? 1u : 0u) << (o4 + c);
+          }
+        }
+        if (xrow) {
+          *reinterpret_cast<float4*>(xrow + p0 * CONV_O + o4) = make_float4(x0[0], x0[1], x0[2], x0[3]);
+          *reinterpret_cast<float4*>(xrow + p1 * CONV_O + o4) = make_float4(x1[0], x1[1], x1[2], x1[3]);
+          if (t == mb) { keep_rs0 = rstd0; keep_rs1 = rstd1; }
         }
         if (TRAIN && brow) {
-          rb0 |= __shfl_xor_sync(0xffffffffu, rb0, 1); rb1 |= __shfl_xor_sync(0xffffffffu, rb1, 1);
-          rb0 |= __shfl_xor_sync(0xffffffffu, rb0, 2); rb1 |= __shfl_xor_sync(0xffffffffu, rb1, 2);
-          if (t == 0) { brow[16 * mb + g] = (uint16_t)rb0; brow[16 * mb + g + 8] = (uint16_t)rb1; }
+          uint32_t rb = rb0 | (rb1 << 16);      // both pixel rows in one register: two shuffles instead of four
+          rb |= __shfl_xor_sync(0xffffffffu, rb, 1);
+          rb |= __shfl_xor_sync(0xffffffffu, rb, 2);
+          if (t == mb) keep_rb = rb;
         }
       }
+    }
+    if (TRAIN) {
+      if (rrow) { rrow[16 * t + g] = keep_rs0; rrow[16 * t + g + 8] = keep_rs1; }
+      if (brow) { brow[16 * t + g] = (uint16_t)keep_rb; brow[16 * t + g + 8] = (uint16_t)(keep_rb >> 16); }
     }
   }
   if (TRAIN && bn_sums != nullptr) {
