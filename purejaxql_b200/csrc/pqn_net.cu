@@ -2057,7 +2057,9 @@ __global__ void __launch_bounds__(ConvBwd16<C>::WARPS * 32, 2)
         const float2 a1 = *reinterpret_cast<const float2*>(my_xh + cswz16(p1, 8 * h + 2 * t));
         z[h][0] = a0.x; z[h][1] = a0.y; z[h][2] = a1.x; z[h][3] = a1.y;
       }
-      const float rstd0 = my_rs[p0], rstd1 = my_rs[p1];
+      // rstd * gs: dz comes out pre-scaled for the fp16 planes (gs is a power of two; the conv-bias sum is unscaled at
+      // the end), which saves a multiplication per element
+      const float rstd0 = my_rs[p0] * gs, rstd1 = my_rs[p1] * gs;
       float dxh[2][4];
       float m1a = 0.f, m2a = 0.f, m1b = 0.f, m2b = 0.f;
 #pragma unroll
@@ -2092,7 +2094,7 @@ __global__ void __launch_bounds__(ConvBwd16<C>::WARPS * 32, 2)
         // B words: (pixel p0, pixel p1) of channel o (j = 0, 2) and of channel o + 1 (j = 1, 3); k-step mb, pair g
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const float v0 = dzv[c] * gs, v1 = dzv[2 + c] * gs;
+          const float v0 = dzv[c], v1 = dzv[2 + c];
           const uint32_t hw = cvt_f16x2_satfinite(v0, v1);
           const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw));
           const __half2 lw = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
@@ -2146,7 +2148,8 @@ __global__ void __launch_bounds__(ConvBwd16<C>::WARPS * 32, 2)
   cp_async_wait_all();
   // ---- reduce and publish (deterministic), as in conv_bwd_mma_kernel; the A coding 2^(2^(g%4) - 15) of this thread's
   // accumulator rows and the dz scale gs are undone here (exact powers of two)
-  const float unscale = __uint_as_float((uint32_t)(127 + 15 - (1 << (g & 3))) << 23) / gs;
+  const float inv_gs = 1.0f / gs;
+  const float unscale = __uint_as_float((uint32_t)(127 + 15 - (1 << (g & 3))) << 23) * inv_gs;
   __syncthreads();  // all warps are done with their slices
   for (int w = 0; w < SM::WARPS; ++w) {
     if (warp == w) {
@@ -2181,7 +2184,7 @@ __global__ void __launch_bounds__(ConvBwd16<C>::WARPS * 32, 2)
         const int o = 8 * (col >> 1) + 2 * t + (col & 1);
         s_red[o] = (w == 0 ? 0.f : s_red[o]) + a_dsc[col];
         s_red[CONV_O + o] = (w == 0 ? 0.f : s_red[CONV_O + o]) + a_dbi[col];
-        s_red[2 * CONV_O + o] = (w == 0 ? 0.f : s_red[2 * CONV_O + o]) + a_dcb[col];
+        s_red[2 * CONV_O + o] = (w == 0 ? 0.f : s_red[2 * CONV_O + o]) + a_dcb[col] * inv_gs;
       }
     }
     __syncthreads();
